@@ -1,0 +1,304 @@
+// oracle/cl_host_runtime.cpp -- TEST INFRASTRUCTURE, not product code.
+//
+// A synchronous, host-memory implementation of the 28 OpenCL entry points of
+// include/CL/cl.h.  Linked with ref_kernels_gpu.cpp / ref_kernels_cpu.cpp (the reference's
+// own .cl kernels compiled for the CPU) it forms oracle/_ref/libOpenCL.so.1: the UNMODIFIED
+// reference host (src/vp8enc.cpp + src/entropy_host.cpp) linked against it is the
+// reference encoder running entirely on the CPU.
+//
+// Semantics fixed here: every enqueued command executes immediately, in
+// program order -- a legal schedule of the host's in-order queues and what a
+// single-threaded CPU OpenCL device would do.  Work-items of one NDRange run on OpenMP
+// threads; the reference's kernels never communicate between work-items (their __local
+// arrays are indexed by the work-item's own local id only), so that is exact.
+#include <CL/cl.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "clc_compat.hpp"
+
+namespace clc {
+thread_local work_item_state g_wi;
+}
+
+extern "C" const clc::kernel_desc vp8ref_gpu_kernels[];
+extern "C" const clc::kernel_desc vp8ref_cpu_kernels[];
+
+struct _cl_platform_id { int dummy; };
+struct _cl_device_id { cl_device_type type; const char *name; };
+struct _cl_context { cl_device_id dev; };
+struct _cl_command_queue { cl_context ctx; };
+struct _cl_mem {
+    bool is_image;
+    size_t size;
+    unsigned char *data;
+    clc::image2d img;
+};
+struct _cl_program { bool is_gpu_program; };
+struct _cl_kernel {
+    const clc::kernel_desc *desc;
+    unsigned char bytes[24][16];
+    size_t sizes[24];
+};
+
+static _cl_platform_id g_platform;
+static _cl_device_id g_cpu_dev = {CL_DEVICE_TYPE_CPU, "vp8oclenc reference kernels on host CPU (cpu device)"};
+static _cl_device_id g_gpu_dev = {CL_DEVICE_TYPE_GPU, "vp8oclenc reference kernels on host CPU (gpu device)"};
+
+static cl_int put_info(const void *src, size_t n, size_t cap, void *dst, size_t *ret) {
+    if (ret) *ret = n;
+    if (dst) {
+        if (cap < n) return CL_INVALID_VALUE;
+        memcpy(dst, src, n);
+    }
+    return CL_SUCCESS;
+}
+
+extern "C" {
+
+cl_int clGetPlatformIDs(cl_uint num_entries, cl_platform_id *platforms, cl_uint *num_platforms) {
+    if (num_platforms) *num_platforms = 1;
+    if (platforms && num_entries >= 1) platforms[0] = &g_platform;
+    return CL_SUCCESS;
+}
+
+cl_int clGetPlatformInfo(cl_platform_id, cl_platform_info, size_t cap, void *dst, size_t *ret) {
+    static const char name[] = "vp8oclenc reference-on-CPU platform (oracle/_ref)";
+    return put_info(name, sizeof(name), cap, dst, ret);
+}
+
+cl_int clGetDeviceIDs(cl_platform_id, cl_device_type type, cl_uint num_entries, cl_device_id *devices,
+                      cl_uint *num_devices) {
+    cl_device_id found[2];
+    cl_uint n = 0;
+    if (type & CL_DEVICE_TYPE_CPU) found[n++] = &g_cpu_dev;
+    if (type & CL_DEVICE_TYPE_GPU) found[n++] = &g_gpu_dev;
+    if (num_devices) *num_devices = n;
+    if (n == 0) return CL_DEVICE_NOT_FOUND;
+    for (cl_uint i = 0; devices && i < n && i < num_entries; ++i) devices[i] = found[i];
+    return CL_SUCCESS;
+}
+
+cl_int clGetDeviceInfo(cl_device_id dev, cl_device_info what, size_t cap, void *dst, size_t *ret) {
+    switch (what) {
+        case CL_DEVICE_NAME: return put_info(dev->name, strlen(dev->name) + 1, cap, dst, ret);
+        case CL_DEVICE_VERSION: return put_info("OpenCL 1.1 subset", 18, cap, dst, ret);
+        case CL_DRIVER_VERSION: return put_info("oracle/_ref", 12, cap, dst, ret);
+        case CL_DEVICE_OPENCL_C_VERSION: return put_info("OpenCL C 1.0 (g++)", 19, cap, dst, ret);
+        case CL_DEVICE_MAX_COMPUTE_UNITS: { cl_uint v = 1; return put_info(&v, sizeof(v), cap, dst, ret); }
+        case CL_DEVICE_MAX_WORK_GROUP_SIZE: { size_t v = 256; return put_info(&v, cap < sizeof(v) ? cap : sizeof(v), cap, dst, ret); }
+        case CL_DEVICE_TYPE: return put_info(&dev->type, sizeof(dev->type), cap, dst, ret);
+        default: return CL_INVALID_VALUE;
+    }
+}
+
+cl_context clCreateContext(const cl_context_properties *, cl_uint n, const cl_device_id *devs,
+                           void (*)(const char *, const void *, size_t, void *), void *, cl_int *err) {
+    if (err) *err = (n >= 1 && devs) ? CL_SUCCESS : CL_INVALID_VALUE;
+    if (n < 1 || !devs) return nullptr;
+    return new _cl_context{devs[0]};
+}
+cl_int clReleaseContext(cl_context c) { delete c; return CL_SUCCESS; }
+
+cl_command_queue clCreateCommandQueue(cl_context ctx, cl_device_id, cl_command_queue_properties, cl_int *err) {
+    if (err) *err = CL_SUCCESS;
+    return new _cl_command_queue{ctx};
+}
+cl_int clReleaseCommandQueue(cl_command_queue q) { delete q; return CL_SUCCESS; }
+
+cl_mem clCreateBuffer(cl_context, cl_mem_flags, size_t size, void *host_ptr, cl_int *err) {
+    _cl_mem *m = new _cl_mem();
+    m->is_image = false;
+    m->size = size;
+    m->data = (unsigned char *)calloc(size ? size : 1, 1);
+    if (host_ptr && m->data) memcpy(m->data, host_ptr, size);
+    if (err) *err = m->data ? CL_SUCCESS : CL_MEM_OBJECT_ALLOCATION_FAILURE;
+    return m;
+}
+
+cl_mem clCreateImage2D(cl_context, cl_mem_flags, const cl_image_format *fmt, size_t w, size_t h, size_t,
+                       void *, cl_int *err) {
+    if (!fmt || fmt->image_channel_order != CL_R || fmt->image_channel_data_type != CL_UNSIGNED_INT8) {
+        if (err) *err = CL_INVALID_IMAGE_FORMAT_DESCRIPTOR;
+        return nullptr;
+    }
+    _cl_mem *m = new _cl_mem();
+    m->is_image = true;
+    m->size = w * h;
+    m->data = (unsigned char *)calloc(m->size ? m->size : 1, 1);
+    m->img.data = m->data;
+    m->img.width = (int)w;
+    m->img.height = (int)h;
+    if (err) *err = CL_SUCCESS;
+    return m;
+}
+
+cl_int clReleaseMemObject(cl_mem m) {
+    if (!m) return CL_INVALID_MEM_OBJECT;
+    free(m->data);
+    delete m;
+    return CL_SUCCESS;
+}
+
+cl_program clCreateProgramWithSource(cl_context, cl_uint count, const char **strings, const size_t *, cl_int *err) {
+    bool gpu = false;
+    for (cl_uint i = 0; i < count; ++i)
+        if (strings[i] && strstr(strings[i], "luma_search_1step")) gpu = true;
+    if (err) *err = CL_SUCCESS;
+    return new _cl_program{gpu};
+}
+cl_int clBuildProgram(cl_program, cl_uint, const cl_device_id *, const char *, void (*)(cl_program, void *), void *) {
+    return CL_SUCCESS;
+}
+cl_int clGetProgramBuildInfo(cl_program, cl_device_id, cl_program_build_info, size_t cap, void *dst, size_t *ret) {
+    return put_info("", 1, cap, dst, ret);
+}
+cl_int clReleaseProgram(cl_program p) { delete p; return CL_SUCCESS; }
+
+cl_kernel clCreateKernel(cl_program prog, const char *name, cl_int *err) {
+    const clc::kernel_desc *tab = prog->is_gpu_program ? vp8ref_gpu_kernels : vp8ref_cpu_kernels;
+    for (; tab->name; ++tab)
+        if (!strcmp(tab->name, name)) {
+            _cl_kernel *k = new _cl_kernel();
+            memset(k, 0, sizeof(*k));
+            k->desc = tab;
+            if (err) *err = CL_SUCCESS;
+            return k;
+        }
+    if (err) *err = CL_INVALID_KERNEL_NAME;
+    return nullptr;
+}
+cl_int clReleaseKernel(cl_kernel k) { delete k; return CL_SUCCESS; }
+
+cl_int clSetKernelArg(cl_kernel k, cl_uint idx, size_t size, const void *value) {
+    if (!k) return CL_INVALID_KERNEL;
+    if ((int)idx >= k->desc->nargs) return CL_INVALID_ARG_INDEX;
+    if (size > 16) return CL_INVALID_ARG_SIZE;
+    memset(k->bytes[idx], 0, 16);
+    if (value) memcpy(k->bytes[idx], value, size);
+    k->sizes[idx] = size;
+    return CL_SUCCESS;
+}
+
+cl_int clEnqueueNDRangeKernel(cl_command_queue, cl_kernel k, cl_uint dim, const size_t *, const size_t *gsz,
+                              const size_t *lsz, cl_uint, const cl_event *, cl_event *) {
+    if (!k) return CL_INVALID_KERNEL;
+    if (dim != 1) return CL_INVALID_WORK_DIMENSION;
+    const int n = k->desc->nargs;
+    void *resolved[24];
+    void *argv[24];
+    for (int i = 0; i < n; ++i) {
+        if (k->desc->is_pointer[i]) {
+            cl_mem m;
+            memcpy(&m, k->bytes[i], sizeof(m));
+            resolved[i] = !m ? nullptr : (m->is_image ? (void *)&m->img : (void *)m->data);
+            argv[i] = &resolved[i];
+        } else {
+            argv[i] = k->bytes[i];
+        }
+    }
+    const long long global = (long long)gsz[0];
+    const long long local = lsz ? (long long)lsz[0] : 1;
+    const clc::kernel_desc *d = k->desc;
+#pragma omp parallel for schedule(dynamic, 1) if (global >= 64)
+    for (long long g0 = 0; g0 < global; g0 += 64) {
+        const long long g1 = g0 + 64 < global ? g0 + 64 : global;
+        for (long long g = g0; g < g1; ++g) {
+            clc::g_wi.global_id = (size_t)g;
+            clc::g_wi.global_size = (size_t)global;
+            clc::g_wi.local_size = (size_t)local;
+            clc::g_wi.local_id = (size_t)(g % local);
+            clc::g_wi.group_id = (size_t)(g / local);
+            d->invoke(argv);
+        }
+    }
+    return CL_SUCCESS;
+}
+
+cl_int clEnqueueReadBuffer(cl_command_queue, cl_mem m, cl_bool, size_t off, size_t size, void *ptr, cl_uint,
+                           const cl_event *, cl_event *) {
+    if (!m || off + size > m->size) return CL_INVALID_VALUE;
+    memcpy(ptr, m->data + off, size);
+    return CL_SUCCESS;
+}
+cl_int clEnqueueWriteBuffer(cl_command_queue, cl_mem m, cl_bool, size_t off, size_t size, const void *ptr, cl_uint,
+                            const cl_event *, cl_event *) {
+    if (!m || off + size > m->size) return CL_INVALID_VALUE;
+    memcpy(m->data + off, ptr, size);
+    return CL_SUCCESS;
+}
+cl_int clEnqueueCopyBuffer(cl_command_queue, cl_mem s, cl_mem d, size_t so, size_t dof, size_t size, cl_uint,
+                           const cl_event *, cl_event *) {
+    if (!s || !d || so + size > s->size || dof + size > d->size) return CL_INVALID_VALUE;
+    memmove(d->data + dof, s->data + so, size);
+    return CL_SUCCESS;
+}
+cl_int clEnqueueWriteImage(cl_command_queue, cl_mem img, cl_bool, const size_t *origin, const size_t *region,
+                           size_t row_pitch, size_t, const void *ptr, cl_uint, const cl_event *, cl_event *) {
+    if (!img || !img->is_image) return CL_INVALID_MEM_OBJECT;
+    const size_t pitch = row_pitch ? row_pitch : region[0];
+    for (size_t y = 0; y < region[1]; ++y)
+        memcpy(img->data + (origin[1] + y) * img->img.width + origin[0], (const unsigned char *)ptr + y * pitch,
+               region[0]);
+    return CL_SUCCESS;
+}
+cl_int clEnqueueCopyImage(cl_command_queue, cl_mem s, cl_mem d, const size_t *so, const size_t *dor,
+                          const size_t *region, cl_uint, const cl_event *, cl_event *) {
+    if (!s || !d || !s->is_image || !d->is_image) return CL_INVALID_MEM_OBJECT;
+    for (size_t y = 0; y < region[1]; ++y)
+        memmove(d->data + (dor[1] + y) * d->img.width + dor[0], s->data + (so[1] + y) * s->img.width + so[0],
+                region[0]);
+    return CL_SUCCESS;
+}
+void *clEnqueueMapBuffer(cl_command_queue, cl_mem m, cl_bool, cl_map_flags, size_t off, size_t size, cl_uint,
+                         const cl_event *, cl_event *, cl_int *err) {
+    if (!m || off + size > m->size) {
+        if (err) *err = CL_INVALID_VALUE;
+        return nullptr;
+    }
+    if (err) *err = CL_SUCCESS;
+    return m->data + off;
+}
+cl_int clEnqueueUnmapMemObject(cl_command_queue, cl_mem, void *, cl_uint, const cl_event *, cl_event *) {
+    return CL_SUCCESS;
+}
+cl_int clFlush(cl_command_queue) { return CL_SUCCESS; }
+cl_int clFinish(cl_command_queue) { return CL_SUCCESS; }
+
+// ---- test hook: run one reference kernel by name on raw host pointers ----------------
+// argv[i] points at the argument value: for pointer parameters a void* holding the host
+// address (for image parameters: the address of a {data,width,height} clc::image2d).
+int vp8ref_run_kernel(const char *name, long long global, long long local, void *const *argv) {
+    const clc::kernel_desc *tabs[2] = {vp8ref_gpu_kernels, vp8ref_cpu_kernels};
+    for (int t = 0; t < 2; ++t)
+        for (const clc::kernel_desc *d = tabs[t]; d->name; ++d)
+            if (!strcmp(d->name, name)) {
+                if (local < 1) local = 1;
+#pragma omp parallel for schedule(dynamic, 1) if (global >= 64)
+                for (long long g0 = 0; g0 < global; g0 += 64) {
+                    const long long g1 = g0 + 64 < global ? g0 + 64 : global;
+                    for (long long g = g0; g < g1; ++g) {
+                        clc::g_wi.global_id = (size_t)g;
+                        clc::g_wi.global_size = (size_t)global;
+                        clc::g_wi.local_size = (size_t)local;
+                        clc::g_wi.local_id = (size_t)(g % local);
+                        clc::g_wi.group_id = (size_t)(g / local);
+                        d->invoke(argv);
+                    }
+                }
+                return 0;
+            }
+    return -1;
+}
+int vp8ref_kernel_nargs(const char *name) {
+    const clc::kernel_desc *tabs[2] = {vp8ref_gpu_kernels, vp8ref_cpu_kernels};
+    for (int t = 0; t < 2; ++t)
+        for (const clc::kernel_desc *d = tabs[t]; d->name; ++d)
+            if (!strcmp(d->name, name)) return d->nargs;
+    return -1;
+}
+
+}  // extern "C"
