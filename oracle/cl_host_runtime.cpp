@@ -24,6 +24,28 @@ namespace clc {
 thread_local work_item_state g_wi;
 }
 
+// ---- optional trace (VP8CL_TRACE=<file>): every create / write / read / image write is
+// appended as {u32 kind, u32 mem index, u64 offset, u64 size, payload}.  Tests use it to
+// replay the real host's per-frame inputs through other implementations and to compare
+// what the host read back.  kind: 0 create buffer, 1 create image, 2 write, 3 read, 4 image write
+static FILE *g_trace = nullptr;
+static unsigned g_next_mem_index = 0;
+static void trace_rec(unsigned kind, unsigned idx, size_t off, size_t size, const void *payload) {
+    if (!g_trace) return;
+    unsigned long long hdr[2] = {(unsigned long long)off, (unsigned long long)size};
+    fwrite(&kind, 4, 1, g_trace);
+    fwrite(&idx, 4, 1, g_trace);
+    fwrite(hdr, 8, 2, g_trace);
+    if (payload) fwrite(payload, 1, size, g_trace);
+}
+static void trace_init() {
+    static bool done = false;
+    if (done) return;
+    done = true;
+    const char *p = getenv("VP8CL_TRACE");
+    if (p && *p) g_trace = fopen(p, "wb");
+}
+
 extern "C" const clc::kernel_desc vp8ref_gpu_kernels[];
 extern "C" const clc::kernel_desc vp8ref_cpu_kernels[];
 
@@ -32,6 +54,7 @@ struct _cl_device_id { cl_device_type type; const char *name; };
 struct _cl_context { cl_device_id dev; };
 struct _cl_command_queue { cl_context ctx; };
 struct _cl_mem {
+    unsigned index;
     bool is_image;
     size_t size;
     unsigned char *data;
@@ -110,9 +133,12 @@ cl_command_queue clCreateCommandQueue(cl_context ctx, cl_device_id, cl_command_q
 cl_int clReleaseCommandQueue(cl_command_queue q) { delete q; return CL_SUCCESS; }
 
 cl_mem clCreateBuffer(cl_context, cl_mem_flags, size_t size, void *host_ptr, cl_int *err) {
+    trace_init();
     _cl_mem *m = new _cl_mem();
+    m->index = g_next_mem_index++;
     m->is_image = false;
     m->size = size;
+    trace_rec(0, m->index, 0, size, nullptr);
     m->data = (unsigned char *)calloc(size ? size : 1, 1);
     if (host_ptr && m->data) memcpy(m->data, host_ptr, size);
     if (err) *err = m->data ? CL_SUCCESS : CL_MEM_OBJECT_ALLOCATION_FAILURE;
@@ -125,9 +151,12 @@ cl_mem clCreateImage2D(cl_context, cl_mem_flags, const cl_image_format *fmt, siz
         if (err) *err = CL_INVALID_IMAGE_FORMAT_DESCRIPTOR;
         return nullptr;
     }
+    trace_init();
     _cl_mem *m = new _cl_mem();
+    m->index = g_next_mem_index++;
     m->is_image = true;
     m->size = w * h;
+    trace_rec(1, m->index, w, h, nullptr);
     m->data = (unsigned char *)calloc(m->size ? m->size : 1, 1);
     m->img.data = m->data;
     m->img.width = (int)w;
@@ -222,12 +251,14 @@ cl_int clEnqueueReadBuffer(cl_command_queue, cl_mem m, cl_bool, size_t off, size
                            const cl_event *, cl_event *) {
     if (!m || off + size > m->size) return CL_INVALID_VALUE;
     memcpy(ptr, m->data + off, size);
+    trace_rec(3, m->index, off, size, ptr);
     return CL_SUCCESS;
 }
 cl_int clEnqueueWriteBuffer(cl_command_queue, cl_mem m, cl_bool, size_t off, size_t size, const void *ptr, cl_uint,
                             const cl_event *, cl_event *) {
     if (!m || off + size > m->size) return CL_INVALID_VALUE;
     memcpy(m->data + off, ptr, size);
+    trace_rec(2, m->index, off, size, ptr);
     return CL_SUCCESS;
 }
 cl_int clEnqueueCopyBuffer(cl_command_queue, cl_mem s, cl_mem d, size_t so, size_t dof, size_t size, cl_uint,
@@ -243,6 +274,7 @@ cl_int clEnqueueWriteImage(cl_command_queue, cl_mem img, cl_bool, const size_t *
     for (size_t y = 0; y < region[1]; ++y)
         memcpy(img->data + (origin[1] + y) * img->img.width + origin[0], (const unsigned char *)ptr + y * pitch,
                region[0]);
+    if (!row_pitch || row_pitch == region[0]) trace_rec(4, img->index, 0, region[0] * region[1], ptr);
     return CL_SUCCESS;
 }
 cl_int clEnqueueCopyImage(cl_command_queue, cl_mem s, cl_mem d, const size_t *so, const size_t *dor,
@@ -262,11 +294,15 @@ void *clEnqueueMapBuffer(cl_command_queue, cl_mem m, cl_bool, cl_map_flags, size
     if (err) *err = CL_SUCCESS;
     return m->data + off;
 }
-cl_int clEnqueueUnmapMemObject(cl_command_queue, cl_mem, void *, cl_uint, const cl_event *, cl_event *) {
+cl_int clEnqueueUnmapMemObject(cl_command_queue, cl_mem m, void *, cl_uint, const cl_event *, cl_event *) {
+    if (m) trace_rec(5, m->index, 0, m->size, m->data); /* kind 5: contents handed back by the host */
     return CL_SUCCESS;
 }
 cl_int clFlush(cl_command_queue) { return CL_SUCCESS; }
-cl_int clFinish(cl_command_queue) { return CL_SUCCESS; }
+cl_int clFinish(cl_command_queue) {
+    if (g_trace) fflush(g_trace);
+    return CL_SUCCESS;
+}
 
 // ---- test hook: run one reference kernel by name on raw host pointers ----------------
 // argv[i] points at the argument value: for pointer parameters a void* holding the host

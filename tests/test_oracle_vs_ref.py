@@ -1,0 +1,338 @@
+"""Pins oracle/vp8_oracle.c (our plain-C restatement) against the REFERENCE's own kernels.
+
+oracle/_ref/libOpenCL.so.1 is /root/reference/src/{GPU,CPU}_kernels.cl compiled for the host
+CPU (oracle/Makefile).  Every test runs one reference __kernel and the corresponding oracle
+function on the same seeded input and demands identical bytes (floats included: both sides
+define mad() as fmaf and round after every other operation).  The module is skipped where the
+reference build is not available (it travels to the GPU box as a prebuilt .so).
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+from _libs import Image, P, make_segment_data, oracle, ref, ref_run
+
+pytestmark = pytest.mark.skipif(ref() is None, reason="oracle/_ref not built (needs /root/reference)")
+
+
+def rng(seed):
+    return np.random.default_rng(seed)
+
+
+def textured(r, h, w, smooth=4):
+    """noise with some spatial correlation so that searches have real minima"""
+    a = r.integers(0, 256, size=(h // smooth + 2, w // smooth + 2)).astype(np.float64)
+    a = np.kron(a, np.ones((smooth, smooth)))[:h, :w]
+    a = a + r.integers(-12, 13, size=(h, w))
+    return np.clip(a, 0, 255).astype(np.uint8)
+
+
+# ------------------------------------------------------------------------------------------
+def test_weight_matches_reference_and_keeps_the_clobber_bug():
+    o, rf = oracle(), ref()
+    r = rng(1)
+    res = r.integers(-255, 256, size=(3000, 16)).astype(np.int32)
+    res[0] = 0
+    res[1] = 255
+    res[2] = -255
+    res[3] = np.tile([255, -255], 8)
+    diff_from_fixed = 0
+    for row in res:
+        arr = (ctypes.c_int * 16)(*row.tolist())
+        a = o.vp8o_weight(arr)
+        b = rf.vp8ref_weight_opt(arr)
+        assert a == b
+        # the "fixed" transform (b1 kept, c1 from rows 1-2) -- what bin/GPU_kernels.cl computes;
+        # Q1 demands that we do NOT match it
+        m = row.reshape(4, 4).astype(np.int64)
+        a1 = (m[0] + m[3]) << 3
+        b1 = (m[1] + m[2]) << 3
+        c1 = (m[1] - m[2]) << 3
+        d1 = (m[0] - m[3]) << 3
+        t = np.stack([a1 + b1, (c1 * 2217 + d1 * 5352 + 14500) >> 12, a1 - b1, (d1 * 2217 - c1 * 5352 + 7500) >> 12])
+        a2 = t[:, 0] + t[:, 3]
+        b2 = t[:, 1] + t[:, 2]
+        c2 = t[:, 1] - t[:, 2]
+        d2 = t[:, 0] - t[:, 3]
+        f = np.stack([(a2 + b2 + 7) >> 4, ((c2 * 2217 + d2 * 5352 + 12000) >> 16) + (d2 != 0), (a2 - b2 + 7) >> 4,
+                      (d2 * 2217 - c2 * 5352 + 51000) >> 16], axis=1)
+        fixed = int(abs(f[0, 0]) // 4 + np.abs(f).sum() - abs(f[0, 0]))
+        diff_from_fixed += fixed != a
+    assert diff_from_fixed > 1000  # the quirk is observable on almost every block
+
+
+@pytest.mark.parametrize("w,h", [(32, 16), (352, 288), (120, 68)])
+def test_downsample(w, h):
+    o = oracle()
+    src = rng(2).integers(0, 256, size=(h, w)).astype(np.uint8)
+    a = np.zeros((h // 2, w // 2), np.uint8)
+    b = np.zeros_like(a)
+    o.vp8o_downsample_x2(P(src), P(a), w, h)
+    ref_run("downsample_x2", w * h // 4, 0, [src, b, w, h])
+    assert np.array_equal(a, b)
+
+
+def _search_case(seed, w, h, rate, big_vectors=False):
+    """returns cur, prev (inside a guard band, the reference reads out of bounds for forbidden
+    candidates), src_net, net_width"""
+    r = rng(seed)
+    guard = 80
+    canvas = textured(r, h + 2 * guard, w + 16)
+    prev_full = canvas.copy().reshape(-1)
+    prev = canvas[guard:guard + h, :w]
+    # current = previous moved by a small global shift + noise, rows packed tightly
+    sx, sy = int(r.integers(-3, 4)), int(r.integers(-3, 4))
+    cur = np.roll(canvas, (sy, sx), axis=(0, 1))[guard:guard + h, :w].astype(np.int32) + r.integers(-6, 7, size=(h, w))
+    cur = np.ascontiguousarray(np.clip(cur, 0, 255).astype(np.uint8))
+    # the reference wants tightly packed planes: build a packed copy with guard rows around it
+    packed = np.zeros((h + 2 * guard) * w + 64, np.uint8)
+    packed[:] = r.integers(0, 256, size=packed.size)
+    packed[guard * w:guard * w + h * w] = np.ascontiguousarray(prev).reshape(-1)
+    net_width = max(2, ((w * rate) // 16) * 2)
+    net_h = max(2, ((h * rate) // 16) * 2) + 2
+    lim = 6 if not big_vectors else 40
+    src_net = (r.integers(-lim, lim + 1, size=(net_h * net_width, 2)) * rate).astype(np.int16)
+    return cur, packed, guard * w, src_net, net_width, net_h
+
+
+@pytest.mark.parametrize("rate", [16, 8, 4, 2, 1])
+@pytest.mark.parametrize("w,h", [(64, 48), (120, 68), (88, 72)])
+def test_luma_search_1step(rate, w, h):
+    o = oracle()
+    for seed, big in ((10, False), (11, True)):
+        cur, packed, off, src_net, net_width, net_h = _search_case(seed + rate, w, h, rate, big)
+        dst_a = np.full((net_h * net_width, 2), 77, np.int16)
+        dst_b = dst_a.copy()
+        o.vp8o_luma_search_1step(P(cur), P(packed, off), P(src_net), P(dst_a), net_width, w, h, rate)
+        n = (w // 8) * (h // 8)
+        n_pad = (n + 255) // 256 * 256
+        ref_run("luma_search_1step", n_pad, 256,
+                [cur, ctypes.c_void_p(packed.ctypes.data + off), src_net, dst_b, net_width, w, h, rate])
+        assert np.array_equal(dst_a, dst_b)
+        assert not np.all(dst_a == 77)
+
+
+@pytest.mark.parametrize("w,h", [(64, 48), (96, 80)])
+def test_luma_search_2step(w, h):
+    o = oracle()
+    for seed in (20, 21, 22):
+        r = rng(seed)
+        ref_img = textured(r, h, w, smooth=3 if seed != 22 else 1)
+        if seed == 22:  # hard edges: exercises the saturating horizontal lines
+            ref_img = (r.integers(0, 2, size=(h, w)) * 255).astype(np.uint8)
+        cur = np.roll(ref_img, (1, -2), axis=(0, 1)).astype(np.int32) + r.integers(-5, 6, size=(h, w))
+        cur = np.clip(cur, 0, 255).astype(np.uint8)
+        nb = w * h // 64
+        net = r.integers(-9, 10, size=(nb, 2)).astype(np.int16)  # full-pel vectors, some leave the frame
+        out_a = np.zeros((nb, 2), np.int16)
+        out_b = np.zeros((nb, 2), np.int16)
+        m_a = np.zeros(nb, np.int32)
+        m_b = np.zeros(nb, np.int32)
+        o.vp8o_luma_search_2step(P(cur), P(ref_img), P(net), P(out_a), P(m_a), w, h)
+        ref_run("luma_search_2step", (nb + 255) // 256 * 256, 256, [cur, Image(ref_img), net, out_b, m_b, w, h])
+        assert np.array_equal(out_a, out_b)
+        assert np.array_equal(m_a, m_b)
+
+
+def test_select_reference_and_pack():
+    o = oracle()
+    w, h = 96, 64
+    M = (w // 16) * (h // 16)
+    r = rng(30)
+    for use_g, use_a in ((0, 0), (1, 0), (0, 1), (1, 1)):
+        nets = [r.integers(-3, 4, size=(M * 4, 2)).astype(np.int16) for _ in range(3)]
+        nets[0][:8] = 1  # some macroblocks with four equal vectors
+        mets = [r.integers(0, 50, size=M * 4).astype(np.int32) for _ in range(3)]  # small range -> many ties
+        ref_a = np.zeros(M, np.int32)
+        ref_b = np.zeros(M, np.int32)
+        vec_a = np.zeros((M, 8), np.int16)
+        vec_b = np.zeros((M, 8), np.int16)
+        o.vp8o_select_reference(P(nets[0]), P(nets[1]), P(nets[2]), P(mets[0]), P(mets[1]), P(mets[2]), P(ref_a),
+                                P(vec_a), w, h, use_g, use_a)
+        ref_run("select_reference", M, 0, [nets[0], nets[1], nets[2], mets[0], mets[1], mets[2], ref_b, vec_b, w,
+                                           use_g, use_a])
+        assert np.array_equal(ref_a, ref_b) and np.array_equal(vec_a, vec_b)
+        parts_a = np.zeros(M, np.int32)
+        parts_b = np.zeros(M, np.int32)
+        s_a = np.zeros(M, np.float32)
+        s_b = np.zeros(M, np.float32)
+        o.vp8o_pack_8x8_into_16x16(P(vec_a), P(parts_a), P(s_a), M)
+        ref_run("pack_8x8_into_16x16", M, 0, [vec_b, parts_b, s_b])
+        assert np.array_equal(parts_a, parts_b) and np.array_equal(s_a, s_b)
+        assert (s_a == -2.0).all()
+
+
+@pytest.mark.parametrize("plane", [0, 1, 2])
+def test_prepare_predictors_and_residual(plane):
+    o = oracle()
+    W, H = 96, 64
+    w, h = (W, H) if plane == 0 else (W // 2, H // 2)
+    M = (W // 16) * (H // 16)
+    for seed in (40, 41):
+        r = rng(seed + plane)
+        # black/white noise makes six-tap overshoot common -> hits the wrapping lines of Q5
+        img = (r.integers(0, 2, size=(h, w)) * 255).astype(np.uint8) if seed == 41 else textured(r, h, w, 2)
+        cur = r.integers(0, 256, size=(h, w)).astype(np.uint8)
+        refs = r.integers(0, 3, size=M).astype(np.int32)
+        # legal vectors: every 8x8 luma block stays inside the frame in quarter pels
+        vec = np.zeros((M, 4, 2), np.int16)
+        for mb in range(M):
+            for q in range(4):
+                bx = (mb % (W // 16)) * 16 + (q % 2) * 8
+                by = (mb // (W // 16)) * 16 + (q // 2) * 8
+                vec[mb, q, 0] = r.integers(-4 * bx, 4 * (W - 8 - bx) + 1)
+                vec[mb, q, 1] = r.integers(-4 * by, 4 * (H - 8 - by) + 1)
+        for ref_id in range(3):
+            pa = np.full((h, w), 9, np.uint8)
+            pb = pa.copy()
+            ra = np.full((h, w), 9, np.int16)
+            rb = ra.copy()
+            o.vp8o_prepare_predictors_and_residual(P(cur), P(img), P(pa), P(ra), P(refs), P(vec), w, h, plane, ref_id)
+            ref_run("prepare_predictors_and_residual", (w // 4) * (h // 4), 0,
+                    [cur, Image(img), pb, rb, refs, vec, w, plane, ref_id])
+            assert np.array_equal(pa, pb)
+            assert np.array_equal(ra, rb)
+
+
+def test_predictor_wrap_quirk_is_exercised():
+    """Q5: at least one input exists where wrapping lines Y+4..Y+6 differ from saturating ones."""
+    o = oracle()
+    w, h = 32, 32
+    img = np.zeros((h, w), np.uint8)
+    img[:, ::2] = 255  # vertical stripes: strong horizontal overshoot at half-pel
+    cur = np.zeros((h, w), np.uint8)
+    refs = np.zeros(4, np.int32)
+    vec = np.zeros((4, 4, 2), np.int16)
+    vec[:, :, 0] = 2  # half-pel in x
+    vec[:, :, 1] = 2
+    pa = np.zeros((h, w), np.uint8)
+    ra = np.zeros((h, w), np.int16)
+    pb = np.zeros((h, w), np.uint8)
+    rb = np.zeros((h, w), np.int16)
+    o.vp8o_prepare_predictors_and_residual(P(cur), P(img), P(pa), P(ra), P(refs), P(vec), w, h, 0, 0)
+    ref_run("prepare_predictors_and_residual", (w // 4) * (h // 4), 0, [cur, Image(img), pb, rb, refs, vec, w, 0, 0])
+    assert np.array_equal(pa, pb)
+
+
+def _transform_case(seed, W, H, ssim_mix):
+    r = rng(seed)
+    M = (W // 16) * (H // 16)
+    res = [r.integers(-255, 256, size=(H, W)).astype(np.int16), r.integers(-80, 81, size=(H // 2, W // 2)).astype(np.int16),
+           r.integers(-80, 81, size=(H // 2, W // 2)).astype(np.int16)]
+    parts = r.integers(0, 2, size=M).astype(np.int32)
+    ssim = np.full(M, -2.0, np.float32)
+    if ssim_mix:
+        ssim = r.choice(np.array([-2.0, 0.5, 0.97], np.float32), size=M)
+    return r, M, res, parts, ssim
+
+
+@pytest.mark.parametrize("qi", [0, 24, 60, 127])
+def test_dct_wht_idct_chain(qi):
+    o = oracle()
+    W, H = 64, 48
+    for ssim_mix, target in ((False, -1.0), (True, 0.9)):
+        r, M, res, parts, ssim = _transform_case(50 + qi, W, H, ssim_mix)
+        sd = make_segment_data((max(0, qi - 6), max(0, qi - 4), max(0, qi - 2), qi))
+        coef_a = r.integers(-5, 6, size=(M, 400)).astype(np.int16)  # stale contents must survive where untouched
+        coef_b = coef_a.copy()
+        seg_a = r.integers(0, 4, size=M).astype(np.int32)
+        seg_b = seg_a.copy()
+        pred = [r.integers(0, 256, size=x.shape).astype(np.uint8) for x in res]
+        rec_a = [np.full(x.shape, 3, np.uint8) for x in res]
+        rec_b = [x.copy() for x in rec_a]
+        for s in (3, 2, 1, 0):
+            for p in range(3):
+                w, h = (W, H) if p == 0 else (W // 2, H // 2)
+                o.vp8o_dct4x4(P(res[p]), P(coef_a), P(seg_a), P(parts), P(ssim), w, h, P(sd), s,
+                              ctypes.c_float(target), p)
+                ref_run("dct4x4", (w // 4) * (h // 4), 0, [res[p], coef_b, seg_b, parts, ssim, w, sd, s, float(target), p])
+            assert np.array_equal(coef_a, coef_b) and np.array_equal(seg_a, seg_b)
+            o.vp8o_wht4x4_iwht4x4(P(coef_a), P(seg_a), P(parts), P(sd), s, M)
+            ref_run("wht4x4_iwht4x4", M, 0, [coef_b, ssim, seg_b, parts, sd, s])
+            assert np.array_equal(coef_a, coef_b)
+            for p in range(3):
+                w, h = (W, H) if p == 0 else (W // 2, H // 2)
+                o.vp8o_idct4x4(P(rec_a[p]), P(pred[p]), P(coef_a), P(seg_a), P(parts), w, h, P(sd), s, p)
+                ref_run("idct4x4", (w // 4) * (h // 4), 0, [rec_b[p], pred[p], coef_b, seg_b, parts, w, sd, s, p])
+                assert np.array_equal(rec_a[p], rec_b[p])
+
+
+def test_ssim_bit_exact():
+    o = oracle()
+    W, H = 96, 64
+    M = (W // 16) * (H // 16)
+    for seed in (60, 61, 62):
+        r = rng(seed)
+        a = textured(r, H, W, 2)
+        noise = r.integers(-20, 21, size=(H, W)) if seed != 62 else r.integers(-2, 3, size=(H, W)) + 9
+        b = np.clip(a.astype(np.int32) + noise, 0, 255).astype(np.uint8)
+        seg = r.integers(0, 2, size=M).astype(np.int32)
+        for mbs, w, h, name in ((16, W, H, "count_SSIM_luma"), (8, W // 2, H // 2, "count_SSIM_chroma")):
+            fa = np.ascontiguousarray(a[:h, :w])
+            fb = np.ascontiguousarray(b[:h, :w])
+            ma = np.full(M, 5.0, np.float32)
+            mb = ma.copy()
+            o.vp8o_count_SSIM(P(fa), P(fb), P(seg), P(ma), w, h, 1, mbs)
+            ref_run(name, M, 0, [fa, fb, seg, mb, w, 1])
+            assert np.array_equal(ma.view(np.uint32), mb.view(np.uint32))
+        m = [r.random(M).astype(np.float32) for _ in range(3)]
+        ga = np.zeros(M, np.float32)
+        gb = np.zeros(M, np.float32)
+        o.vp8o_gather_SSIM(P(m[0]), P(m[1]), P(m[2]), P(ga), M)
+        ref_run("gather_SSIM", M, 0, [m[0], m[1], m[2], gb])
+        assert np.array_equal(ga.view(np.uint32), gb.view(np.uint32))
+
+
+def test_filter_mask():
+    o = oracle()
+    W, H = 96, 64
+    M = (W // 16) * (H // 16)
+    r = rng(70)
+    coef = (r.integers(-3, 4, size=(M, 400)) * (r.random((M, 400)) < 0.05)).astype(np.int16)
+    coef[0] = 0
+    coef[1] = 0
+    coef[1, 24 * 16 + 3] = -7  # only Y2 set
+    coef[2] = 0
+    coef[2, 5 * 16] = 4  # only a luma DC set
+    parts = r.integers(0, 3, size=M).astype(np.int32)
+    parts[:3] = [0, 0, 0]
+    nz_a = np.zeros(M, np.int32)
+    nz_b = np.zeros(M, np.int32)
+    mk_a = np.zeros(M, np.int32)
+    mk_b = np.zeros(M, np.int32)
+    o.vp8o_prepare_filter_mask(P(coef), P(nz_a), P(parts), P(mk_a), W, H)
+    ref_run("prepare_filter_mask", 4, 1, [coef, nz_b, parts, mk_b, W, H, 4])
+    assert np.array_equal(nz_a, nz_b) and np.array_equal(mk_a, mk_b)
+    assert mk_a[0] == 0 and mk_a[1] == -1 and nz_a[2] == 0  # a luma DC of a 16x16 MB is not counted
+
+
+@pytest.mark.parametrize("mb_size,name", [(16, "loop_filter_frame_luma"), (8, "loop_filter_frame_chroma")])
+def test_loop_filter(mb_size, name):
+    o = oracle()
+    mbw, mbh = 7, 5
+    w, h = mbw * mb_size, mbh * mb_size
+    M = mbw * mbh
+    for seed, levels, sharp in ((80, (10, 20, 40, 63), 0), (81, (63, 63, 63, 63), 0), (82, (30, 8, 0, 50), 3),
+                                (83, (5, 5, 5, 5), 7)):
+        r = rng(seed)
+        # 4x4 blocks with small level steps + mild noise: most edges pass the filter mask
+        lv = 128 + np.cumsum(r.integers(-6, 7, size=(h // 4, w // 4)), axis=1) + \
+            np.cumsum(r.integers(-6, 7, size=(h // 4, w // 4)), axis=0)
+        frame = (np.kron(lv, np.ones((4, 4), np.int64)) + r.integers(-2, 3, size=(h, w))).clip(0, 255).astype(np.uint8)
+        if seed == 81:  # near-saturated blocky content: drives intermediates out of [-128,127] (Q7)
+            blocks = r.choice(np.array([0, 3, 252, 255], np.uint8), size=(h // 4, w // 4))
+            frame = (np.kron(blocks, np.ones((4, 4), np.uint8)).astype(np.int32) +
+                     r.integers(-3, 4, size=(h, w))).clip(0, 255).astype(np.uint8)
+        seg = r.integers(0, 4, size=M).astype(np.int32)
+        if seed == 82:
+            seg[: M // 2] = r.choice(np.array([0, 1, 3], np.int32), size=M // 2)  # level-0 segment only later (Q6)
+        mask = r.choice(np.array([0, -1], np.int32), size=M)
+        sd = make_segment_data(lf_level=levels, sharpness=sharp)
+        fa = frame.copy()
+        fb = frame.copy()
+        o.vp8o_loop_filter_frame(P(fa), P(seg), P(mask), P(sd), w, h, mb_size)
+        ref_run(name, 1, 0, [fb, seg, mask, sd, w, h])
+        assert np.array_equal(fa, fb)
+        changed = float((fa != frame).mean())
+        assert changed > (0.02 if seed != 83 else 0.0), changed
