@@ -1,0 +1,114 @@
+/*
+ * vp8b200.h -- kernel-level C ABI of the B200 engine behind vp8oclenc's OpenCL boundary.
+ *
+ * One entry point per reference __kernel on the inter-frame hot path.
+ * Each call has whole-NDRange semantics: it does what the reference host obtains by
+ * enqueueing that kernel over its full global size (src/inter_part.h, src/loop_filter.h)
+ * with the arguments bound in src/init.h:597-1271.  All pointers are DEVICE pointers;
+ * `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  Calls are
+ * asynchronous; the return value is 0 or a negative cudaError_t of the launch.
+ *
+ * The library (vp8oclenc_b200/lib/libvp8b200.so) contains only CUDA code for sm_100a: there
+ * is no CPU fallback, every entry point fails with a CUDA error when no device is present.
+ *
+ * Layouts (identical to the reference's, src/vp8enc.h:80-120):
+ *   planes        tightly packed uint8, luma stride = width, chroma = width/2
+ *   vector nets   short2 per 8x8 block, stride net_width = 2*mb_width at EVERY pyramid level
+ *   MB_vectors    4 x short2 per macroblock (TL,TR,BL,BR), quarter-pel units
+ *   MB coeffs     25 blocks x 16 int16 per macroblock in zig-zag position order;
+ *                 blocks 0-15 Y raster, 16-19 U, 20-23 V, 24 Y2
+ *   segment_data  4 x 11 int32
+ */
+#ifndef VP8B200_H
+#define VP8B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct {
+    int32_t y_ac_i, y_dc_idelta, y2_dc_idelta, y2_ac_idelta, uv_dc_idelta, uv_ac_idelta;
+    int32_t loop_filter_level, mbedge_limit, sub_bedge_limit, interior_limit, hev_threshold;
+} vp8b200_segment_data; /* src/vp8enc.h:80-92, src/GPU_kernels.cl:24-36 */
+
+/* library / device identification; returns 0 when a CUDA device is usable */
+int vp8b200_device_info(char *name, int name_cap, int *sm_count, int *cc_major, int *cc_minor);
+const char *vp8b200_version(void);
+
+/* replaces reset_vectors, src/GPU_kernels.cl:404-427 (enqueued at src/inter_part.h:5-6); n = 4*mb_count */
+int vp8b200_reset_vectors(void *stream, int16_t *last_net1, int16_t *last_net2, int16_t *golden_net1,
+                          int16_t *golden_net2, int16_t *altref_net1, int16_t *altref_net2, int32_t *last_Bdiff,
+                          int32_t *golden_Bdiff, int32_t *altref_Bdiff, int n);
+
+/* replaces downsample_x2, src/GPU_kernels.cl:429-451 (src/inter_part.h:11-33) */
+int vp8b200_downsample_x2(void *stream, const uint8_t *src, uint8_t *dst, int src_width, int src_height);
+
+/* replaces luma_search_1step, src/GPU_kernels.cl:459-560 (src/inter_part.h:109-219) */
+int vp8b200_luma_search_1step(void *stream, const uint8_t *current_frame, const uint8_t *prev_frame,
+                              const int16_t *src_net, int16_t *dst_net, int net_width, int width, int height,
+                              int pixel_rate);
+
+/* replaces luma_search_2step + construct_opt1/2, src/GPU_kernels.cl:776-1203 (src/inter_part.h:221-236).
+ * ref_frame is the width x height luma plane the reference binds as an image (clamp-to-edge reads). */
+int vp8b200_luma_search_2step(void *stream, const uint8_t *current_frame, const uint8_t *ref_frame,
+                              const int16_t *net, int16_t *ref_net, int32_t *ref_Bdiff, int width, int height);
+
+/* replaces select_reference, src/GPU_kernels.cl:1205-1283 (src/inter_part.h:250-255) */
+int vp8b200_select_reference(void *stream, const int16_t *last_net, const int16_t *golden_net,
+                             const int16_t *altref_net, const int32_t *last_Bdiff, const int32_t *golden_Bdiff,
+                             const int32_t *altref_Bdiff, int32_t *MB_reference_frame, int16_t *MB_vectors, int width,
+                             int height, int use_golden, int use_altref);
+
+/* replaces pack_8x8_into_16x16, src/GPU_kernels.cl:1346-1366 (src/inter_part.h:257-258) */
+int vp8b200_pack_8x8_into_16x16(void *stream, const int16_t *MB_vectors, int32_t *MB_parts, float *MB_SSIM,
+                                int mb_count);
+
+/* replaces prepare_predictors_and_residual + construct, src/GPU_kernels.cl:574-774,1285-1344
+ * (src/inter_part.h:268-321).  width/height are the plane's; plane 0=Y 1=U 2=V; ref 0=LAST 1=GOLDEN 2=ALTREF */
+int vp8b200_prepare_predictors_and_residual(void *stream, const uint8_t *current_frame, const uint8_t *ref_frame,
+                                            uint8_t *predictor, int16_t *residual, const int32_t *MB_reference_frame,
+                                            const int16_t *MB_vectors, int width, int height, int plane, int ref);
+
+/* replaces dct4x4, src/GPU_kernels.cl:1368-1496 (src/inter_part.h:334-343) */
+int vp8b200_dct4x4(void *stream, const int16_t *residual, int16_t *MB, int32_t *MB_segment_id,
+                   const int32_t *MB_parts, const float *MB_SSIM, int width, int height,
+                   const vp8b200_segment_data *SD, int segment_id, float SSIM_target, int plane);
+
+/* replaces wht4x4_iwht4x4, src/GPU_kernels.cl:257-401,1498-1543 (src/inter_part.h:345-346) */
+int vp8b200_wht4x4_iwht4x4(void *stream, int16_t *MB, int32_t *MB_segment_id, const int32_t *MB_parts,
+                           const vp8b200_segment_data *SD, int segment_id, int mb_count);
+
+/* replaces idct4x4, src/GPU_kernels.cl:192-255,1545-1608 (src/inter_part.h:349-357) */
+int vp8b200_idct4x4(void *stream, uint8_t *recon_frame, const uint8_t *predictor, const int16_t *MB,
+                    const int32_t *MB_segment_id, const int32_t *MB_parts, int width, int height,
+                    const vp8b200_segment_data *SD, int segment_id, int plane);
+
+/* replaces count_SSIM_luma (mb_size 16) and count_SSIM_chroma (mb_size 8),
+ * src/GPU_kernels.cl:1610-2095 (src/inter_part.h:361-370) */
+int vp8b200_count_SSIM(void *stream, const uint8_t *frame1, const uint8_t *frame2, const int32_t *MB_segment_id,
+                       float *metric, int width, int height, int segment_id, int mb_size);
+
+/* replaces gather_SSIM, src/GPU_kernels.cl:2097-2105 (src/inter_part.h:377) */
+int vp8b200_gather_SSIM(void *stream, const float *metric1, const float *metric2, const float *metric3,
+                        float *MB_SSIM, int mb_count);
+
+/* replaces prepare_filter_mask, src/CPU_kernels.cl:782-827 (src/loop_filter.h:25-33) */
+int vp8b200_prepare_filter_mask(void *stream, const int16_t *MB, int32_t *MB_non_zero_coeffs,
+                                const int32_t *MB_parts, int32_t *mb_mask, int width, int height);
+
+/* replaces loop_filter_frame_luma (mb_size 16) / loop_filter_frame_chroma (mb_size 8),
+ * src/CPU_kernels.cl:829-1075,1333-1438 (src/loop_filter.h:140-183): the VP8 normal loop
+ * filter in raster macroblock order, run as a wavefront over macroblock rows */
+int vp8b200_loop_filter_frame(void *stream, uint8_t *frame, const int32_t *MB_segment_ids, const int32_t *mb_mask,
+                              const vp8b200_segment_data *SD, int width, int height, int mb_size);
+
+/* the three planes of one frame in a single launch (Y, U, V run concurrently) */
+int vp8b200_loop_filter_planes(void *stream, uint8_t *y, uint8_t *u, uint8_t *v, const int32_t *MB_segment_ids,
+                               const int32_t *mb_mask, const vp8b200_segment_data *SD, int width, int height);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VP8B200_H */

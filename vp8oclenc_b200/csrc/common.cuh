@@ -1,0 +1,102 @@
+// Shared device helpers of the vp8oclenc_b200 CUDA engine (sm_100a).
+//
+// Arithmetic contract: 32-bit two's-complement integers,
+// arithmetic >>, truncating /.  Every quirk of the reference kernels that is observable in
+// motion vectors, coefficients or reconstructed pixels is reproduced and cited where it lives.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "vp8b200.h"
+
+#define VP8_LAUNCH_CHECK() \
+    do {                   \
+        cudaError_t e_ = cudaGetLastError(); \
+        return e_ == cudaSuccess ? 0 : -(int)e_; \
+    } while (0)
+
+namespace vp8 {
+
+enum { ARE16x16 = 0, ARE8x8 = 1, ARE4x4 = 2 };
+enum { LAST = 0, GOLDEN = 1, ALTREF = 2 };
+
+// VP8 quantiser tables (RFC 6386 14.1; reference copy: src/GPU_kernels.cl:58-80)
+static __constant__ const short c_dc_q[128] = {
+    4,   5,   6,   7,   8,   9,   10,  10,  11,  12,  13,  14,  15,  16,  17,  17,  18,  19,  20,  20,  21,  21,
+    22,  22,  23,  23,  24,  25,  25,  26,  27,  28,  29,  30,  31,  32,  33,  34,  35,  36,  37,  37,  38,  39,
+    40,  41,  42,  43,  44,  45,  46,  46,  47,  48,  49,  50,  51,  52,  53,  54,  55,  56,  57,  58,  59,  60,
+    61,  62,  63,  64,  65,  66,  67,  68,  69,  70,  71,  72,  73,  74,  75,  76,  76,  77,  78,  79,  80,  81,
+    82,  83,  84,  85,  86,  87,  88,  89,  91,  93,  95,  96,  98,  100, 101, 102, 104, 106, 108, 110, 112, 114,
+    116, 118, 122, 124, 126, 128, 130, 132, 134, 136, 138, 140, 143, 145, 148, 151, 154, 157};
+static __constant__ const short c_ac_q[128] = {
+    4,   5,   6,   7,   8,   9,   10,  11,  12,  13,  14,  15,  16,  17,  18,  19,  20,  21,  22,  23,  24,  25,
+    26,  27,  28,  29,  30,  31,  32,  33,  34,  35,  36,  37,  38,  39,  40,  41,  42,  43,  44,  45,  46,  47,
+    48,  49,  50,  51,  52,  53,  54,  55,  56,  57,  58,  60,  62,  64,  66,  68,  70,  72,  74,  76,  78,  80,
+    82,  84,  86,  88,  90,  92,  94,  96,  98,  100, 102, 104, 106, 108, 110, 112, 114, 116, 119, 122, 125, 128,
+    131, 134, 137, 140, 143, 146, 149, 152, 155, 158, 161, 164, 167, 170, 173, 177, 181, 185, 189, 193, 197, 201,
+    205, 209, 213, 217, 221, 225, 229, 234, 239, 245, 249, 254, 259, 264, 269, 274, 279, 284};
+
+// six-tap sub-pixel filters indexed by eighth-pel phase (RFC 6386 subpixel_filters;
+// reference copy: src/GPU_kernels.cl:563-572)
+static __constant__ const short c_sixtap[8][6] = {
+    {0, 0, 128, 0, 0, 0},     {0, -6, 123, 12, -1, 0}, {2, -11, 108, 36, -8, 1}, {0, -9, 93, 50, -6, 0},
+    {3, -16, 77, 77, -16, 3}, {0, -6, 50, 93, -9, 0},  {1, -8, 36, 108, -11, 2}, {0, -1, 12, 123, -6, 0}};
+
+// position in the zig-zag scan of raster coefficient k (src/GPU_kernels.cl:1489)
+static __constant__ const unsigned char c_inv_zigzag[16] = {0, 1, 5, 6, 2, 4, 7, 12, 3, 8, 11, 13, 9, 10, 14, 15};
+
+// the same table as a packed literal, so that unrolled loops index it at compile time
+__device__ __forceinline__ constexpr int inv_zz(int k) { return (int)((0xFEA9DB83C7426510ULL >> (4 * k)) & 15); }
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
+__device__ __forceinline__ int sat8(int v) { return min(max(v, 0), 255); }
+
+// Block cost of a 4x4 residual r[row*4+col] (weight_opt, src/GPU_kernels.cl:85-190).
+// Pass 1 runs down the columns with the reference's register clobber (Q1): the "b1" term is
+// overwritten by c1 and the odd outputs use the RAW third row in place of c1.  Pass 2 is the
+// regular VP8 second pass along the rows.  Result = |DC|/4 + sum of the other magnitudes.
+__device__ __forceinline__ int weight4x4(const int (&r)[16]) {
+    int o[16];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int a1 = (r[k] + r[12 + k]) << 3;
+        const int d1 = (r[k] - r[12 + k]) << 3;
+        const int c1 = (r[4 + k] - r[8 + k]) << 3;
+        const int x = r[8 + k];
+        o[k] = a1 + c1;
+        o[8 + k] = a1 - c1;
+        o[4 + k] = (x * 2217 + d1 * 5352 + 14500) >> 12;
+        o[12 + k] = (d1 * 2217 - x * 5352 + 7500) >> 12;
+    }
+    int sum = 0;
+#pragma unroll
+    for (int row = 0; row < 4; ++row) {
+        const int a = o[4 * row] + o[4 * row + 3], d = o[4 * row] - o[4 * row + 3];
+        const int b = o[4 * row + 1] + o[4 * row + 2], c = o[4 * row + 1] - o[4 * row + 2];
+        const int f0 = (a + b + 7) >> 4;
+        const int f2 = (a - b + 7) >> 4;
+        const int f1 = ((c * 2217 + d * 5352 + 12000) >> 16) + (d != 0);
+        const int f3 = (d * 2217 - c * 5352 + 51000) >> 16;
+        sum += (row == 0 ? (abs(f0) >> 2) : abs(f0)) + abs(f1) + abs(f2) + abs(f3);
+    }
+    return sum;
+}
+
+// quantisers of one segment, derived exactly as the device code of the reference does it
+// in three places (Q11; src/GPU_kernels.cl:1394-1408, 1515-1524, 1568-1582)
+struct Quants {
+    int y_dc, y_ac, uv_dc, uv_ac, y2_dc, y2_ac;
+};
+__device__ __forceinline__ Quants derive_quants(const vp8b200_segment_data *SD, int seg) {
+    Quants q;
+    const int i = SD[seg].y_ac_i;
+    q.y_ac = c_ac_q[i];
+    q.y_dc = c_dc_q[clampi(i + SD[0].y_dc_idelta, 0, 127)];
+    q.uv_dc = min((int)c_dc_q[clampi(i + SD[0].uv_dc_idelta, 0, 127)], 132);
+    q.uv_ac = c_ac_q[clampi(i + SD[0].uv_ac_idelta, 0, 127)];
+    q.y2_dc = c_dc_q[clampi(i + SD[0].y2_dc_idelta, 0, 127)] * 2;
+    q.y2_ac = max(31 * c_ac_q[clampi(i + SD[0].y2_ac_idelta, 0, 127)] / 20, 8);
+    return q;
+}
+
+}  // namespace vp8

@@ -1,0 +1,139 @@
+"""Python host-side mirror of the kernel-level C ABI (include/vp8b200.h).
+
+One function per reference __kernel, same names and argument meaning as the reference's
+kernels (src/GPU_kernels.cl, src/CPU_kernels.cl).  Arguments are torch CUDA tensors (torch is
+only used for device memory and streams); every call is forwarded to libvp8b200.so, which
+contains nothing but CUDA code -- there is no CPU fallback: loading fails loudly when the
+library has not been built, and every call raises on a CUDA error.
+"""
+import ctypes
+import os
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_PKG, "lib", "libvp8b200.so")
+_lib = None
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise EngineError("%s is missing: run `python -m vp8oclenc_b200.build` (there is no fallback path)" % _LIB_PATH)
+        _lib = ctypes.CDLL(_LIB_PATH)
+        _lib.vp8b200_version.restype = ctypes.c_char_p
+    return _lib
+
+
+def _p(t):
+    if t is None:
+        return ctypes.c_void_p(0)
+    if not t.is_cuda:
+        raise EngineError("vp8oclenc_b200 kernels take CUDA tensors only")
+    if not t.is_contiguous():
+        raise EngineError("tensor must be contiguous")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise EngineError("%s failed: CUDA error %d" % (what, -rc))
+
+
+def device_info():
+    name = ctypes.create_string_buffer(256)
+    sm, major, minor = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    _check(lib().vp8b200_device_info(name, 256, ctypes.byref(sm), ctypes.byref(major), ctypes.byref(minor)), "device_info")
+    return dict(name=name.value.decode(), sm_count=sm.value, cc=(major.value, minor.value))
+
+
+def segment_data_tensor(sd_np):
+    """numpy int32 [4, 11] -> device copy"""
+    return torch.from_numpy(sd_np.copy()).cuda()
+
+
+def reset_vectors(last1, last2, gold1, gold2, alt1, alt2, last_d, gold_d, alt_d):
+    _check(lib().vp8b200_reset_vectors(_stream(), _p(last1), _p(last2), _p(gold1), _p(gold2), _p(alt1), _p(alt2),
+                                       _p(last_d), _p(gold_d), _p(alt_d), ctypes.c_int(last_d.numel())), "reset_vectors")
+
+
+def downsample_x2(src, dst, src_width, src_height):
+    _check(lib().vp8b200_downsample_x2(_stream(), _p(src), _p(dst), src_width, src_height), "downsample_x2")
+
+
+def luma_search_1step(current_frame, prev_frame, src_net, dst_net, net_width, width, height, pixel_rate):
+    _check(lib().vp8b200_luma_search_1step(_stream(), _p(current_frame), _p(prev_frame), _p(src_net), _p(dst_net),
+                                           net_width, width, height, pixel_rate), "luma_search_1step")
+
+
+def luma_search_2step(current_frame, ref_frame, net, ref_net, ref_Bdiff, width, height):
+    _check(lib().vp8b200_luma_search_2step(_stream(), _p(current_frame), _p(ref_frame), _p(net), _p(ref_net),
+                                           _p(ref_Bdiff), width, height), "luma_search_2step")
+
+
+def select_reference(last_net, golden_net, altref_net, last_d, golden_d, altref_d, MB_reference_frame, MB_vectors,
+                     width, height, use_golden, use_altref):
+    _check(lib().vp8b200_select_reference(_stream(), _p(last_net), _p(golden_net), _p(altref_net), _p(last_d),
+                                          _p(golden_d), _p(altref_d), _p(MB_reference_frame), _p(MB_vectors), width,
+                                          height, int(use_golden), int(use_altref)), "select_reference")
+
+
+def pack_8x8_into_16x16(MB_vectors, MB_parts, MB_SSIM):
+    _check(lib().vp8b200_pack_8x8_into_16x16(_stream(), _p(MB_vectors), _p(MB_parts), _p(MB_SSIM),
+                                             ctypes.c_int(MB_parts.numel())), "pack_8x8_into_16x16")
+
+
+def prepare_predictors_and_residual(current_frame, ref_frame, predictor, residual, MB_reference_frame, MB_vectors,
+                                    width, height, plane, ref):
+    _check(lib().vp8b200_prepare_predictors_and_residual(_stream(), _p(current_frame), _p(ref_frame), _p(predictor),
+                                                         _p(residual), _p(MB_reference_frame), _p(MB_vectors), width,
+                                                         height, plane, ref), "prepare_predictors_and_residual")
+
+
+def dct4x4(residual, MB, MB_segment_id, MB_parts, MB_SSIM, width, height, SD, segment_id, SSIM_target, plane):
+    _check(lib().vp8b200_dct4x4(_stream(), _p(residual), _p(MB), _p(MB_segment_id), _p(MB_parts), _p(MB_SSIM), width,
+                                height, _p(SD), segment_id, ctypes.c_float(SSIM_target), plane), "dct4x4")
+
+
+def wht4x4_iwht4x4(MB, MB_segment_id, MB_parts, SD, segment_id):
+    _check(lib().vp8b200_wht4x4_iwht4x4(_stream(), _p(MB), _p(MB_segment_id), _p(MB_parts), _p(SD), segment_id,
+                                        ctypes.c_int(MB_parts.numel())), "wht4x4_iwht4x4")
+
+
+def idct4x4(recon_frame, predictor, MB, MB_segment_id, MB_parts, width, height, SD, segment_id, plane):
+    _check(lib().vp8b200_idct4x4(_stream(), _p(recon_frame), _p(predictor), _p(MB), _p(MB_segment_id), _p(MB_parts),
+                                 width, height, _p(SD), segment_id, plane), "idct4x4")
+
+
+def count_SSIM(frame1, frame2, MB_segment_id, metric, width, height, segment_id, mb_size):
+    _check(lib().vp8b200_count_SSIM(_stream(), _p(frame1), _p(frame2), _p(MB_segment_id), _p(metric), width, height,
+                                    segment_id, mb_size), "count_SSIM")
+
+
+def gather_SSIM(metric1, metric2, metric3, MB_SSIM):
+    _check(lib().vp8b200_gather_SSIM(_stream(), _p(metric1), _p(metric2), _p(metric3), _p(MB_SSIM),
+                                     ctypes.c_int(MB_SSIM.numel())), "gather_SSIM")
+
+
+def prepare_filter_mask(MB, MB_non_zero_coeffs, MB_parts, mb_mask, width, height):
+    _check(lib().vp8b200_prepare_filter_mask(_stream(), _p(MB), _p(MB_non_zero_coeffs), _p(MB_parts), _p(mb_mask),
+                                             width, height), "prepare_filter_mask")
+
+
+def loop_filter_frame(frame, MB_segment_ids, mb_mask, SD, width, height, mb_size):
+    _check(lib().vp8b200_loop_filter_frame(_stream(), _p(frame), _p(MB_segment_ids), _p(mb_mask), _p(SD), width,
+                                           height, mb_size), "loop_filter_frame")
+
+
+def loop_filter_planes(y, u, v, MB_segment_ids, mb_mask, SD, width, height):
+    _check(lib().vp8b200_loop_filter_planes(_stream(), _p(y), _p(u), _p(v), _p(MB_segment_ids), _p(mb_mask), _p(SD),
+                                            width, height), "loop_filter_planes")
