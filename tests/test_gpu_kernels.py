@@ -74,7 +74,7 @@ def test_luma_search_1step(eng, rate, w, h):
         prev = textured(r, h, w)
         sx, sy = int(r.integers(-3, 4)), int(r.integers(-3, 4))
         cur = np.clip(np.roll(prev, (sy, sx), axis=(0, 1)).astype(np.int32) + r.integers(-6, 7, size=(h, w)), 0, 255).astype(np.uint8)
-        net_width = max(2, ((w * rate) // 16) * 2)
+        net_width = max(2, (w * rate) // 8)  # >= blocks per row, like 2*mb_width in the encoder
         net_h = max(2, ((h * rate) // 16) * 2) + 2
         src_net = (r.integers(-lim, lim + 1, size=(net_h * net_width, 2)) * rate).astype(np.int16)
         dst_a = np.full((net_h * net_width, 2), 77, np.int16)

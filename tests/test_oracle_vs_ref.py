@@ -89,7 +89,7 @@ def _search_case(seed, w, h, rate, big_vectors=False):
     packed = np.zeros((h + 2 * guard) * w + 64, np.uint8)
     packed[:] = r.integers(0, 256, size=packed.size)
     packed[guard * w:guard * w + h * w] = np.ascontiguousarray(prev).reshape(-1)
-    net_width = max(2, ((w * rate) // 16) * 2)
+    net_width = max(2, (w * rate) // 8)  # >= blocks per row, like 2*mb_width in the encoder
     net_h = max(2, ((h * rate) // 16) * 2) + 2
     lim = 6 if not big_vectors else 40
     src_net = (r.integers(-lim, lim + 1, size=(net_h * net_width, 2)) * rate).astype(np.int16)

@@ -197,11 +197,13 @@ k_luma_search_2step(const uint8_t *__restrict__ cur, const uint8_t *__restrict__
     }
     __syncthreads();
 
-    if (tid < 104) {
-        const int k = tid >> 2, j = tid & 3;
+    {
+        // 104 work units; the 24 spare lanes of the last warp run the zero-vector path with
+        // valid=false so that the full-mask shuffles below are executed by whole warps
+        const int k = min(tid >> 2, 25), j = tid & 3;
         const int sx = j >> 1, sy = (j & 1) * 4;  // sub-block (x word, y row offset); order as dx4/dy4
         int r[16];
-        bool valid = true;
+        bool valid = tid < 104;
         int penalty = 0;
         if (k < 25) {
             const int xi = k % 5, yi = k / 5;
