@@ -1,0 +1,83 @@
+"""End-to-end drop-in test: the UNMODIFIED reference host, once with the reference's own kernels
+on the CPU (oracle/_ref/libOpenCL.so.1) and once with our CUDA shim
+(vp8oclenc_b200/lib/libOpenCL.so.1), on the same synthetic clip and the same -h options.
+The two .ivf files must be byte-identical, and so must everything the host read back over the
+OpenCL boundary (vectors, parts, reference ids, coefficients, segment ids, reconstruction;
+the float SSIM within 1e-5 as the north star allows, in practice it is bit-identical too).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import _trace
+from _libs import ROOT
+
+torch = pytest.importorskip("torch")
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a CUDA device"),
+              pytest.mark.skipif(not _trace.have_host(), reason="reference host binary not built")]
+
+SHIM_DIR = os.path.join(ROOT, "vp8oclenc_b200", "lib")
+
+CASES = {
+    # name: (w, h, frames, host args)
+    "qcif": (176, 144, 14, ["-qmin", 20, "-qmax", 44, "-g", 12, "-altref-range", 4, "-partitions", 2, "-threads", 2]),
+    "cif": (352, 288, 20, ["-qmin", 24, "-qmax", 24, "-g", 60, "-altref-range", 5, "-partitions", 1, "-threads", 2]),
+    "cif_ssim": (352, 288, 12, ["-qmin", 10, "-qmax", 50, "-g", 30, "-altref-range", 3, "-partitions", 4, "-threads", 12,
+                                "-SSIM-target", "93"]),
+    "odd": (200, 120, 8, ["-qmin", 30, "-qmax", 30, "-g", 8, "-altref-range", 2, "-partitions", 8, "-threads", 12]),
+}
+
+
+def first_divergence(tr_a, tr_b):
+    fa, _ = _trace.split_frames(_trace.read_trace(tr_a))
+    fb, _ = _trace.split_frames(_trace.read_trace(tr_b))
+    for i, (a, b) in enumerate(zip(fa, fb)):
+        for (ka, na), (kb, nb) in zip(a["order"], b["order"]):
+            if (ka, na) != (kb, nb):
+                return "frame %d: call sequence differs: %s %s vs %s %s" % (i, ka, na, kb, nb)
+        for kind in ("r",):
+            for name in a[kind]:
+                for j, (pa, pb) in enumerate(zip(a[kind][name], b[kind].get(name, []))):
+                    if pa != pb:
+                        if name == "macroblock_SSIM_gpu":
+                            xa, xb = np.frombuffer(pa, np.float32), np.frombuffer(pb, np.float32)
+                            if np.allclose(xa, xb, atol=1e-5, rtol=0):
+                                continue
+                        x, y = np.frombuffer(pa, np.uint8), np.frombuffer(pb, np.uint8)
+                        k = int(np.flatnonzero(x != y)[0]) if x.size == y.size else -1
+                        return "frame %d: read #%d of %s differs at byte %d of %d" % (i, j, name, k, x.size)
+    return None
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_ivf_and_readbacks_identical(case, tmp_path):
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_y4m
+    w, h, frames, args = CASES[case]
+    d = str(tmp_path)
+    y4m = os.path.join(d, "clip.y4m")
+    gen_y4m.write_y4m(y4m, w, h, frames)
+    _trace.run_host(_trace.REF_DIR, d, y4m, os.path.join(d, "ref.ivf"), args, trace=os.path.join(d, "ref.trace"))
+    _trace.run_host(SHIM_DIR, d, y4m, os.path.join(d, "b200.ivf"), args, trace=os.path.join(d, "b200.trace"))
+    div = first_divergence(os.path.join(d, "ref.trace"), os.path.join(d, "b200.trace"))
+    assert div is None, div
+    a = open(os.path.join(d, "ref.ivf"), "rb").read()
+    b = open(os.path.join(d, "b200.ivf"), "rb").read()
+    assert len(a) > 32 + 12 * frames
+    assert a == b, "the .ivf bitstreams differ (sizes %d / %d)" % (len(a), len(b))
+
+
+def test_without_trace_same_bitstream(tmp_path):
+    """the trace forces synchronisation; the asynchronous path must give the same bytes"""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_y4m
+    w, h, frames, args = CASES["cif"]
+    d = str(tmp_path)
+    y4m = os.path.join(d, "clip.y4m")
+    gen_y4m.write_y4m(y4m, w, h, frames)
+    _trace.run_host(_trace.REF_DIR, d, y4m, os.path.join(d, "ref.ivf"), args)
+    _trace.run_host(SHIM_DIR, d, y4m, os.path.join(d, "b200.ivf"), args)
+    assert open(os.path.join(d, "ref.ivf"), "rb").read() == open(os.path.join(d, "b200.ivf"), "rb").read()

@@ -1,0 +1,596 @@
+// libOpenCL.so.1 of vp8oclenc_b200: the 28 OpenCL entry points the reference host calls
+// (include/CL/cl.h) implemented over the CUDA runtime and the kernel-level
+// engine of include/vp8b200.h.  The unmodified reference host (src/vp8enc.cpp, src/init.h,
+// src/inter_part.h, src/loop_filter.h, src/entropy_host.cpp ...) links against this library
+// instead of a vendor OpenCL and runs its inter-frame hot path on a B200.
+//
+//  * One platform with two devices, a "GPU" and a "CPU" one (src/init.h:119-150 needs both);
+//    both are the B200.  All queues of all contexts map to ONE CUDA stream: commands execute
+//    in program order, which is a legal schedule of the host's in-order queues.
+//  * clCreateProgramWithSource ignores the text; clCreateKernel(name) resolves to a native
+//    launcher; clSetKernelArg records the bytes; clEnqueueNDRangeKernel dispatches.
+//  * Kernels of the "GPU program" and the loop filter / filter mask of the "CPU program" are
+//    CUDA kernels.  The three boolean-coder kernels of the CPU program run on host threads
+//    (entropy_host.cpp).  There is no CPU fallback for anything else: without a CUDA device
+//    platform discovery fails.
+//  * Every buffer has a device allocation and, on demand, a pinned host mirror with validity
+//    flags; map/unmap and the host-executed kernels use the mirror, everything else the device.
+#include <CL/cl.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "entropy_host.h"
+#include "vp8b200.h"
+
+// ------------------------------------------------------------------------------------------
+struct _cl_platform_id { int unused; };
+struct _cl_device_id { cl_device_type type; };
+struct _cl_context { cl_device_id dev; };
+struct _cl_command_queue { cl_context ctx; };
+struct _cl_program { bool gpu_program; };
+
+struct _cl_mem {
+    unsigned index;
+    bool is_image;
+    size_t size;
+    int width, height;   // images
+    void *dev;           // device allocation (always)
+    void *host;          // pinned mirror (lazily)
+    bool dev_valid, host_valid;
+    bool mapped_for_write;
+};
+
+enum KernelId {
+    K_RESET_VECTORS, K_DOWNSAMPLE, K_SEARCH1, K_SEARCH2, K_SELECT_REF, K_PREDICT, K_PACK, K_DCT, K_WHT, K_IDCT,
+    K_SSIM_LUMA, K_SSIM_CHROMA, K_GATHER_SSIM,
+    K_FILTER_MASK, K_LF_LUMA, K_LF_CHROMA, K_COUNT_PROBS, K_NUM_DIV_DENOM, K_ENCODE_COEFFS, K_COUNT
+};
+struct KernelInfo { const char *name; bool gpu_program; int nargs; };
+static const KernelInfo kKernels[K_COUNT] = {
+    {"reset_vectors", true, 9}, {"downsample_x2", true, 4}, {"luma_search_1step", true, 8},
+    {"luma_search_2step", true, 7}, {"select_reference", true, 11}, {"prepare_predictors_and_residual", true, 9},
+    {"pack_8x8_into_16x16", true, 3}, {"dct4x4", true, 10}, {"wht4x4_iwht4x4", true, 6}, {"idct4x4", true, 9},
+    {"count_SSIM_luma", true, 6}, {"count_SSIM_chroma", true, 6}, {"gather_SSIM", true, 4},
+    {"prepare_filter_mask", false, 7}, {"loop_filter_frame_luma", false, 6}, {"loop_filter_frame_chroma", false, 6},
+    {"count_probs", false, 10}, {"num_div_denom", false, 3}, {"encode_coefficients", false, 11}};
+
+struct _cl_kernel {
+    KernelId id;
+    unsigned char bytes[12][16];
+    bool set[12];
+};
+
+// ------------------------------------------------------------------------------------------
+static _cl_platform_id g_platform;
+static _cl_device_id g_cpu_dev = {CL_DEVICE_TYPE_CPU};
+static _cl_device_id g_gpu_dev = {CL_DEVICE_TYPE_GPU};
+static cudaStream_t g_stream = nullptr;
+static bool g_cuda_ok = false, g_cuda_tried = false;
+static char g_dev_name[256] = "no CUDA device";
+static int g_sm_count = 0;
+static unsigned g_next_index = 0;
+static FILE *g_trace = nullptr;
+
+// deferred luma / chroma-U loop filters, so that the three planes go out as ONE launch
+struct PendingLF { cl_mem frame, seg, mask, sd; int w, h; };
+static PendingLF g_pending_lf[2];
+static int g_num_pending_lf = 0;
+
+static bool cuda_init() {
+    if (g_cuda_tried) return g_cuda_ok;
+    g_cuda_tried = true;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n < 1) {
+        fprintf(stderr, "vp8oclenc_b200: no CUDA device -- this OpenCL shim has no CPU fallback\n");
+        return false;
+    }
+    const char *dev_env = getenv("VP8B200_DEVICE");
+    if (dev_env) cudaSetDevice(atoi(dev_env));
+    if (cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking) != cudaSuccess) return false;
+    vp8b200_device_info(g_dev_name, sizeof(g_dev_name), &g_sm_count, nullptr, nullptr);
+    const char *tr = getenv("VP8CL_TRACE");
+    if (tr && *tr) g_trace = fopen(tr, "wb");
+    g_cuda_ok = true;
+    return true;
+}
+
+static void trace_rec(unsigned kind, unsigned idx, size_t off, size_t size, const void *payload) {
+    if (!g_trace) return;
+    unsigned long long hdr[2] = {(unsigned long long)off, (unsigned long long)size};
+    fwrite(&kind, 4, 1, g_trace);
+    fwrite(&idx, 4, 1, g_trace);
+    fwrite(hdr, 8, 2, g_trace);
+    if (payload) fwrite(payload, 1, size, g_trace);
+}
+
+static cl_int put_info(const void *src, size_t n, size_t cap, void *dst, size_t *ret) {
+    if (ret) *ret = n;
+    if (dst) {
+        if (cap < n) return CL_INVALID_VALUE;
+        memcpy(dst, src, n);
+    }
+    return CL_SUCCESS;
+}
+
+static inline cl_int cuda_rc(cudaError_t e) { return e == cudaSuccess ? CL_SUCCESS : CL_OUT_OF_RESOURCES; }
+
+// ---- buffer coherence ---------------------------------------------------------------------
+static bool ensure_host_alloc(cl_mem m) {
+    if (m->host) return true;
+    if (cudaHostAlloc(&m->host, m->size ? m->size : 1, cudaHostAllocDefault) != cudaSuccess) return false;
+    m->host_valid = false;
+    return true;
+}
+// device copy up to date (uploads a host-side modification on the stream)
+static void *dev_ptr(cl_mem m, bool will_write) {
+    if (!m) return nullptr;
+    if (!m->dev_valid) {
+        cudaMemcpyAsync(m->dev, m->host, m->size, cudaMemcpyHostToDevice, g_stream);
+        m->dev_valid = true;
+    }
+    if (will_write) m->host_valid = false;
+    return m->dev;
+}
+// host mirror up to date (downloads and waits)
+static void *host_ptr(cl_mem m, bool will_write, bool discard = false) {
+    if (!m) return nullptr;
+    if (!ensure_host_alloc(m)) return nullptr;
+    if (!m->host_valid) {
+        if (!discard) {
+            cudaMemcpyAsync(m->host, m->dev, m->size, cudaMemcpyDeviceToHost, g_stream);
+            cudaStreamSynchronize(g_stream);
+        }
+        m->host_valid = true;
+    }
+    if (will_write) m->dev_valid = false;
+    return m->host;
+}
+
+static void launch_lf(int count);
+static inline void flush_pending() {
+    if (g_num_pending_lf) launch_lf(g_num_pending_lf);
+}
+
+// ---- kernel argument access ----------------------------------------------------------------
+static inline cl_mem arg_mem(cl_kernel k, int i) {
+    cl_mem m;
+    memcpy(&m, k->bytes[i], sizeof(m));
+    return m;
+}
+static inline int arg_int(cl_kernel k, int i) {
+    int v;
+    memcpy(&v, k->bytes[i], 4);
+    return v;
+}
+static inline float arg_float(cl_kernel k, int i) {
+    float v;
+    memcpy(&v, k->bytes[i], 4);
+    return v;
+}
+template <class T> static inline T *in(cl_kernel k, int i) { return (T *)dev_ptr(arg_mem(k, i), false); }
+template <class T> static inline T *out(cl_kernel k, int i) { return (T *)dev_ptr(arg_mem(k, i), true); }
+template <class T> static inline T *hin(cl_kernel k, int i) { return (T *)host_ptr(arg_mem(k, i), false); }
+template <class T> static inline T *hout(cl_kernel k, int i) { return (T *)host_ptr(arg_mem(k, i), true); }
+
+static void launch_lf(int count) {
+    // count pending planes (luma [, chroma U]) that could not be fused: launch them one by one
+    for (int i = 0; i < count; ++i) {
+        PendingLF &p = g_pending_lf[i];
+        vp8b200_loop_filter_frame(g_stream, (uint8_t *)dev_ptr(p.frame, true), (const int32_t *)dev_ptr(p.seg, false),
+                                  (const int32_t *)dev_ptr(p.mask, false),
+                                  (const vp8b200_segment_data *)dev_ptr(p.sd, false), p.w, p.h, i == 0 ? 16 : 8);
+    }
+    g_num_pending_lf = 0;
+}
+
+static cl_int dispatch(cl_kernel k, size_t global) {
+    void *s = g_stream;
+    int rc = 0;
+    if (k->id != K_LF_CHROMA) flush_pending();
+    switch (k->id) {
+        case K_RESET_VECTORS:
+            rc = vp8b200_reset_vectors(s, out<int16_t>(k, 0), out<int16_t>(k, 1), out<int16_t>(k, 2), out<int16_t>(k, 3),
+                                       out<int16_t>(k, 4), out<int16_t>(k, 5), out<int32_t>(k, 6), out<int32_t>(k, 7),
+                                       out<int32_t>(k, 8), (int)global);
+            break;
+        case K_DOWNSAMPLE:
+            rc = vp8b200_downsample_x2(s, in<uint8_t>(k, 0), out<uint8_t>(k, 1), arg_int(k, 2), arg_int(k, 3));
+            break;
+        case K_SEARCH1:
+            rc = vp8b200_luma_search_1step(s, in<uint8_t>(k, 0), in<uint8_t>(k, 1), in<int16_t>(k, 2), out<int16_t>(k, 3),
+                                           arg_int(k, 4), arg_int(k, 5), arg_int(k, 6), arg_int(k, 7));
+            break;
+        case K_SEARCH2:
+            rc = vp8b200_luma_search_2step(s, in<uint8_t>(k, 0), in<uint8_t>(k, 1), in<int16_t>(k, 2), out<int16_t>(k, 3),
+                                           out<int32_t>(k, 4), arg_int(k, 5), arg_int(k, 6));
+            break;
+        case K_SELECT_REF: {
+            const int width = arg_int(k, 8);
+            const int mbs = (int)(arg_mem(k, 6)->size / 4);
+            const int height = (mbs / (width / 16)) * 16;
+            rc = vp8b200_select_reference(s, in<int16_t>(k, 0), in<int16_t>(k, 1), in<int16_t>(k, 2), in<int32_t>(k, 3),
+                                          in<int32_t>(k, 4), in<int32_t>(k, 5), out<int32_t>(k, 6), out<int16_t>(k, 7),
+                                          width, height, arg_int(k, 9), arg_int(k, 10));
+            break;
+        }
+        case K_PREDICT: {
+            cl_mem img = arg_mem(k, 1);
+            rc = vp8b200_prepare_predictors_and_residual(s, in<uint8_t>(k, 0), in<uint8_t>(k, 1), out<uint8_t>(k, 2),
+                                                         out<int16_t>(k, 3), in<int32_t>(k, 4), in<int16_t>(k, 5),
+                                                         arg_int(k, 6), img->height, arg_int(k, 7), arg_int(k, 8));
+            break;
+        }
+        case K_PACK:
+            rc = vp8b200_pack_8x8_into_16x16(s, in<int16_t>(k, 0), out<int32_t>(k, 1), out<float>(k, 2), (int)global);
+            break;
+        case K_DCT: {
+            const int width = arg_int(k, 5);
+            const int height = (int)(global / (size_t)(width / 4)) * 4;
+            rc = vp8b200_dct4x4(s, in<int16_t>(k, 0), out<int16_t>(k, 1), out<int32_t>(k, 2), in<int32_t>(k, 3),
+                                in<float>(k, 4), width, height, in<vp8b200_segment_data>(k, 6), arg_int(k, 7),
+                                arg_float(k, 8), arg_int(k, 9));
+            break;
+        }
+        case K_WHT:
+            rc = vp8b200_wht4x4_iwht4x4(s, out<int16_t>(k, 0), out<int32_t>(k, 2), in<int32_t>(k, 3),
+                                        in<vp8b200_segment_data>(k, 4), arg_int(k, 5), (int)global);
+            break;
+        case K_IDCT: {
+            const int width = arg_int(k, 5);
+            const int height = (int)(global / (size_t)(width / 4)) * 4;
+            rc = vp8b200_idct4x4(s, out<uint8_t>(k, 0), in<uint8_t>(k, 1), in<int16_t>(k, 2), in<int32_t>(k, 3),
+                                 in<int32_t>(k, 4), width, height, in<vp8b200_segment_data>(k, 6), arg_int(k, 7),
+                                 arg_int(k, 8));
+            break;
+        }
+        case K_SSIM_LUMA:
+        case K_SSIM_CHROMA: {
+            const int n = k->id == K_SSIM_LUMA ? 16 : 8;
+            const int width = arg_int(k, 4);
+            const int height = (int)(global / (size_t)(width / n)) * n;
+            rc = vp8b200_count_SSIM(s, in<uint8_t>(k, 0), in<uint8_t>(k, 1), in<int32_t>(k, 2), out<float>(k, 3), width,
+                                    height, arg_int(k, 5), n);
+            break;
+        }
+        case K_GATHER_SSIM:
+            rc = vp8b200_gather_SSIM(s, in<float>(k, 0), in<float>(k, 1), in<float>(k, 2), out<float>(k, 3), (int)global);
+            break;
+        case K_FILTER_MASK:
+            rc = vp8b200_prepare_filter_mask(s, in<int16_t>(k, 0), out<int32_t>(k, 1), in<int32_t>(k, 2),
+                                             out<int32_t>(k, 3), arg_int(k, 4), arg_int(k, 5));
+            break;
+        case K_LF_LUMA:
+            g_pending_lf[0] = {arg_mem(k, 0), arg_mem(k, 1), arg_mem(k, 2), arg_mem(k, 3), arg_int(k, 4), arg_int(k, 5)};
+            g_num_pending_lf = 1;
+            break;
+        case K_LF_CHROMA: {
+            PendingLF p = {arg_mem(k, 0), arg_mem(k, 1), arg_mem(k, 2), arg_mem(k, 3), arg_int(k, 4), arg_int(k, 5)};
+            const PendingLF &y = g_pending_lf[0];
+            const bool same = g_num_pending_lf >= 1 && p.seg == y.seg && p.mask == y.mask && p.sd == y.sd &&
+                              p.w * 2 == y.w && p.h * 2 == y.h;
+            if (same && g_num_pending_lf == 1) {
+                g_pending_lf[1] = p;
+                g_num_pending_lf = 2;
+            } else if (same && g_num_pending_lf == 2) {
+                const PendingLF &u = g_pending_lf[1];
+                rc = vp8b200_loop_filter_planes(s, (uint8_t *)dev_ptr(y.frame, true), (uint8_t *)dev_ptr(u.frame, true),
+                                                (uint8_t *)dev_ptr(p.frame, true), (const int32_t *)dev_ptr(y.seg, false),
+                                                (const int32_t *)dev_ptr(y.mask, false),
+                                                (const vp8b200_segment_data *)dev_ptr(y.sd, false), y.w, y.h);
+                g_num_pending_lf = 0;
+            } else {
+                flush_pending();
+                rc = vp8b200_loop_filter_frame(s, (uint8_t *)dev_ptr(p.frame, true), (const int32_t *)dev_ptr(p.seg, false),
+                                               (const int32_t *)dev_ptr(p.mask, false),
+                                               (const vp8b200_segment_data *)dev_ptr(p.sd, false), p.w, p.h, 8);
+            }
+            break;
+        }
+        case K_COUNT_PROBS:
+            vp8host::count_probs(hin<int16_t>(k, 0), hin<int32_t>(k, 1), hin<int32_t>(k, 2), hout<uint32_t>(k, 3),
+                                 hout<uint32_t>(k, 4), hout<uint8_t>(k, 5), arg_int(k, 6), arg_int(k, 7), arg_int(k, 8));
+            break;
+        case K_NUM_DIV_DENOM:
+            vp8host::num_div_denom(hout<uint32_t>(k, 0), hin<uint32_t>(k, 1), arg_int(k, 2));
+            break;
+        case K_ENCODE_COEFFS:
+            vp8host::encode_coefficients(hin<int16_t>(k, 0), hin<int32_t>(k, 1), hin<int32_t>(k, 2), hout<uint8_t>(k, 3),
+                                         hout<int32_t>(k, 4), hin<uint8_t>(k, 5), hin<uint32_t>(k, 6), arg_int(k, 7),
+                                         arg_int(k, 8), arg_int(k, 9), arg_int(k, 10));
+            break;
+        default:
+            return CL_INVALID_KERNEL;
+    }
+    return rc == 0 ? CL_SUCCESS : CL_OUT_OF_RESOURCES;
+}
+
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+cl_int clGetPlatformIDs(cl_uint num_entries, cl_platform_id *platforms, cl_uint *num_platforms) {
+    if (!cuda_init()) {
+        if (num_platforms) *num_platforms = 0;
+        return CL_DEVICE_NOT_FOUND;
+    }
+    if (num_platforms) *num_platforms = 1;
+    if (platforms && num_entries >= 1) platforms[0] = &g_platform;
+    return CL_SUCCESS;
+}
+
+cl_int clGetPlatformInfo(cl_platform_id, cl_platform_info, size_t cap, void *dst, size_t *ret) {
+    static const char name[] = "vp8oclenc_b200 (CUDA sm_100a engine behind the OpenCL boundary)";
+    return put_info(name, sizeof(name), cap, dst, ret);
+}
+
+cl_int clGetDeviceIDs(cl_platform_id, cl_device_type type, cl_uint num_entries, cl_device_id *devices,
+                      cl_uint *num_devices) {
+    if (!cuda_init()) return CL_DEVICE_NOT_FOUND;
+    cl_device_id found[2];
+    cl_uint n = 0;
+    if (type & CL_DEVICE_TYPE_CPU) found[n++] = &g_cpu_dev;
+    if (type & CL_DEVICE_TYPE_GPU) found[n++] = &g_gpu_dev;
+    if (num_devices) *num_devices = n;
+    if (n == 0) return CL_DEVICE_NOT_FOUND;
+    for (cl_uint i = 0; devices && i < n && i < num_entries; ++i) devices[i] = found[i];
+    return CL_SUCCESS;
+}
+
+cl_int clGetDeviceInfo(cl_device_id dev, cl_device_info what, size_t cap, void *dst, size_t *ret) {
+    char buf[320];
+    switch (what) {
+        case CL_DEVICE_NAME:
+            snprintf(buf, sizeof(buf), "%s (%s role)", g_dev_name, dev->type == CL_DEVICE_TYPE_GPU ? "GPU" : "CPU-program");
+            return put_info(buf, strlen(buf) + 1, cap, dst, ret);
+        case CL_DEVICE_VERSION: return put_info("OpenCL 1.1 subset over CUDA", 28, cap, dst, ret);
+        case CL_DRIVER_VERSION: return put_info(vp8b200_version(), strlen(vp8b200_version()) + 1, cap, dst, ret);
+        case CL_DEVICE_OPENCL_C_VERSION: return put_info("none (native sm_100a kernels)", 30, cap, dst, ret);
+        case CL_DEVICE_MAX_COMPUTE_UNITS: { cl_uint v = (cl_uint)g_sm_count; return put_info(&v, sizeof(v), cap, dst, ret); }
+        case CL_DEVICE_MAX_WORK_GROUP_SIZE: { size_t v = 1024; return put_info(&v, cap < sizeof(v) ? cap : sizeof(v), cap, dst, ret); }
+        case CL_DEVICE_TYPE: return put_info(&dev->type, sizeof(dev->type), cap, dst, ret);
+        default: return CL_INVALID_VALUE;
+    }
+}
+
+cl_context clCreateContext(const cl_context_properties *, cl_uint n, const cl_device_id *devs,
+                           void (*)(const char *, const void *, size_t, void *), void *, cl_int *err) {
+    const bool ok = n >= 1 && devs && cuda_init();
+    if (err) *err = ok ? CL_SUCCESS : CL_INVALID_VALUE;
+    return ok ? new _cl_context{devs[0]} : nullptr;
+}
+cl_int clReleaseContext(cl_context c) { delete c; return CL_SUCCESS; }
+
+cl_command_queue clCreateCommandQueue(cl_context ctx, cl_device_id, cl_command_queue_properties, cl_int *err) {
+    if (err) *err = CL_SUCCESS;
+    return new _cl_command_queue{ctx};
+}
+cl_int clReleaseCommandQueue(cl_command_queue q) {
+    flush_pending();
+    cudaStreamSynchronize(g_stream);
+    delete q;
+    return CL_SUCCESS;
+}
+
+static cl_mem new_mem(size_t size, bool image, int w, int h, bool want_host, cl_int *err) {
+    _cl_mem *m = new _cl_mem();
+    m->index = g_next_index++;
+    m->is_image = image;
+    m->size = size;
+    m->width = w;
+    m->height = h;
+    m->host = nullptr;
+    m->mapped_for_write = false;
+    // zero-filled like the reference runtime's calloc: block 24 of never-16x16 macroblocks and the
+    // nets of never-searched blocks are read before they are first written (Q4, Q9)
+    cudaError_t e = cudaMalloc(&m->dev, size ? size : 1);
+    if (e == cudaSuccess) e = cudaMemsetAsync(m->dev, 0, size ? size : 1, g_stream);
+    m->dev_valid = true;
+    m->host_valid = false;
+    if (e == cudaSuccess && want_host) {
+        if (!ensure_host_alloc(m)) e = cudaErrorMemoryAllocation;
+        else { memset(m->host, 0, size); m->host_valid = true; }
+    }
+    if (err) *err = e == cudaSuccess ? CL_SUCCESS : CL_MEM_OBJECT_ALLOCATION_FAILURE;
+    trace_rec(image ? 1 : 0, m->index, image ? (size_t)w : 0, image ? (size_t)h : size, nullptr);
+    return m;
+}
+
+cl_mem clCreateBuffer(cl_context, cl_mem_flags flags, size_t size, void *host_ptr_in, cl_int *err) {
+    cl_mem m = new_mem(size, false, 0, 0, (flags & CL_MEM_ALLOC_HOST_PTR) != 0, err);
+    if (host_ptr_in && (flags & (CL_MEM_COPY_HOST_PTR | CL_MEM_USE_HOST_PTR)))
+        cudaMemcpyAsync(m->dev, host_ptr_in, size, cudaMemcpyHostToDevice, g_stream);
+    return m;
+}
+
+cl_mem clCreateImage2D(cl_context, cl_mem_flags, const cl_image_format *fmt, size_t w, size_t h, size_t, void *,
+                       cl_int *err) {
+    if (!fmt || fmt->image_channel_order != CL_R || fmt->image_channel_data_type != CL_UNSIGNED_INT8) {
+        if (err) *err = CL_INVALID_IMAGE_FORMAT_DESCRIPTOR;
+        return nullptr;
+    }
+    return new_mem(w * h, true, (int)w, (int)h, false, err);
+}
+
+cl_int clReleaseMemObject(cl_mem m) {
+    if (!m) return CL_INVALID_MEM_OBJECT;
+    flush_pending();
+    cudaStreamSynchronize(g_stream);
+    cudaFree(m->dev);
+    if (m->host) cudaFreeHost(m->host);
+    delete m;
+    return CL_SUCCESS;
+}
+
+cl_program clCreateProgramWithSource(cl_context ctx, cl_uint, const char **, const size_t *, cl_int *err) {
+    if (err) *err = CL_SUCCESS;
+    // which of the two programs this is follows from the device its context was made for
+    return new _cl_program{ctx->dev->type == CL_DEVICE_TYPE_GPU};
+}
+cl_int clBuildProgram(cl_program, cl_uint, const cl_device_id *, const char *, void (*)(cl_program, void *), void *) {
+    return CL_SUCCESS;
+}
+cl_int clGetProgramBuildInfo(cl_program, cl_device_id, cl_program_build_info, size_t cap, void *dst, size_t *ret) {
+    return put_info("", 1, cap, dst, ret);
+}
+cl_int clReleaseProgram(cl_program p) { delete p; return CL_SUCCESS; }
+
+cl_kernel clCreateKernel(cl_program prog, const char *name, cl_int *err) {
+    for (int i = 0; i < K_COUNT; ++i)
+        if (kKernels[i].gpu_program == prog->gpu_program && !strcmp(kKernels[i].name, name)) {
+            _cl_kernel *k = new _cl_kernel();
+            memset(k, 0, sizeof(*k));
+            k->id = (KernelId)i;
+            if (err) *err = CL_SUCCESS;
+            return k;
+        }
+    // normal_loop_filter_MBH/MBV and the GPU-program prepare_filter_mask (-loop-filter-on-gpu) are dead
+    // code in the reference's src/GPU_kernels.cl as well: not provided
+    if (err) *err = CL_INVALID_KERNEL_NAME;
+    return nullptr;
+}
+cl_int clReleaseKernel(cl_kernel k) { delete k; return CL_SUCCESS; }
+
+cl_int clSetKernelArg(cl_kernel k, cl_uint idx, size_t size, const void *value) {
+    if (!k) return CL_INVALID_KERNEL;
+    if ((int)idx >= kKernels[k->id].nargs) return CL_INVALID_ARG_INDEX;
+    if (size > 16) return CL_INVALID_ARG_SIZE;
+    memset(k->bytes[idx], 0, 16);
+    if (value) memcpy(k->bytes[idx], value, size);
+    k->set[idx] = true;
+    return CL_SUCCESS;
+}
+
+cl_int clEnqueueNDRangeKernel(cl_command_queue, cl_kernel k, cl_uint dim, const size_t *, const size_t *gsz,
+                              const size_t *, cl_uint, const cl_event *, cl_event *) {
+    if (!k) return CL_INVALID_KERNEL;
+    if (dim != 1 || !gsz) return CL_INVALID_WORK_DIMENSION;
+    for (int i = 0; i < kKernels[k->id].nargs; ++i)
+        if (!k->set[i]) return CL_INVALID_KERNEL_ARGS;
+    return dispatch(k, gsz[0]);
+}
+
+cl_int clEnqueueReadBuffer(cl_command_queue, cl_mem m, cl_bool blocking, size_t off, size_t size, void *ptr, cl_uint,
+                           const cl_event *, cl_event *) {
+    if (!m || off + size > m->size) return CL_INVALID_VALUE;
+    flush_pending();
+    if (m->dev_valid) {
+        cudaError_t e = cudaMemcpyAsync(ptr, (char *)m->dev + off, size, cudaMemcpyDeviceToHost, g_stream);
+        if (e != cudaSuccess) return cuda_rc(e);
+        if (blocking || g_trace) cudaStreamSynchronize(g_stream);
+    } else {
+        memcpy(ptr, (char *)m->host + off, size);
+    }
+    trace_rec(3, m->index, off, size, ptr);
+    return CL_SUCCESS;
+}
+
+cl_int clEnqueueWriteBuffer(cl_command_queue, cl_mem m, cl_bool blocking, size_t off, size_t size, const void *ptr,
+                            cl_uint, const cl_event *, cl_event *) {
+    if (!m || off + size > m->size) return CL_INVALID_VALUE;
+    flush_pending();
+    trace_rec(2, m->index, off, size, ptr);
+    if (m->host && ptr == (char *)m->host + off) {
+        // the host writes a mapped buffer onto itself (intra_transform(), src/intra_part.h:1122-1124)
+        m->host_valid = true;
+        m->dev_valid = false;
+        return CL_SUCCESS;
+    }
+    if (!m->dev_valid) {
+        if (off == 0 && size == m->size) {
+            m->dev_valid = true;  // fully overwritten on the device below
+        } else {
+            // the current contents live in the host mirror (a buffer the host-executed entropy kernels
+            // work on, e.g. coeff_probs): keep it there
+            memcpy((char *)m->host + off, ptr, size);
+            return CL_SUCCESS;
+        }
+    }
+    cudaError_t e = cudaMemcpyAsync((char *)m->dev + off, ptr, size, cudaMemcpyHostToDevice, g_stream);
+    m->host_valid = false;
+    if (blocking) cudaStreamSynchronize(g_stream);
+    return cuda_rc(e);
+}
+
+cl_int clEnqueueCopyBuffer(cl_command_queue, cl_mem s, cl_mem d, size_t so, size_t dof, size_t size, cl_uint,
+                           const cl_event *, cl_event *) {
+    if (!s || !d || so + size > s->size || dof + size > d->size) return CL_INVALID_VALUE;
+    flush_pending();
+    const char *sp = (const char *)dev_ptr(s, false);
+    char *dp = (char *)dev_ptr(d, true);
+    return cuda_rc(cudaMemcpyAsync(dp + dof, sp + so, size, cudaMemcpyDeviceToDevice, g_stream));
+}
+
+cl_int clEnqueueWriteImage(cl_command_queue, cl_mem img, cl_bool blocking, const size_t *origin, const size_t *region,
+                           size_t row_pitch, size_t, const void *ptr, cl_uint, const cl_event *, cl_event *) {
+    if (!img || !img->is_image) return CL_INVALID_MEM_OBJECT;
+    flush_pending();
+    const size_t pitch = row_pitch ? row_pitch : region[0];
+    char *dst = (char *)dev_ptr(img, true) + origin[1] * img->width + origin[0];
+    cudaError_t e = cudaMemcpy2DAsync(dst, img->width, ptr, pitch, region[0], region[1], cudaMemcpyHostToDevice, g_stream);
+    if (pitch == region[0]) trace_rec(4, img->index, 0, region[0] * region[1], ptr);
+    if (blocking) cudaStreamSynchronize(g_stream);
+    return cuda_rc(e);
+}
+
+cl_int clEnqueueCopyImage(cl_command_queue, cl_mem s, cl_mem d, const size_t *so, const size_t *dor,
+                          const size_t *region, cl_uint, const cl_event *, cl_event *) {
+    if (!s || !d || !s->is_image || !d->is_image) return CL_INVALID_MEM_OBJECT;
+    flush_pending();
+    const char *sp = (const char *)dev_ptr(s, false) + so[1] * s->width + so[0];
+    char *dp = (char *)dev_ptr(d, true) + dor[1] * d->width + dor[0];
+    return cuda_rc(cudaMemcpy2DAsync(dp, d->width, sp, s->width, region[0], region[1], cudaMemcpyDeviceToDevice, g_stream));
+}
+
+void *clEnqueueMapBuffer(cl_command_queue, cl_mem m, cl_bool, cl_map_flags flags, size_t off, size_t size, cl_uint,
+                         const cl_event *, cl_event *, cl_int *err) {
+    if (!m || off + size > m->size) {
+        if (err) *err = CL_INVALID_VALUE;
+        return nullptr;
+    }
+    flush_pending();
+    const bool discard = (flags & CL_MAP_WRITE_INVALIDATE_REGION) && off == 0 && size == m->size;
+    const bool writes = (flags & (CL_MAP_WRITE | CL_MAP_WRITE_INVALIDATE_REGION)) != 0;
+    char *p = (char *)host_ptr(m, false, discard);
+    if (!p) {
+        if (err) *err = CL_MAP_FAILURE;
+        return nullptr;
+    }
+    // in-flight asynchronous reads into other mapped buffers must have landed before the host looks
+    cudaStreamSynchronize(g_stream);
+    m->mapped_for_write = writes;
+    if (writes) m->dev_valid = false;  // the host owns the contents until the unmap
+    if (err) *err = CL_SUCCESS;
+    return p + off;
+}
+
+cl_int clEnqueueUnmapMemObject(cl_command_queue, cl_mem m, void *, cl_uint, const cl_event *, cl_event *) {
+    if (!m) return CL_INVALID_MEM_OBJECT;
+    if (g_trace) {
+        cudaStreamSynchronize(g_stream);
+        trace_rec(5, m->index, 0, m->size, m->host);
+    }
+    if (m->mapped_for_write) {
+        // asynchronous device->host reads that targeted this mapping (the host reads the coefficient
+        // and reconstruction buffers straight into mapped memory, src/vp8enc.cpp:422-433) are ordered
+        // before any later upload on the same stream
+        m->host_valid = true;
+        m->dev_valid = false;
+        m->mapped_for_write = false;
+    }
+    return CL_SUCCESS;
+}
+
+cl_int clFlush(cl_command_queue) {
+    flush_pending();
+    return CL_SUCCESS;
+}
+cl_int clFinish(cl_command_queue) {
+    flush_pending();
+    if (g_trace) fflush(g_trace);
+    return cuda_rc(cudaStreamSynchronize(g_stream));
+}
+
+}  // extern "C"
