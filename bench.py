@@ -1,0 +1,372 @@
+#!/usr/bin/env python3
+"""bench.py -- encoded frames/s of vp8oclenc's inter-frame hot path on B200 (BASELINE.json).
+
+A "step" is one encoded inter frame: pyramid + hierarchical motion search over LAST / GOLDEN /
+ALTREF, reference selection, six-tap prediction, DCT/WHT/quantise, dequantise/reconstruct,
+SSIM, filter mask and the normal loop filter, on a synthetic 1080p clip (tools/gen_y4m.py).
+
+  value     frames/s of the CUDA engine with every input frame already resident in HBM
+            (vp8b200_engine_inter_frame + vp8b200_engine_loop_filter), CUDA events, L2 flushed
+            between timed steps
+  e2e       frames/s of the UNMODIFIED reference host program running against our OpenCL shim
+            (vp8oclenc_b200/lib/libOpenCL.so.1) on the same clip: Y4M in, IVF out, every
+            host<->device copy, the host's intra/entropy/bitstream work and file I/O included
+  roofline  the dominant kernel (quarter-pel motion search) against the measured integer
+            issue rate of the device, plus an HBM line for the loop filter
+  cpu_baseline / --impl reference
+            the reference itself (its own host + its own .cl kernels compiled for the CPU,
+            oracle/_ref) on a bounded sample of the same clip on all host cores
+
+Multi-GPU (torchrun, one rank per GPU): independent keyframe-delimited segments per GPU, no
+collective on the data path ("scaling": "weak").
+"""
+import argparse
+import ctypes
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WIDTH, HEIGHT = 1920, 1080          # configs[1] of BASELINE.json
+WRK_W, WRK_H = 1920, 1088           # padded to macroblocks as the host does (src/init.h:381-386)
+ENC_ARGS = ["-qmin", "24", "-qmax", "24", "-g", "150", "-altref-range", "5", "-partitions", "8", "-threads", "12"]
+ALTREF_RANGE = 5
+QI = (24, 24, 24, 24)
+
+GPU_STUB = "// vp8oclenc_b200 placeholder: kernels are built into libOpenCL.so.1; program = GPU (luma_search_1step)\n"
+CPU_STUB = "// vp8oclenc_b200 placeholder: kernels are built into libOpenCL.so.1; program = CPU (encode_coefficients)\n"
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu_index, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        exe = shutil.which("nvidia-smi")
+        if not exe:
+            return
+        self.proc = subprocess.Popen([exe, "-i", str(self.gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                      "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        self.t = threading.Thread(target=self._pump, daemon=True)
+        self.t.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_encoder_timed(host_bin, lib_dir, workdir, y4m, ivf, frames_total, env_extra=None):
+    """runs the reference host program and timestamps its per-frame "-print-info" lines.
+    returns (list of completion times per frame, stdout)"""
+    os.makedirs(workdir, exist_ok=True)
+    with open(os.path.join(workdir, "GPU_kernels.cl"), "w") as f:
+        f.write(GPU_STUB)
+    with open(os.path.join(workdir, "CPU_kernels.cl"), "w") as f:
+        f.write(CPU_STUB)
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = lib_dir + os.pathsep + env.get("LD_LIBRARY_PATH", "")
+    env.update(env_extra or {})
+    cmd = [host_bin, "-i", y4m, "-o", ivf] + ENC_ARGS + ["-print-info"]
+    stdbuf = shutil.which("stdbuf")
+    if stdbuf:
+        cmd = [stdbuf, "-oL"] + cmd
+    t0 = time.perf_counter()
+    p = subprocess.Popen(cmd, cwd=workdir, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    stamps, out = [], []
+    for line in p.stdout:
+        out.append(line)
+        if "br=" in line:  # printed once per finished frame (src/vp8enc.cpp:482-483)
+            stamps.append(time.perf_counter() - t0)
+    p.wait()
+    if p.returncode != 777 % 256:
+        sys.stderr.write("".join(out[-30:]))
+        raise RuntimeError("encoder exited with %d" % p.returncode)
+    if len(stamps) != frames_total:
+        raise RuntimeError("expected %d frame lines, saw %d" % (frames_total, len(stamps)))
+    return stamps, "".join(out)
+
+
+def reference_arm(args, tmp):
+    """the reference's own CPU implementation: its host + its .cl kernels compiled for the CPU
+    (oracle/_ref), all host cores (OpenMP), on a bounded sample of the same workload"""
+    import gen_y4m
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    host_bin = os.path.join(ref_dir, "vp8enc")
+    if not os.path.exists(host_bin) or not os.path.exists(os.path.join(ref_dir, "libOpenCL.so.1")):
+        return None
+    warm = max(1, min(args.warmup, 2))
+    steps = max(1, min(args.steps, args.ref_frames))
+    n = 1 + warm + steps
+    y4m = os.path.join(tmp, "ref_clip.y4m")
+    gen_y4m.write_y4m(y4m, WIDTH, HEIGHT, n)
+    stamps, _ = run_encoder_timed(host_bin, ref_dir, os.path.join(tmp, "ref_run"), y4m, os.path.join(tmp, "ref.ivf"), n)
+    dt = stamps[-1] - stamps[warm]  # frame 0 is the key frame, then `warm` untimed inter frames
+    fps = steps / dt
+    return {"value": fps, "unit": "frames/s", "cores": os.cpu_count(), "kind": "reference",
+            "sample": "%d inter frames of the 1080p clip after 1 key + %d warm-up frames; unmodified reference host with "
+                      "its own .cl kernels compiled for the CPU (oracle/_ref), OpenMP over work-items" % (steps, warm),
+            "ms_per_step": 1000.0 * dt / steps, "steps": steps, "warmup": warm}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ref-frames", type=int, default=6, help="timed frames of the CPU reference sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    tmp = tempfile.mkdtemp(prefix="vp8bench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    config = {"workload": "1920x1080 synthetic YUV420 (tools/gen_y4m.py), padded to 1920x1088, LAST+GOLDEN+ALTREF, "
+                          "q=24, altref-range 5, 8 partitions, loop filter on the GPU",
+              "frame_size": [WIDTH, HEIGHT], "segments_per_gpu": 1}
+    try:
+        if args.impl == "reference":
+            if rank != 0:
+                return 0
+            r = reference_arm(args, tmp)
+            if r is None:
+                print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref (compiled reference) is not present"}))
+                return 0
+            line = {"impl": "reference", "metric": "encoded frames/s at 1080p", "value": r["value"], "unit": "frames/s",
+                    "n_gpus": args.gpus, "steps": r["steps"], "warmup": r["warmup"], "ms_per_step": r["ms_per_step"],
+                    "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32",
+                    "data": "synthetic", "config": config,
+                    "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                    "e2e": {"value": r["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            print(json.dumps(line))
+            return 0
+        return b200_arm(args, rank, world, local_rank, tmp, config)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def b200_arm(args, rank, world, local_rank, tmp, config):
+    import numpy as np
+    import torch
+    import gen_y4m
+    from vp8oclenc_b200 import host as eng
+    from vp8oclenc_b200.hostlogic import HostState, make_segment_data
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: vp8oclenc_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    K, W = args.steps, args.warmup
+    M = (WRK_W // 16) * (WRK_H // 16)
+    N = WRK_W * WRK_H
+
+    # ---- synthetic frames: every rank encodes its own keyframe-delimited segment -----------------
+    nframes = 1 + W + K
+    clip = gen_y4m.Clip(WRK_W, WRK_H)
+    first = rank * nframes
+    host_frames = [clip.frame(first + i) for i in range(nframes)]
+    dev_frames = [[torch.from_numpy(np.ascontiguousarray(p)).cuda() for p in f] for f in host_frames]
+    sd = make_segment_data(QI)
+
+    e = eng.Engine(WRK_W, WRK_H)
+    stream_ptr = e.stream
+    ext_stream = torch.cuda.ExternalStream(stream_ptr)
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    torch.cuda.synchronize()
+    state = HostState(10 ** 6, ALTREF_RANGE)
+    state.next_frame()
+    e.set_reconstruction(*dev_frames[0])  # the key frame's reconstruction seeds LAST/GOLDEN/ALTREF
+
+    def step(i):
+        st = state.next_frame()
+        y, u, v = dev_frames[i]
+        e.inter_frame(y, u, v, sd, -1.0, st["prev_golden"], st["prev_altref"], st["altref_differs"])
+        n1 = e.last_launch_count
+        e.loop_filter(None)
+        return n1 + e.last_launch_count, 1 + (not st["prev_golden"]) + (not st["prev_altref"] and st["altref_differs"])
+
+    for i in range(1, 1 + W):
+        step(i)
+    e.synchronize()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    launches, refs_searched = 0, 0
+    with torch.cuda.stream(ext_stream):
+        for k in range(K):
+            flush_buf.fill_(k & 255)           # L2 flush between timed steps, outside the timed span
+            ev[k][0].record(ext_stream)
+            n, r = step(1 + W + k)
+            ev[k][1].record(ext_stream)
+            launches += n
+            refs_searched += r
+    e.synchronize()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = sum(step_ms)
+    clocks = sampler.stop() if rank == 0 else None
+    if dist:
+        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    value = world * K / (total_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel, timed live on the stream it is launched on -------------
+    roofline = roofline_hbm = None
+    if rank == 0:
+        L = eng.lib()
+        L.vp8b200_measure_int_ops_per_second.restype = ctypes.c_double
+        int_peak = L.vp8b200_measure_int_ops_per_second(ctypes.c_void_p(stream_ptr), 5)
+        cur_y = dev_frames[-1][0]
+        ref_y = dev_frames[-2][0]
+        nb = N // 64
+        net = torch.zeros((nb, 2), dtype=torch.int16, device="cuda")
+        outn = torch.zeros((nb, 2), dtype=torch.int16, device="cuda")
+        met = torch.zeros(nb, dtype=torch.int32, device="cuda")
+        reps = 10
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        with torch.cuda.stream(ext_stream):
+            for _ in range(3):
+                eng.luma_search_2step(cur_y, ref_y, net, outn, met, WRK_W, WRK_H)
+            for a, b in evs:
+                flush_buf.fill_(1)
+                a.record(ext_stream)
+                eng.luma_search_2step(cur_y, ref_y, net, outn, met, WRK_W, WRK_H)
+                b.record(ext_stream)
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b in evs) / reps
+        ops = 1381.0 * N  # algorithmic int-ops of the quarter-pel level per reference
+        roofline = {"kernel": "luma_search_2step", "bound": "int_alu", "achieved": ops / (ms * 1e-3) / 1e12,
+                    "peak": int_peak / 1e12, "unit": "Tiop/s", "frac": (ops / (ms * 1e-3)) / int_peak,
+                    "traffic": None, "ms_per_launch": ms,
+                    "note": "algorithmic = 1381 int-ops per luma pixel per reference (SURVEY 8d); peak = measured "
+                            "IMAD:add/logic 1:2 issue rate of this device (vp8b200_measure_int_ops_per_second)"}
+        # loop filter: HBM line (3N bytes read + written once each -> 3N algorithmic bytes per SURVEY 8d)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        seg = torch.zeros(M, dtype=torch.int32, device="cuda")
+        mask = torch.full((M,), -1, dtype=torch.int32, device="cuda")
+        sd_dev = torch.from_numpy(sd).cuda()
+        planes = [t.clone() for t in dev_frames[-1]]
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        with torch.cuda.stream(ext_stream):
+            for _ in range(2):
+                eng.loop_filter_planes(planes[0], planes[1], planes[2], seg, mask, sd_dev, WRK_W, WRK_H)
+            for a, b in evs:
+                flush_buf.fill_(2)
+                a.record(ext_stream)
+                eng.loop_filter_planes(planes[0], planes[1], planes[2], seg, mask, sd_dev, WRK_W, WRK_H)
+                b.record(ext_stream)
+        torch.cuda.synchronize()
+        ms_lf = sum(a.elapsed_time(b) for a, b in evs) / reps
+        gbs = 3.0 * N / (ms_lf * 1e-3) / 1e9
+        roofline_hbm = {"kernel": "loop_filter_planes", "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": gbs / hbm_peak, "traffic": None, "ms_per_launch": ms_lf,
+                        "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
+                        "note": "dependency-bound wavefront of mb_w+2(mb_h-1)=%d stages, not bandwidth-bound" % (WRK_W // 16 + 2 * (WRK_H // 16 - 1))}
+    e.close()
+
+    # ---- end to end: the unmodified reference host against our OpenCL shim -------------------------
+    e2e = None
+    if rank == 0 and not args.no_e2e:
+        host_bin = os.path.join(ROOT, "vp8oclenc_b200", "bin", "vp8enc")
+        lib_dir = os.path.join(ROOT, "vp8oclenc_b200", "lib")
+        if os.path.exists(host_bin):
+            n = 1 + W + K
+            y4m = os.path.join(tmp, "clip.y4m")
+            gen_y4m.write_y4m(y4m, WIDTH, HEIGHT, n)
+            stats = os.path.join(tmp, "shim_stats.json")
+            stamps, _ = run_encoder_timed(host_bin, lib_dir, os.path.join(tmp, "run"), y4m, os.path.join(tmp, "out.ivf"), n,
+                                          {"VP8B200_STATS": stats, "VP8B200_DEVICE": str(local_rank)})
+            dt = stamps[-1] - stamps[W]
+            e2e = {"value": K / dt, "unit": "frames/s", "ms_per_step": 1000.0 * dt / K, "processes": 1,
+                   "what": "unmodified reference host (vp8enc.cpp + entropy_host.cpp) + libOpenCL.so.1 shim; Y4M file in, "
+                           "IVF file out; all host<->device copies, host intra/entropy work and file I/O included"}
+            try:
+                s = json.load(open(stats))
+                frames_counted = max(1, n)
+                e2e["h2d_bytes_per_step"] = int(s["h2d_bytes"] / frames_counted)
+                e2e["d2h_bytes_per_step"] = int(s["d2h_bytes"] / frames_counted)
+                e2e["shim_kernel_launches_per_step"] = s["kernel_launches"] / frames_counted
+            except Exception:
+                e2e["h2d_bytes_per_step"] = e2e["d2h_bytes_per_step"] = None
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = reference_arm(args, tmp)
+        if r:
+            cpu_baseline = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {"metric": "encoded frames/s at 1080p", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K,
+                "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8/int32", "data": "synthetic",
+                "config": dict(config, l2="flushed between timed steps (256 MiB fill outside the timed span)",
+                               refs_searched_per_frame=refs_searched / K,
+                               me_mpix_per_s=value * N / 1e6),
+                "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roofline,
+                "roofline_hbm": roofline_hbm, "cpu_baseline": cpu_baseline}
+        print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

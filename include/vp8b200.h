@@ -37,6 +37,11 @@ typedef struct {
 int vp8b200_device_info(char *name, int name_cap, int *sm_count, int *cc_major, int *cc_minor);
 const char *vp8b200_version(void);
 
+/* Measures the 32-bit integer instruction rate of the device (ops/s) with a 1:2 IMAD : add/logic
+ * micro-benchmark on `stream`; the roofline denominator of the motion-search kernels, which are
+ * integer-ALU bound.  Returns < 0 on a CUDA error. */
+double vp8b200_measure_int_ops_per_second(void *stream, int repeats);
+
 /* replaces reset_vectors, src/GPU_kernels.cl:404-427 (enqueued at src/inter_part.h:5-6); n = 4*mb_count */
 int vp8b200_reset_vectors(void *stream, int16_t *last_net1, int16_t *last_net2, int16_t *golden_net1,
                           int16_t *golden_net2, int16_t *altref_net1, int16_t *altref_net2, int32_t *last_Bdiff,
@@ -107,6 +112,62 @@ int vp8b200_loop_filter_frame(void *stream, uint8_t *frame, const int32_t *MB_se
 /* the three planes of one frame in a single launch (Y, U, V run concurrently) */
 int vp8b200_loop_filter_planes(void *stream, uint8_t *y, uint8_t *u, uint8_t *v, const int32_t *MB_segment_ids,
                                const int32_t *mb_mask, const vp8b200_segment_data *SD, int width, int height);
+
+/* ------------------------------------------------------------------------------------------
+ * Frame-level engine: one object owns every per-frame device buffer the reference creates in
+ * init_all() (src/init.h:430-593: pyramids, LAST/GOLDEN/ALTREF planes, vector nets, metrics,
+ * predictors, residuals, coefficient / vector / parts / reference / segment-id / SSIM arrays)
+ * and runs the enqueue sequence of prepare_GPU_buffers() + inter_transform()
+ * (src/inter_part.h:1-384) followed by the filter mask and the loop filter
+ * (src/loop_filter.h:25-46,140-183) on one CUDA stream.  It is the same work the OpenCL shim
+ * performs when the unmodified host drives it kernel by kernel.
+ */
+typedef struct vp8b200_engine vp8b200_engine;
+
+/* stream: cudaStream_t as void*, NULL = a private stream */
+vp8b200_engine *vp8b200_engine_create(int width, int height, void *stream);
+void vp8b200_engine_destroy(vp8b200_engine *e);
+void *vp8b200_engine_stream(vp8b200_engine *e);
+int vp8b200_engine_synchronize(vp8b200_engine *e);
+
+/* Seeds the reconstruction buffers (what the host uploads as LAST at src/vp8enc.cpp:395-401, e.g. the
+ * loop-filtered key frame) from device (on_device=1) or host memory. */
+int vp8b200_engine_set_reconstruction(vp8b200_engine *e, const uint8_t *y, const uint8_t *u, const uint8_t *v,
+                                      int on_device);
+
+/* One inter frame with the current frame already resident in device memory.  On return (stream
+ * order) the coefficient/vector/... buffers hold this frame's results and the reconstruction
+ * buffers hold the UNFILTERED reconstruction.  prev_is_golden / prev_is_altref /
+ * altref_differs_from_golden are the host's flags of src/inter_part.h:35-50,103-104. */
+int vp8b200_engine_inter_frame(vp8b200_engine *e, const uint8_t *cur_y, const uint8_t *cur_u, const uint8_t *cur_v,
+                               const vp8b200_segment_data *SD_host, float SSIM_target, int prev_is_golden,
+                               int prev_is_altref, int altref_differs_from_golden);
+
+/* Filter mask + normal loop filter of the three reconstruction planes in place (they then are
+ * the next frame's LAST). */
+int vp8b200_engine_loop_filter(vp8b200_engine *e, const vp8b200_segment_data *SD_host);
+
+/* The call with HOST buffers (pinned or pageable): uploads the current frame, runs
+ * inter_frame + loop_filter, downloads every array the reference host reads back
+ * (src/inter_part.h:263-265, src/vp8enc.cpp:422-433) plus the loop-filtered planes, and waits.
+ * Any output pointer may be NULL. */
+int vp8b200_engine_encode_frame_host(vp8b200_engine *e, const uint8_t *cur_y, const uint8_t *cur_u,
+                                     const uint8_t *cur_v, const vp8b200_segment_data *SD, float SSIM_target,
+                                     int prev_is_golden, int prev_is_altref, int altref_differs_from_golden,
+                                     int16_t *MB_coeffs, int16_t *MB_vectors, int32_t *MB_parts,
+                                     int32_t *MB_reference_frame, int32_t *MB_segment_id, float *MB_SSIM,
+                                     int32_t *MB_non_zero_coeffs, uint8_t *recon_y, uint8_t *recon_u,
+                                     uint8_t *recon_v);
+
+/* device pointers of the engine's result buffers */
+enum {
+    VP8B200_BUF_COEFFS = 0, VP8B200_BUF_VECTORS, VP8B200_BUF_PARTS, VP8B200_BUF_REFERENCE_FRAME,
+    VP8B200_BUF_SEGMENT_ID, VP8B200_BUF_SSIM, VP8B200_BUF_NON_ZERO, VP8B200_BUF_RECON_Y, VP8B200_BUF_RECON_U,
+    VP8B200_BUF_RECON_V, VP8B200_BUF_COUNT
+};
+void *vp8b200_engine_buffer(vp8b200_engine *e, int which);
+/* number of kernels the last inter_frame + loop_filter launched */
+int vp8b200_engine_last_launch_count(vp8b200_engine *e);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,98 @@
+"""Frame-level parity: vp8b200_engine_* (the CUDA pipeline of one inter frame + loop filter)
+against the oracle's vp8o_inter_frame / vp8o_loop_filter_planes over a sequence of frames with the
+LAST / GOLDEN / ALTREF rotation of the reference host.  Bit-exact for every array, frame after
+frame (errors would accumulate through the reference frames)."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import _trace
+from _libs import P, ROOT, make_segment_data, oracle
+
+torch = pytest.importorskip("torch")
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a CUDA device")]
+
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+
+def run_sequence(w, h, nframes, altref_range, ssim_target, qi, host_api):
+    import gen_y4m
+    from vp8oclenc_b200 import host as eng
+    o = oracle()
+    clip = gen_y4m.Clip(w, h)
+    M = (w // 16) * (h // 16)
+    e = eng.Engine(w, h)
+    ctx = ctypes.c_void_p(o.vp8o_ctx_create(w, h))
+    state = _trace.HostState(10 ** 6, altref_range)
+    sd = make_segment_data(qi)
+    y0, u0, v0 = clip.frame(0)
+    state.next_frame()  # frame 0 is the key frame; its (pretend) reconstruction seeds LAST
+    rec = [y0.copy().reshape(-1), u0.copy().reshape(-1), v0.copy().reshape(-1)]
+    e.set_reconstruction(torch.from_numpy(rec[0]).cuda(), torch.from_numpy(rec[1]).cuda(), torch.from_numpy(rec[2]).cuda())
+    refs_seen = set()
+    for i in range(1, nframes):
+        st = state.next_frame()
+        y, u, v = [np.ascontiguousarray(p).reshape(-1) for p in clip.frame(i)]
+        coef = np.zeros(M * 400, np.int16)
+        vec = np.zeros(M * 8, np.int16)
+        parts = np.zeros(M, np.int32)
+        refid = np.zeros(M, np.int32)
+        seg = np.zeros(M, np.int32)
+        ssim = np.zeros(M, np.float32)
+        nz = np.zeros(M, np.int32)
+        o.vp8o_inter_frame(ctx, P(y), P(u), P(v), P(rec[0]), P(rec[1]), P(rec[2]), P(sd), ctypes.c_float(ssim_target),
+                           st["prev_golden"], st["prev_altref"], st["altref_differs"], P(coef), P(vec), P(parts),
+                           P(refid), P(seg), P(ssim))
+        unfiltered = [r.copy() for r in rec]
+        o.vp8o_loop_filter_planes(P(rec[0]), P(rec[1]), P(rec[2]), P(coef), P(parts), P(seg), P(sd), P(nz), w, h)
+        if host_api:
+            out = {k: torch.empty(n, dtype=dt).pin_memory() for k, (dt, n) in dict(
+                coeffs=(torch.int16, M * 400), vectors=(torch.int16, M * 8), parts=(torch.int32, M),
+                reference_frame=(torch.int32, M), segment_id=(torch.int32, M), ssim=(torch.float32, M),
+                non_zero=(torch.int32, M), recon_y=(torch.uint8, w * h), recon_u=(torch.uint8, w * h // 4),
+                recon_v=(torch.uint8, w * h // 4)).items()}
+            e.encode_frame_host(torch.from_numpy(y).pin_memory(), torch.from_numpy(u).pin_memory(),
+                                torch.from_numpy(v).pin_memory(), sd, ssim_target, st["prev_golden"], st["prev_altref"],
+                                st["altref_differs"], out)
+            got = {k: t.numpy() for k, t in out.items()}
+        else:
+            e.inter_frame(torch.from_numpy(y).cuda(), torch.from_numpy(u).cuda(), torch.from_numpy(v).cuda(), sd,
+                          ssim_target, st["prev_golden"], st["prev_altref"], st["altref_differs"])
+            got = {k: e.read(k) for k in ("coeffs", "vectors", "parts", "reference_frame", "segment_id", "ssim")}
+            for k, p in zip(("recon_y", "recon_u", "recon_v"), unfiltered):
+                assert np.array_equal(e.read(k), p), "unfiltered %s, frame %d" % (k, i)
+            e.loop_filter(sd)
+            got.update({k: e.read(k) for k in ("non_zero", "recon_y", "recon_u", "recon_v")})
+        assert np.array_equal(got["vectors"], vec), "vectors, frame %d" % i
+        assert np.array_equal(got["parts"], parts), "parts, frame %d" % i
+        assert np.array_equal(got["reference_frame"], refid), "reference ids, frame %d" % i
+        assert np.array_equal(got["segment_id"], seg), "segment ids, frame %d" % i
+        assert np.array_equal(got["coeffs"], coef), "coefficients, frame %d" % i
+        assert np.array_equal(got["ssim"].view(np.uint32), ssim.view(np.uint32)), "SSIM, frame %d" % i
+        assert np.array_equal(got["non_zero"], nz), "non-zero counts, frame %d" % i
+        for k, p in zip(("recon_y", "recon_u", "recon_v"), rec):
+            assert np.array_equal(got[k], p), "loop-filtered %s, frame %d" % (k, i)
+        refs_seen |= set(refid.tolist())
+    o.vp8o_ctx_destroy(ctx)
+    e.close()
+    return refs_seen
+
+
+def test_engine_sequence_cif_three_references():
+    refs = run_sequence(352, 288, 12, 4, -1.0, (24, 24, 24, 24), host_api=False)
+    assert len(refs) >= 2, refs  # GOLDEN and/or ALTREF really were chosen for some macroblocks
+
+
+def test_engine_sequence_ssim_ladder():
+    run_sequence(352, 288, 6, 3, 0.93, (6, 20, 35, 50), host_api=False)
+
+
+def test_engine_host_buffers_api():
+    run_sequence(176, 144, 8, 3, -1.0, (30, 30, 30, 30), host_api=True)
+
+
+def test_engine_1080p_two_frames():
+    run_sequence(1920, 1088, 3, 5, -1.0, (24, 24, 24, 24), host_api=True)

@@ -74,6 +74,17 @@ static char g_dev_name[256] = "no CUDA device";
 static int g_sm_count = 0;
 static unsigned g_next_index = 0;
 static FILE *g_trace = nullptr;
+// statistics, written as JSON to $VP8B200_STATS at exit (bench.py reads them)
+static unsigned long long g_h2d_bytes = 0, g_d2h_bytes = 0, g_kernel_launches = 0, g_host_kernels = 0;
+static void write_stats() {
+    const char *p = getenv("VP8B200_STATS");
+    if (!p || !*p) return;
+    if (FILE *f = fopen(p, "w")) {
+        fprintf(f, "{\"h2d_bytes\": %llu, \"d2h_bytes\": %llu, \"kernel_launches\": %llu, \"host_kernels\": %llu}\n",
+                g_h2d_bytes, g_d2h_bytes, g_kernel_launches, g_host_kernels);
+        fclose(f);
+    }
+}
 
 // deferred luma / chroma-U loop filters, so that the three planes go out as ONE launch
 struct PendingLF { cl_mem frame, seg, mask, sd; int w, h; };
@@ -94,6 +105,7 @@ static bool cuda_init() {
     vp8b200_device_info(g_dev_name, sizeof(g_dev_name), &g_sm_count, nullptr, nullptr);
     const char *tr = getenv("VP8CL_TRACE");
     if (tr && *tr) g_trace = fopen(tr, "wb");
+    atexit(write_stats);
     g_cuda_ok = true;
     return true;
 }
@@ -130,6 +142,7 @@ static void *dev_ptr(cl_mem m, bool will_write) {
     if (!m) return nullptr;
     if (!m->dev_valid) {
         cudaMemcpyAsync(m->dev, m->host, m->size, cudaMemcpyHostToDevice, g_stream);
+        g_h2d_bytes += m->size;
         m->dev_valid = true;
     }
     if (will_write) m->host_valid = false;
@@ -142,6 +155,7 @@ static void *host_ptr(cl_mem m, bool will_write, bool discard = false) {
     if (!m->host_valid) {
         if (!discard) {
             cudaMemcpyAsync(m->host, m->dev, m->size, cudaMemcpyDeviceToHost, g_stream);
+            g_d2h_bytes += m->size;
             cudaStreamSynchronize(g_stream);
         }
         m->host_valid = true;
@@ -180,6 +194,7 @@ static void launch_lf(int count) {
     // count pending planes (luma [, chroma U]) that could not be fused: launch them one by one
     for (int i = 0; i < count; ++i) {
         PendingLF &p = g_pending_lf[i];
+        ++g_kernel_launches;
         vp8b200_loop_filter_frame(g_stream, (uint8_t *)dev_ptr(p.frame, true), (const int32_t *)dev_ptr(p.seg, false),
                                   (const int32_t *)dev_ptr(p.mask, false),
                                   (const vp8b200_segment_data *)dev_ptr(p.sd, false), p.w, p.h, i == 0 ? 16 : 8);
@@ -191,6 +206,8 @@ static cl_int dispatch(cl_kernel k, size_t global) {
     void *s = g_stream;
     int rc = 0;
     if (k->id != K_LF_CHROMA) flush_pending();
+    if (k->id >= K_COUNT_PROBS) ++g_host_kernels;
+    else if (k->id != K_LF_LUMA && k->id != K_LF_CHROMA) ++g_kernel_launches;
     switch (k->id) {
         case K_RESET_VECTORS:
             rc = vp8b200_reset_vectors(s, out<int16_t>(k, 0), out<int16_t>(k, 1), out<int16_t>(k, 2), out<int16_t>(k, 3),
@@ -277,6 +294,7 @@ static cl_int dispatch(cl_kernel k, size_t global) {
                 g_num_pending_lf = 2;
             } else if (same && g_num_pending_lf == 2) {
                 const PendingLF &u = g_pending_lf[1];
+                ++g_kernel_launches;
                 rc = vp8b200_loop_filter_planes(s, (uint8_t *)dev_ptr(y.frame, true), (uint8_t *)dev_ptr(u.frame, true),
                                                 (uint8_t *)dev_ptr(p.frame, true), (const int32_t *)dev_ptr(y.seg, false),
                                                 (const int32_t *)dev_ptr(y.mask, false),
@@ -284,6 +302,7 @@ static cl_int dispatch(cl_kernel k, size_t global) {
                 g_num_pending_lf = 0;
             } else {
                 flush_pending();
+                ++g_kernel_launches;
                 rc = vp8b200_loop_filter_frame(s, (uint8_t *)dev_ptr(p.frame, true), (const int32_t *)dev_ptr(p.seg, false),
                                                (const int32_t *)dev_ptr(p.mask, false),
                                                (const vp8b200_segment_data *)dev_ptr(p.sd, false), p.w, p.h, 8);
@@ -478,6 +497,7 @@ cl_int clEnqueueReadBuffer(cl_command_queue, cl_mem m, cl_bool blocking, size_t 
     flush_pending();
     if (m->dev_valid) {
         cudaError_t e = cudaMemcpyAsync(ptr, (char *)m->dev + off, size, cudaMemcpyDeviceToHost, g_stream);
+        g_d2h_bytes += size;
         if (e != cudaSuccess) return cuda_rc(e);
         if (blocking || g_trace) cudaStreamSynchronize(g_stream);
     } else {
@@ -509,6 +529,7 @@ cl_int clEnqueueWriteBuffer(cl_command_queue, cl_mem m, cl_bool blocking, size_t
         }
     }
     cudaError_t e = cudaMemcpyAsync((char *)m->dev + off, ptr, size, cudaMemcpyHostToDevice, g_stream);
+    g_h2d_bytes += size;
     m->host_valid = false;
     if (blocking) cudaStreamSynchronize(g_stream);
     return cuda_rc(e);
@@ -530,6 +551,7 @@ cl_int clEnqueueWriteImage(cl_command_queue, cl_mem img, cl_bool blocking, const
     const size_t pitch = row_pitch ? row_pitch : region[0];
     char *dst = (char *)dev_ptr(img, true) + origin[1] * img->width + origin[0];
     cudaError_t e = cudaMemcpy2DAsync(dst, img->width, ptr, pitch, region[0], region[1], cudaMemcpyHostToDevice, g_stream);
+    g_h2d_bytes += region[0] * region[1];
     if (pitch == region[0]) trace_rec(4, img->index, 0, region[0] * region[1], ptr);
     if (blocking) cudaStreamSynchronize(g_stream);
     return cuda_rc(e);

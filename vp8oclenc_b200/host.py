@@ -137,3 +137,103 @@ def loop_filter_frame(frame, MB_segment_ids, mb_mask, SD, width, height, mb_size
 def loop_filter_planes(y, u, v, MB_segment_ids, mb_mask, SD, width, height):
     _check(lib().vp8b200_loop_filter_planes(_stream(), _p(y), _p(u), _p(v), _p(MB_segment_ids), _p(mb_mask), _p(SD),
                                             width, height), "loop_filter_planes")
+
+
+# ---------------------------------------------------------------------------------------------
+class Engine:
+    """Frame-level engine (vp8b200_engine_* of include/vp8b200.h): the sequence of
+    prepare_GPU_buffers() + inter_transform() + loop filter of the reference host
+    (src/inter_part.h, src/loop_filter.h) on one CUDA stream."""
+
+    BUF = dict(coeffs=0, vectors=1, parts=2, reference_frame=3, segment_id=4, ssim=5, non_zero=6, recon_y=7,
+               recon_u=8, recon_v=9)
+
+    def __init__(self, width, height, stream=None):
+        L = lib()
+        L.vp8b200_engine_create.restype = ctypes.c_void_p
+        L.vp8b200_engine_buffer.restype = ctypes.c_void_p
+        L.vp8b200_engine_stream.restype = ctypes.c_void_p
+        self.width, self.height = width, height
+        self.mb_count = (width // 16) * (height // 16)
+        h = L.vp8b200_engine_create(width, height, ctypes.c_void_p(stream or 0))
+        if not h:
+            raise EngineError("vp8b200_engine_create failed (no CUDA device, or size not a multiple of 16)")
+        self._h = ctypes.c_void_p(h)
+
+    def close(self):
+        if self._h:
+            lib().vp8b200_engine_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    @property
+    def stream(self):
+        return lib().vp8b200_engine_stream(self._h)
+
+    def synchronize(self):
+        _check(lib().vp8b200_engine_synchronize(self._h), "engine_synchronize")
+
+    def set_reconstruction(self, y, u, v):
+        on_dev = int(y.is_cuda)
+        ptr = (lambda t: _p(t)) if on_dev else (lambda t: ctypes.c_void_p(t.data_ptr()))
+        _check(lib().vp8b200_engine_set_reconstruction(self._h, ptr(y), ptr(u), ptr(v), on_dev), "set_reconstruction")
+
+    def inter_frame(self, cur_y, cur_u, cur_v, sd_np, ssim_target, prev_is_golden, prev_is_altref, altref_differs):
+        _check(lib().vp8b200_engine_inter_frame(self._h, _p(cur_y), _p(cur_u), _p(cur_v),
+                                                ctypes.c_void_p(sd_np.ctypes.data), ctypes.c_float(ssim_target),
+                                                int(prev_is_golden), int(prev_is_altref), int(altref_differs)),
+               "engine_inter_frame")
+
+    def loop_filter(self, sd_np=None):
+        p = ctypes.c_void_p(sd_np.ctypes.data) if sd_np is not None else ctypes.c_void_p(0)
+        _check(lib().vp8b200_engine_loop_filter(self._h, p), "engine_loop_filter")
+
+    def encode_frame_host(self, cur_y, cur_u, cur_v, sd_np, ssim_target, prev_is_golden, prev_is_altref, altref_differs,
+                          out):
+        """cur_* and the tensors in `out` (dict keyed like BUF) are HOST tensors (pinned for speed)"""
+        def hp(name):
+            t = out.get(name)
+            return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+        _check(lib().vp8b200_engine_encode_frame_host(
+            self._h, ctypes.c_void_p(cur_y.data_ptr()), ctypes.c_void_p(cur_u.data_ptr()),
+            ctypes.c_void_p(cur_v.data_ptr()), ctypes.c_void_p(sd_np.ctypes.data), ctypes.c_float(ssim_target),
+            int(prev_is_golden), int(prev_is_altref), int(altref_differs), hp("coeffs"), hp("vectors"), hp("parts"),
+            hp("reference_frame"), hp("segment_id"), hp("ssim"), hp("non_zero"), hp("recon_y"), hp("recon_u"),
+            hp("recon_v")), "engine_encode_frame_host")
+
+    def buffer_ptr(self, name):
+        return lib().vp8b200_engine_buffer(self._h, self.BUF[name])
+
+    def read(self, name):
+        """device result buffer -> numpy (synchronising)"""
+        import numpy as np
+        M, w, h = self.mb_count, self.width, self.height
+        shapes = dict(coeffs=(np.int16, M * 400), vectors=(np.int16, M * 8), parts=(np.int32, M),
+                      reference_frame=(np.int32, M), segment_id=(np.int32, M), ssim=(np.float32, M),
+                      non_zero=(np.int32, M), recon_y=(np.uint8, w * h), recon_u=(np.uint8, w * h // 4),
+                      recon_v=(np.uint8, w * h // 4))
+        dt, n = shapes[name]
+        out = np.empty(n, dt)
+        self.synchronize()
+        rc = _cudart().cudaMemcpy(ctypes.c_void_p(out.ctypes.data), ctypes.c_void_p(self.buffer_ptr(name)),
+                                  ctypes.c_size_t(out.nbytes), 2)
+        if rc != 0:
+            raise EngineError("cudaMemcpy D2H failed: %d" % rc)
+        return out
+
+    @property
+    def last_launch_count(self):
+        return lib().vp8b200_engine_last_launch_count(self._h)
+
+
+_cudart_lib = None
+
+
+def _cudart():
+    global _cudart_lib
+    if _cudart_lib is None:
+        import glob
+        cands = glob.glob("/usr/local/cuda/lib64/libcudart.so*") + glob.glob("/usr/local/cuda/targets/*/lib/libcudart.so*")
+        _cudart_lib = ctypes.CDLL(sorted(cands)[0]) if cands else ctypes.CDLL("libcudart.so")
+    return _cudart_lib
