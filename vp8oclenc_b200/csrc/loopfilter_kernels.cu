@@ -3,12 +3,20 @@
 //
 // The reference filters a plane with ONE work-item walking the macroblocks in raster order.
 // Raster order only constrains MB(r,c) to run after MB(r,c-1) (its left edge) and after
-// MB(r-1,c+1) (whose left-edge filter rewrites the bottom-right pixels of MB(r-1,c), which the
-// top-edge filter of MB(r,c) reads).  All macroblocks with the same c + 2r are therefore
-// independent: the kernel runs the mb_w + 2(mb_h-1) anti-diagonal "stages" as a wavefront,
-// 16 lanes per macroblock (one per pixel row, then one per pixel column), all three planes
-// concurrently.  The honest bound of this kernel is stages x (L2 round trip + filter latency),
-// not HBM bandwidth ("hard parts").
+// MB(r-1,c+1) (whose left-edge filter rewrites the right-most pixels of MB(r-1,c), which the
+// top-edge filter of MB(r,c) reads).  The kernel therefore runs ONE CTA PER MACROBLOCK ROW of
+// every plane, all rows of all three planes concurrently, as a wavefront:
+//   * the row's whole pixel strip (16 x width luma, 8 x width/2 chroma) is loaded into shared
+//     memory once with coalesced 16-byte loads and written back once; the serial walk along the
+//     row touches shared memory only;
+//   * rows talk through global memory: a row publishes, per macroblock, its final bottom four
+//     pixel lines and then a progress counter (release); the row below acquires the counter,
+//     reads those four lines (bypassing L1), filters the shared edge and owns the three lines it
+//     rewrites from then on;
+//   * rows are handed to CTAs through an atomic ticket in launch order, so a waiting row's
+//     predecessor is always already running: no deadlock whatever the residency.
+// The bound of this kernel is the dependency chain ~ (mb_w + c*mb_h) macroblock steps of eight
+// serial edge filters each, not HBM bandwidth ("hard parts").
 //
 // Arithmetic: the reference uses short8 lanes.  Every intermediate stays far inside int16
 // (pixels - 128 drift by at most a few dozen between the clamped stores, the largest product
@@ -82,96 +90,219 @@ __device__ __forceinline__ void filter_line(int (&v)[N + 4], bool mb_edge, bool 
     }
 }
 
+__device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d) {
+    return (uint32_t)sat8(a + 128) | ((uint32_t)sat8(b + 128) << 8) | ((uint32_t)sat8(c + 128) << 16) |
+           ((uint32_t)sat8(d + 128) << 24);
+}
+
+__device__ __forceinline__ int ld_acquire(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int *p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// loads that must observe another SM's stores: bypass the (non-coherent) L1
+__device__ __forceinline__ uint32_t ld_cg_u8(const uint8_t *p) {
+    uint32_t v;
+    asm volatile("ld.global.cg.u8 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 struct LFPlanes {
     uint8_t *ptr[3];
 };
 
-// One CTA per plane, 64 macroblock slots x 16 lanes.
+constexpr int LF_THREADS = 128;
+
+// one macroblock row of one plane; smem = strip of N rows, stride S = width + 4 (word stride
+// odd -> the row-per-lane accesses of the horizontal pass are bank-conflict free), then the
+// per-macroblock limits
 template <int N>
-__device__ void lf_plane(uint8_t *__restrict__ frame, const int *__restrict__ seg, const int *__restrict__ mb_mask,
-                         const vp8b200_segment_data *__restrict__ SD, int width, int height, int *s_stop) {
-    const int mbw = width / N, mbh = height / N, mb_count = mbw * mbh;
-    const int tid = threadIdx.x, slot = tid >> 4, lane = tid & 15;
+__device__ void lf_row(uint8_t *__restrict__ frame, const int *__restrict__ seg, const int *__restrict__ mb_mask,
+                       const vp8b200_segment_data *__restrict__ SD, int width, int height, int r, int stop,
+                       int *progress, unsigned char *smem) {
+    const int mbw = width / N, mbh = height / N;
+    const int S = width + 4;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ncols = max(0, min(mbw, stop - r * mbw));  // macroblocks of this row before the Q6 stop
+    if (ncols == 0) return;
+    uint8_t *strip = smem;
+    int4 *lims = reinterpret_cast<int4 *>(smem + ((N * S + 15) & ~15));  // {mb_lim, b_lim, int_lim, hev_thr | inner<<16}
+    const int y0 = r * N;
 
-    // "if (SD[i].loop_filter_level == 0) return;" ends the WHOLE plane at the first such
-    // macroblock in raster order (Q6): find that index
-    if (tid == 0) *s_stop = mb_count;
+    // ---- stage the strip and the per-macroblock limits ----
+    // 8-byte chunks: plane widths are multiples of 8 (chroma of a 16-aligned luma), rows 8-byte aligned
+    const int chunks = width / 8;
+    for (int i = tid; i < N * chunks; i += LF_THREADS) {
+        const int row = i / chunks, xc = i % chunks;
+        const uint2 v = *reinterpret_cast<const uint2 *>(frame + (size_t)(y0 + row) * width + 8 * xc);
+        uint32_t *d = reinterpret_cast<uint32_t *>(strip + row * S + 4 + 8 * xc);
+        d[0] = v.x; d[1] = v.y;
+    }
+    for (int c = tid; c < ncols; c += LF_THREADS) {
+        const int mb = r * mbw + c;
+        const vp8b200_segment_data *sd = SD + seg[mb];
+        lims[c] = make_int4((short)sd->mbedge_limit, (short)sd->sub_bedge_limit, (short)sd->interior_limit,
+                            ((short)sd->hev_threshold & 0xffff) | (mb_mask[mb] != 0 ? 0x10000 : 0));
+    }
     __syncthreads();
-    int first = mb_count;
-    for (int mb = tid; mb < mb_count; mb += blockDim.x)
-        if (SD[seg[mb]].loop_filter_level == 0) {
-            first = mb;
-            break;
-        }
-    if (first < mb_count) atomicMin(s_stop, first);
-    __syncthreads();
-    const int stop = *s_stop;
 
-    const int stages = mbw + 2 * (mbh - 1);
-    for (int s = 0; s < stages; ++s) {
-        for (int r0 = 0; r0 < mbh; r0 += 64) {
-            const int r = r0 + slot, c = s - 2 * r;
-            const int mb = r * mbw + c;
-            const bool active = r < mbh && c >= 0 && c < mbw && mb < stop && lane < N;
-            int mb_lim = 0, b_lim = 0, int_lim = 0, hev_thr = 0;
-            bool inner = false;
-            const int x0 = c * N, y0 = r * N;
-            if (active) {
-                const vp8b200_segment_data *sd = SD + seg[mb];
-                int_lim = (short)sd->interior_limit;
-                mb_lim = (short)sd->mbedge_limit;
-                b_lim = (short)sd->sub_bedge_limit;
-                hev_thr = (short)sd->hev_threshold;
-                inner = mb_mask[mb] != 0;
-                // pass 1: vertical edges, one lane per pixel row
-                uint8_t *row = frame + (size_t)(y0 + lane) * width + x0;
-                int v[N + 4];
+    // ---- the serial walk, warp-specialised so that warp 0 never waits for global memory ----
+    //   warp 0  filters: pass 1 (vertical edges) + pass 2 (horizontal edges) per macroblock, shared memory only
+    //   warp 1  prefetches the four pixel lines above each macroblock once the row above has finalised them
+    //   warp 2  publishes the bottom four lines of every finalised macroblock and the progress counter
+    // hand-offs between the three are counters in shared memory.
+    constexpr int TOPQ = 8;  // depth of the top-line ring
+    uint32_t *topq = reinterpret_cast<uint32_t *>(lims + mbw);             // [TOPQ][4 lines][N/4 words]
+    volatile int *flags = reinterpret_cast<volatile int *>(topq + TOPQ * N);  // h_done, v_done, top_ready
+    if (tid < 3) flags[tid] = 0;
+    __syncthreads();
+    const int *above = progress - 1;  // progress counter of row r-1 (only read when r > 0)
+
+    if (warp == 0) {
+        for (int c = 0; c < ncols; ++c) {
+            const int4 lm = lims[c];
+            const int mb_lim = lm.x, b_lim = lm.y, int_lim = lm.z, hev_thr = lm.w & 0xffff;
+            const bool inner = (lm.w >> 16) != 0;
+            const int x0 = c * N;
+            // pass 1: vertical edges, one lane per pixel row
+            if (lane < N) {
+                uint32_t *row = reinterpret_cast<uint32_t *>(strip + lane * S + 4 + x0);
                 uint32_t words[N / 4 + 1];
-                words[0] = x0 > 0 ? *reinterpret_cast<const uint32_t *>(row - 4) : 0;
+                words[0] = c > 0 ? row[-1] : 0;
 #pragma unroll
-                for (int k = 0; k < N / 4; ++k) words[k + 1] = *reinterpret_cast<const uint32_t *>(row + 4 * k);
+                for (int k = 0; k < N / 4; ++k) words[k + 1] = row[k];
+                int v[N + 4];
 #pragma unroll
                 for (int k = 0; k < N + 4; ++k) v[k] = (int)((words[k >> 2] >> (8 * (k & 3))) & 255) - 128;
-                filter_line<N>(v, x0 > 0, inner, mb_lim, b_lim, int_lim, hev_thr);
+                filter_line<N>(v, c > 0, inner, mb_lim, b_lim, int_lim, hev_thr);
+                if (c > 0) row[-1] = pack4(v[0], v[1], v[2], v[3]);
 #pragma unroll
-                for (int k = 0; k < N / 4 + 1; ++k)
-                    words[k] = (uint32_t)sat8(v[4 * k] + 128) | ((uint32_t)sat8(v[4 * k + 1] + 128) << 8) |
-                               ((uint32_t)sat8(v[4 * k + 2] + 128) << 16) | ((uint32_t)sat8(v[4 * k + 3] + 128) << 24);
-                if (x0 > 0) *reinterpret_cast<uint32_t *>(row - 4) = words[0];
-#pragma unroll
-                for (int k = 0; k < N / 4; ++k) *reinterpret_cast<uint32_t *>(row + 4 * k) = words[k + 1];
+                for (int k = 0; k < N / 4; ++k) row[k] = pack4(v[4 * k + 4], v[4 * k + 5], v[4 * k + 6], v[4 * k + 7]);
             }
-            __syncwarp();  // both passes of a macroblock live in one warp (16 lanes)
-            if (active) {
-                // pass 2: horizontal edges, one lane per pixel column
-                uint8_t *col = frame + (size_t)y0 * width + x0 + lane;
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                flags[0] = c + 1;  // h_done: macroblock c-1 is final now
+            }
+            // pass 2: horizontal edges, one lane per pixel column
+            if (r > 0) {
+                while (flags[2] < c + 1) {}  // top lines of macroblock c are in the ring
+                __threadfence_block();
+            }
+            if (lane < N) {
                 int v[N + 4];
+                if (r > 0) {
+                    const uint8_t *tq = reinterpret_cast<const uint8_t *>(topq + (c % TOPQ) * N) + lane;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) v[k] = y0 > 0 ? (int)col[(ptrdiff_t)(k - 4) * width] - 128 : 0;
+                    for (int k = 0; k < 4; ++k) v[k] = (int)tq[k * N] - 128;
+                } else {
+                    v[0] = v[1] = v[2] = v[3] = 0;
+                }
+                uint8_t *scol = strip + 4 + x0 + lane;
 #pragma unroll
-                for (int k = 0; k < N; ++k) v[k + 4] = (int)col[(size_t)k * width] - 128;
-                filter_line<N>(v, y0 > 0, inner, mb_lim, b_lim, int_lim, hev_thr);
-                if (y0 > 0) {
+                for (int k = 0; k < N; ++k) v[k + 4] = (int)scol[k * S] - 128;
+                filter_line<N>(v, r > 0, inner, mb_lim, b_lim, int_lim, hev_thr);
+                if (r > 0) {  // three lines of the row above now belong to this row: straight to global memory
+                    uint8_t *gcol = frame + (size_t)y0 * width + x0 + lane;
 #pragma unroll
-                    for (int k = 1; k < 4; ++k) col[(ptrdiff_t)(k - 4) * width] = (uint8_t)sat8(v[k] + 128);
+                    for (int k = 1; k < 4; ++k) gcol[(ptrdiff_t)(k - 4) * width] = (uint8_t)sat8(v[k] + 128);
                 }
 #pragma unroll
-                for (int k = 0; k < N; ++k) col[(size_t)k * width] = (uint8_t)sat8(v[k + 4] + 128);
+                for (int k = 0; k < N; ++k) scol[k * S] = (uint8_t)sat8(v[k + 4] + 128);
+            }
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                flags[1] = c + 1;  // v_done
             }
         }
-        __syncthreads();
+    } else if (warp == 1) {
+        if (r > 0) {
+            for (int c = 0; c < ncols; ++c) {
+                while (c - flags[1] >= TOPQ) __nanosleep(40);  // ring slot free again
+                if (lane == 0)
+                    while (ld_acquire(above) < c + 1) __nanosleep(20);  // MB(r-1,c) final <=> MB(r-1,c+1) edge-filtered
+                __syncwarp();
+                if (lane < N) {  // 4 lines x N/4 words
+                    const int line = lane / (N / 4), wd = lane % (N / 4);
+                    uint32_t w;
+                    const uint8_t *g = frame + (size_t)(y0 - 4 + line) * width + c * N + 4 * wd;
+                    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(w) : "l"(g) : "memory");
+                    topq[(c % TOPQ) * N + line * (N / 4) + wd] = w;
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence_block();
+                    flags[2] = c + 1;  // top_ready
+                }
+            }
+        }
+    } else if (warp == 2) {
+        for (int c = 0; c < ncols; ++c) {
+            // macroblock c is final once pass 1 of macroblock c+1 ran, the last one after its own pass 2
+            if (c + 1 < ncols) {
+                while (flags[0] < c + 2) __nanosleep(40);
+            } else {
+                while (flags[1] < ncols) __nanosleep(40);
+            }
+            __threadfence_block();
+            if (lane < N) {
+                const int line = N - 4 + lane / (N / 4), wd = lane % (N / 4);
+                const uint32_t w = *reinterpret_cast<const uint32_t *>(strip + line * S + 4 + c * N + 4 * wd);
+                *reinterpret_cast<uint32_t *>(frame + (size_t)(y0 + line) * width + c * N + 4 * wd) = w;
+            }
+            __syncwarp();
+            if (lane == 0) st_release(progress, c + 1 < ncols ? c + 1 : mbw + 1);
+        }
     }
+    __syncthreads();
+    // ---- write back lines 0..N-5 of the filtered range (the last four lines are already out,
+    // and the row below may have rewritten three of them since) ----
+    const int out_chunks = ncols * N / 8;
+    for (int i = tid; i < (N - 4) * out_chunks; i += LF_THREADS) {
+        const int row = i / out_chunks, xc = i % out_chunks;
+        const uint32_t *s = reinterpret_cast<const uint32_t *>(strip + row * S + 4 + 8 * xc);
+        *reinterpret_cast<uint2 *>(frame + (size_t)(y0 + row) * width + 8 * xc) = make_uint2(s[0], s[1]);
+    }
+    (void)mbh;
 }
 
-__global__ void __launch_bounds__(1024)
-k_loop_filter(LFPlanes planes, int first_plane, const int *__restrict__ seg, const int *__restrict__ mb_mask,
-              const vp8b200_segment_data *__restrict__ SD, int luma_width, int luma_height) {
-    __shared__ int s_stop;
-    const int plane = first_plane + blockIdx.x;
+// ctrl[0] = ticket counter, ctrl[1 + plane*max_rows + row] = progress of that row
+__global__ void __launch_bounds__(LF_THREADS)
+k_loop_filter(LFPlanes planes, int first_plane, int num_planes, const int *__restrict__ seg,
+              const int *__restrict__ mb_mask, const vp8b200_segment_data *__restrict__ SD, int luma_width,
+              int luma_height, int *ctrl, int max_rows) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ int s_ticket, s_stop;
+    const int mbw = luma_width / 16, mbh = luma_height / 16, mb_count = mbw * mbh;
+    if (threadIdx.x == 0) {
+        s_ticket = atomicAdd(&ctrl[0], 1);
+        s_stop = mb_count;
+    }
+    __syncthreads();
+    // "if (SD[i].loop_filter_level == 0) return;" ends the WHOLE plane at the first such macroblock
+    // in raster order (Q6): find that index
+    unsigned zero_mask = 0;  // segments whose filter level is 0
+#pragma unroll
+    for (int sgm = 0; sgm < 4; ++sgm) zero_mask |= (SD[sgm].loop_filter_level == 0) << sgm;
+    if (zero_mask) {  // rare: scan the segment map for the first such macroblock
+        int first = mb_count;
+        for (int mb = threadIdx.x; mb < mb_count && first == mb_count; mb += LF_THREADS)
+            if ((zero_mask >> seg[mb]) & 1) first = mb;
+        if (first < mb_count) atomicMin(&s_stop, first);
+    }
+    __syncthreads();
+    const int t = s_ticket;
+    const int plane = first_plane + t % num_planes, r = t / num_planes;
+    if (r >= mbh) return;
+    int *progress = ctrl + 1 + (plane - first_plane) * max_rows + r;
     if (plane == 0)
-        lf_plane<16>(planes.ptr[0], seg, mb_mask, SD, luma_width, luma_height, &s_stop);
+        lf_row<16>(planes.ptr[0], seg, mb_mask, SD, luma_width, luma_height, r, s_stop, progress, smem);
     else
-        lf_plane<8>(planes.ptr[plane], seg, mb_mask, SD, luma_width / 2, luma_height / 2, &s_stop);
+        lf_row<8>(planes.ptr[plane], seg, mb_mask, SD, luma_width / 2, luma_height / 2, r, s_stop, progress, smem);
 }
 
 // one warp per macroblock: sum of |coefficient| over the positions the entropy coder will
@@ -209,6 +340,34 @@ __global__ void k_prepare_filter_mask(const int *__restrict__ MB, int *__restric
 
 using namespace vp8;
 
+// ticket + progress counters, one allocation per process (launches on different streams must
+// not overlap; the engine and the shim use a single stream)
+static int *g_lf_ctrl = nullptr;
+static const int LF_MAX_ROWS = 2048;
+
+static int launch_loop_filter(void *stream, LFPlanes p, int first_plane, int num_planes, const int32_t *seg,
+                              const int32_t *mb_mask, const vp8b200_segment_data *SD, int luma_w, int luma_h) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int mbh = luma_h / 16;
+    if (mbh > LF_MAX_ROWS) return -(int)cudaErrorInvalidValue;
+    if (!g_lf_ctrl && cudaMalloc((void **)&g_lf_ctrl, sizeof(int) * (1 + 3 * LF_MAX_ROWS)) != cudaSuccess)
+        return -(int)cudaErrorMemoryAllocation;
+    cudaMemsetAsync(g_lf_ctrl, 0, sizeof(int) * (1 + (size_t)num_planes * LF_MAX_ROWS), st);
+    const int strip_w = first_plane == 0 ? luma_w : luma_w / 2;
+    const int strip_n = first_plane == 0 ? 16 : 8;
+    const size_t smem = (((size_t)strip_n * (strip_w + 4) + 15) & ~(size_t)15) + (size_t)(luma_w / 16) * sizeof(int4) +
+                        8 * 16 * sizeof(uint32_t) + 16;  // strip + limits + top-line ring + flags
+    static size_t configured = 0;
+    if (smem > configured) {
+        if (cudaFuncSetAttribute(k_loop_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return -(int)cudaGetLastError();
+        configured = smem;
+    }
+    k_loop_filter<<<mbh * num_planes, LF_THREADS, smem, st>>>(p, first_plane, num_planes, seg, mb_mask, SD, luma_w, luma_h,
+                                                             g_lf_ctrl, LF_MAX_ROWS);
+    VP8_LAUNCH_CHECK();
+}
+
 extern "C" int vp8b200_prepare_filter_mask(void *stream, const int16_t *MB, int32_t *nz, const int32_t *parts,
                                            int32_t *mb_mask, int width, int height) {
     const int M = (width / 16) * (height / 16);
@@ -223,11 +382,8 @@ extern "C" int vp8b200_loop_filter_frame(void *stream, uint8_t *frame, const int
     LFPlanes p;
     p.ptr[0] = p.ptr[1] = p.ptr[2] = frame;
     // the chroma path takes the LUMA size and halves it
-    if (mb_size == 16)
-        k_loop_filter<<<1, 1024, 0, (cudaStream_t)stream>>>(p, 0, seg, mb_mask, SD, width, height);
-    else
-        k_loop_filter<<<1, 1024, 0, (cudaStream_t)stream>>>(p, 1, seg, mb_mask, SD, width * 2, height * 2);
-    VP8_LAUNCH_CHECK();
+    if (mb_size == 16) return launch_loop_filter(stream, p, 0, 1, seg, mb_mask, SD, width, height);
+    return launch_loop_filter(stream, p, 1, 1, seg, mb_mask, SD, width * 2, height * 2);
 }
 
 extern "C" int vp8b200_loop_filter_planes(void *stream, uint8_t *y, uint8_t *u, uint8_t *v, const int32_t *seg,
@@ -238,6 +394,5 @@ extern "C" int vp8b200_loop_filter_planes(void *stream, uint8_t *y, uint8_t *u, 
     p.ptr[0] = y;
     p.ptr[1] = u;
     p.ptr[2] = v;
-    k_loop_filter<<<3, 1024, 0, (cudaStream_t)stream>>>(p, 0, seg, mb_mask, SD, width, height);
-    VP8_LAUNCH_CHECK();
+    return launch_loop_filter(stream, p, 0, 3, seg, mb_mask, SD, width, height);
 }
