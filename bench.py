@@ -154,6 +154,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ref-frames", type=int, default=6, help="timed frames of the CPU reference sample")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-procs", type=int, default=0, help="encoder instances per GPU for the e2e run (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -323,29 +324,66 @@ def b200_arm(args, rank, world, local_rank, tmp, config):
     e.close()
 
     # ---- end to end: the unmodified reference host against our OpenCL shim -------------------------
+    # Every rank runs `procs` encoder instances on its GPU, each on its own keyframe-delimited
+    # segment of 1 + W + K frames (vp8oclenc_b200/segments.py); frames/s counts the frames all
+    # instances finish between "every instance is past its warm-up" and "the last instance is done".
     e2e = None
-    if rank == 0 and not args.no_e2e:
-        host_bin = os.path.join(ROOT, "vp8oclenc_b200", "bin", "vp8enc")
-        lib_dir = os.path.join(ROOT, "vp8oclenc_b200", "lib")
-        if os.path.exists(host_bin):
+    if not args.no_e2e:
+        from vp8oclenc_b200 import segments
+        if os.path.exists(segments.HOST_BIN):
             n = 1 + W + K
-            y4m = os.path.join(tmp, "clip.y4m")
-            gen_y4m.write_y4m(y4m, WIDTH, HEIGHT, n)
-            stats = os.path.join(tmp, "shim_stats.json")
-            stamps, _ = run_encoder_timed(host_bin, lib_dir, os.path.join(tmp, "run"), y4m, os.path.join(tmp, "out.ivf"), n,
-                                          {"VP8B200_STATS": stats, "VP8B200_DEVICE": str(local_rank)})
-            dt = stamps[-1] - stamps[W]
-            e2e = {"value": K / dt, "unit": "frames/s", "ms_per_step": 1000.0 * dt / K, "processes": 1,
+
+            def run(P, tag):
+                paths = []
+                for p in range(P):
+                    y4m = os.path.join(tmp, "e2e_%s_%d_%d.y4m" % (tag, rank, p))
+                    gen_y4m.write_y4m(y4m, WIDTH, HEIGHT, n, start=(rank * P + p) * n)
+                    paths.append(y4m)
+                if dist:
+                    dist.barrier()
+                procs = [segments.EncoderProcess(paths[p], paths[p][:-4] + ".ivf", ENC_ARGS,
+                                                 os.path.join(tmp, "run_%s_%d_%d" % (tag, rank, p)), device=local_rank,
+                                                 env_extra={"VP8B200_STATS": paths[p][:-4] + ".stats"}) for p in range(P)]
+                stamps = [pr.wait() for pr in procs]
+                for st in stamps:
+                    if len(st) != n:
+                        raise RuntimeError("an encoder instance finished %d of %d frames" % (len(st), n))
+                t0 = max(st[W] for st in stamps)
+                t1 = max(st[-1] for st in stamps)
+                if dist:  # one window for all ranks (perf_counter is a per-host monotonic clock; one node)
+                    tt = torch.tensor([t0, t1], device="cuda", dtype=torch.float64)
+                    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                    t0, t1 = float(tt[0].item()), float(tt[1].item())
+                count = sum(1 for st in stamps for x in st if x > t0)
+                if dist:
+                    cc = torch.tensor([float(count)], device="cuda", dtype=torch.float64)
+                    dist.all_reduce(cc, op=dist.ReduceOp.SUM)
+                    count = int(cc.item())
+                h2d = d2h = launches_ps = None
+                try:
+                    s0 = json.load(open(paths[0][:-4] + ".stats"))
+                    h2d, d2h, launches_ps = int(s0["h2d_bytes"] / n), int(s0["d2h_bytes"] / n), s0["kernel_launches"] / n
+                except Exception:
+                    pass
+                for pth in paths:
+                    for ext in (".y4m", ".ivf"):
+                        try:
+                            os.remove(pth[:-4] + ext)
+                        except OSError:
+                            pass
+                return count / (t1 - t0), count, h2d, d2h, launches_ps
+
+            P = args.e2e_procs or max(1, min(8, (os.cpu_count() or 2) // max(2, 2 * world)))
+            fps1, _, h2d, d2h, lps = run(1, "single")
+            fpsP, cnt, _, _, _ = (fps1, K, 0, 0, 0) if P == 1 else run(P, "multi")
+            best = max(fps1, fpsP)
+            e2e = {"value": best, "unit": "frames/s", "ms_per_step": 1000.0 / best,
+                   "processes_per_gpu": P if fpsP >= fps1 else 1, "single_process_fps": fps1 * (1 if not dist else 1),
+                   "multi_process_fps": fpsP, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                   "shim_kernel_launches_per_step": lps,
                    "what": "unmodified reference host (vp8enc.cpp + entropy_host.cpp) + libOpenCL.so.1 shim; Y4M file in, "
-                           "IVF file out; all host<->device copies, host intra/entropy work and file I/O included"}
-            try:
-                s = json.load(open(stats))
-                frames_counted = max(1, n)
-                e2e["h2d_bytes_per_step"] = int(s["h2d_bytes"] / frames_counted)
-                e2e["d2h_bytes_per_step"] = int(s["d2h_bytes"] / frames_counted)
-                e2e["shim_kernel_launches_per_step"] = s["kernel_launches"] / frames_counted
-            except Exception:
-                e2e["h2d_bytes_per_step"] = e2e["d2h_bytes_per_step"] = None
+                           "IVF file out; all host<->device copies, host intra/entropy work and file I/O included; "
+                           "instances encode independent keyframe-delimited segments (no collective)"}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
