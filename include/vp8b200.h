@@ -99,6 +99,18 @@ int vp8b200_count_SSIM(void *stream, const uint8_t *frame1, const uint8_t *frame
 int vp8b200_gather_SSIM(void *stream, const float *metric1, const float *metric2, const float *metric3,
                         float *MB_SSIM, int mb_count);
 
+/* ONE launch for the tail of inter_transform() (src/inter_part.h:268-378): replaces
+ * prepare_predictors_and_residual x9, and per segment dct4x4 x3, wht4x4_iwht4x4, idct4x4 x3,
+ * count_SSIM_luma, count_SSIM_chroma x2, gather_SSIM (53 launches).  img[3*ref + plane] are the
+ * reference planes (NULL where a reference is unused).  Predictors/residuals stay on chip.
+ * Requires SSIM_target >= -2 (true for every value the reference's CLI can produce). */
+int vp8b200_mb_predict_transform_fused(void *stream, const uint8_t *cur_y, const uint8_t *cur_u, const uint8_t *cur_v,
+                                       const uint8_t *const img[9], const int32_t *MB_reference_frame,
+                                       const int16_t *MB_vectors, const int32_t *MB_parts, int16_t *MB,
+                                       int32_t *MB_segment_id, float *MB_SSIM, uint8_t *recon_y, uint8_t *recon_u,
+                                       uint8_t *recon_v, const vp8b200_segment_data *SD, float SSIM_target, int width,
+                                       int height);
+
 /* replaces prepare_filter_mask, src/CPU_kernels.cl:782-827 (src/loop_filter.h:25-33) */
 int vp8b200_prepare_filter_mask(void *stream, const int16_t *MB, int32_t *MB_non_zero_coeffs,
                                 const int32_t *MB_parts, int32_t *mb_mask, int width, int height);

@@ -18,13 +18,15 @@ pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not torch.cuda.is_available(),
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 
-def run_sequence(w, h, nframes, altref_range, ssim_target, qi, host_api):
+def run_sequence(w, h, nframes, altref_range, ssim_target, qi, host_api, fused=True):
     import gen_y4m
     from vp8oclenc_b200 import host as eng
     o = oracle()
     clip = gen_y4m.Clip(w, h)
     M = (w // 16) * (h // 16)
+    os.environ["VP8B200_FUSED"] = "1" if fused else "0"  # read by vp8b200_engine_create
     e = eng.Engine(w, h)
+    os.environ.pop("VP8B200_FUSED")
     ctx = ctypes.c_void_p(o.vp8o_ctx_create(w, h))
     state = _trace.HostState(10 ** 6, altref_range)
     sd = make_segment_data(qi)
@@ -88,6 +90,17 @@ def test_engine_sequence_cif_three_references():
 
 def test_engine_sequence_ssim_ladder():
     run_sequence(352, 288, 6, 3, 0.93, (6, 20, 35, 50), host_api=False)
+
+
+@pytest.mark.parametrize("target", [-1.0, 0.93])
+def test_engine_kernel_per_kernel_sequence(target):
+    """the unfused path (one launch per reference kernel, as the OpenCL shim replays it)"""
+    run_sequence(352, 288, 5, 3, target, (6, 20, 35, 50), host_api=False, fused=False)
+
+
+def test_engine_odd_macroblock_counts():
+    """sizes whose macroblock count is not a multiple of the fused kernel's CTA size"""
+    run_sequence(208, 176, 4, 3, 0.9, (10, 24, 40, 60), host_api=False)
 
 
 def test_engine_host_buffers_api():

@@ -1,6 +1,7 @@
 // Frame-level engine (see include/vp8b200.h): owns the per-frame device buffers and runs the
 // reference's enqueue sequence (src/inter_part.h:1-384, src/loop_filter.h) on one CUDA stream.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -26,6 +27,7 @@ struct vp8b200_engine {
     cudaEvent_t sd_event[8];
     int sd_next;
     int launches;
+    bool fused;  // VP8B200_FUSED=0 selects the kernel-per-kernel sequence
 };
 
 namespace {
@@ -52,6 +54,7 @@ extern "C" vp8b200_engine *vp8b200_engine_create(int width, int height, void *st
     e->w = width;
     e->h = height;
     e->M = (width / 16) * (height / 16);
+    { const char *f = getenv("VP8B200_FUSED"); e->fused = !(f && f[0] == '0'); }
     if (stream) {
         e->stream = (cudaStream_t)stream;
     } else {
@@ -208,6 +211,15 @@ static int inter_frame_body(vp8b200_engine *e, const uint8_t *cur_y, const uint8
                                  e->ref_frame, e->vectors, w, h, use_golden, use_altref));
     TRY(vp8b200_pack_8x8_into_16x16(s, e->vectors, e->parts, e->ssim, M));
 
+    if (e->fused && SSIM_target >= -2.0f) {
+        const uint8_t *img[9];
+        for (int r = 0; r < 3; ++r)
+            for (int p = 0; p < 3; ++p) img[3 * r + p] = use[r] ? e->img[r][p] : nullptr;
+        TRY(vp8b200_mb_predict_transform_fused(s, cur_y, cur_u, cur_v, img, e->ref_frame, e->vectors, e->parts, e->coeffs,
+                                               e->seg_id, e->ssim, recon[0], recon[1], recon[2], e->sd_dev, SSIM_target,
+                                               w, h));
+        return 0;
+    }
     for (int p = 0; p < 3; ++p)
         for (int r = 0; r < 3; ++r)
             if (use[r])
