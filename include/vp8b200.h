@@ -60,6 +60,16 @@ int vp8b200_luma_search_1step(void *stream, const uint8_t *current_frame, const 
 int vp8b200_luma_search_2step(void *stream, const uint8_t *current_frame, const uint8_t *ref_frame,
                               const int16_t *net, int16_t *ref_net, int32_t *ref_Bdiff, int width, int height);
 
+/* The same two kernels for up to three references (LAST, GOLDEN, ALTREF) in ONE launch: the host
+ * enqueues the per-reference instances back to back on three queues (src/inter_part.h:122-135 and
+ * the following levels); they are independent, so they run as grid.y = nrefs. */
+int vp8b200_luma_search_1step_multi(void *stream, const uint8_t *current_frame, int nrefs,
+                                    const uint8_t *const *prev_frame, const int16_t *const *src_net,
+                                    int16_t *const *dst_net, int net_width, int width, int height, int pixel_rate);
+int vp8b200_luma_search_2step_multi(void *stream, const uint8_t *current_frame, int nrefs,
+                                    const uint8_t *const *ref_frame, const int16_t *const *net, int16_t *const *ref_net,
+                                    int32_t *const *ref_Bdiff, int width, int height);
+
 /* replaces select_reference, src/GPU_kernels.cl:1205-1283 (src/inter_part.h:250-255) */
 int vp8b200_select_reference(void *stream, const int16_t *last_net, const int16_t *golden_net,
                              const int16_t *altref_net, const int32_t *last_Bdiff, const int32_t *golden_Bdiff,

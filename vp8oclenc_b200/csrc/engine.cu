@@ -197,15 +197,44 @@ static int inter_frame_body(vp8b200_engine *e, const uint8_t *cur_y, const uint8
     // pyramid search, src/inter_part.h:109-236; nets ping-pong 1->2, 2->1, 1->2, 2->1, 1->2, qpel 2->1 (Q4)
     uint8_t **pyr[3] = {e->last_pyr, e->gold_pyr, e->alt_pyr};
     const int use[3] = {1, use_golden, use_altref};
-    for (int k = 4; k >= 0; --k) {
-        const int src = (k & 1) ? 1 : 0;
+    if (e->fused) {
+        // the references in use are searched by one launch per level (grid.y = reference)
+        int nrefs = 0;
+        const uint8_t *rp[3];
+        const int16_t *sn[3];
+        int16_t *dn[3];
+        int32_t *met[3];
+        int rid[3];
+        for (int r = 0; r < 3; ++r)
+            if (use[r]) rid[nrefs++] = r;
+        for (int k = 4; k >= 0; --k) {
+            const int src = (k & 1) ? 1 : 0;
+            for (int i = 0; i < nrefs; ++i) {
+                rp[i] = pyr[rid[i]][k];
+                sn[i] = e->net[rid[i]][src];
+                dn[i] = e->net[rid[i]][src ^ 1];
+            }
+            TRY(vp8b200_luma_search_1step_multi(s, cpyr[k], nrefs, rp, sn, dn, (w / 16) * 2, w >> k, h >> k, 1 << k));
+        }
+        for (int i = 0; i < nrefs; ++i) {
+            rp[i] = e->img[rid[i]][0];
+            sn[i] = e->net[rid[i]][1];
+            dn[i] = e->net[rid[i]][0];
+            met[i] = e->metrics[rid[i]];
+        }
+        TRY(vp8b200_luma_search_2step_multi(s, cur_y, nrefs, rp, sn, dn, met, w, h));
+    } else {
+        for (int k = 4; k >= 0; --k) {
+            const int src = (k & 1) ? 1 : 0;
+            for (int r = 0; r < 3; ++r)
+                if (use[r])
+                    TRY(vp8b200_luma_search_1step(s, cpyr[k], pyr[r][k], e->net[r][src], e->net[r][src ^ 1], (w / 16) * 2,
+                                                  w >> k, h >> k, 1 << k));
+        }
         for (int r = 0; r < 3; ++r)
             if (use[r])
-                TRY(vp8b200_luma_search_1step(s, cpyr[k], pyr[r][k], e->net[r][src], e->net[r][src ^ 1], (w / 16) * 2,
-                                              w >> k, h >> k, 1 << k));
+                TRY(vp8b200_luma_search_2step(s, cur_y, e->img[r][0], e->net[r][1], e->net[r][0], e->metrics[r], w, h));
     }
-    for (int r = 0; r < 3; ++r)
-        if (use[r]) TRY(vp8b200_luma_search_2step(s, cur_y, e->img[r][0], e->net[r][1], e->net[r][0], e->metrics[r], w, h));
 
     TRY(vp8b200_select_reference(s, e->net[0][0], e->net[1][0], e->net[2][0], e->metrics[0], e->metrics[1], e->metrics[2],
                                  e->ref_frame, e->vectors, w, h, use_golden, use_altref));

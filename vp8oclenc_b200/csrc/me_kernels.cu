@@ -44,10 +44,25 @@ __global__ void k_downsample_x2(const uint8_t *__restrict__ src, uint8_t *__rest
 constexpr int S1_BLOCKS = 8;             // 8x8 blocks per CTA
 constexpr int S1_THREADS = S1_BLOCKS * 100;  // (25 candidates x 4 sub-blocks) per block = 25 full warps
 
+// up to three references (LAST / GOLDEN / ALTREF) searched by one launch: blockIdx.y picks the set
+struct Search1Refs {
+    const uint8_t *prev[3];
+    const short2 *src_net[3];
+    short2 *dst_net[3];
+};
+struct Search2Refs {
+    const uint8_t *ref[3];
+    const short2 *net[3];
+    short2 *ref_net[3];
+    int *ref_Bdiff[3];
+};
+
 __global__ void __launch_bounds__(S1_THREADS)
-k_luma_search_1step(const uint8_t *__restrict__ cur, const uint8_t *__restrict__ prev,
-                    const short2 *__restrict__ src_net, short2 *__restrict__ dst_net, int net_width, int width,
-                    int height, int rate, int nblocks) {
+k_luma_search_1step(const uint8_t *__restrict__ cur, Search1Refs refs, int net_width, int width, int height, int rate,
+                    int nblocks) {
+    const uint8_t *__restrict__ prev = refs.prev[blockIdx.y];
+    const short2 *__restrict__ src_net = refs.src_net[blockIdx.y];
+    short2 *__restrict__ dst_net = refs.dst_net[blockIdx.y];
     __shared__ uint8_t s_win[S1_BLOCKS][12][12];   // prev pixels [c+v0-2, c+v0+10) in both axes
     __shared__ uint8_t s_cur[S1_BLOCKS][8][8];
     __shared__ int s_cx[S1_BLOCKS], s_cy[S1_BLOCKS], s_vx[S1_BLOCKS], s_vy[S1_BLOCKS];
@@ -150,9 +165,11 @@ __device__ __forceinline__ int s2_origin(int i) { return i < 2 ? -1 : 0; }
 __device__ __forceinline__ int s2_phase(int i) { return (0x46024 >> (4 * (4 - i))) & 15; }
 
 __global__ void __launch_bounds__(S2_THREADS)
-k_luma_search_2step(const uint8_t *__restrict__ cur, const uint8_t *__restrict__ ref,
-                    const short2 *__restrict__ net, short2 *__restrict__ ref_net, int *__restrict__ ref_Bdiff,
-                    int width, int height) {
+k_luma_search_2step(const uint8_t *__restrict__ cur, Search2Refs refs, int width, int height) {
+    const uint8_t *__restrict__ ref = refs.ref[blockIdx.y];
+    const short2 *__restrict__ net = refs.net[blockIdx.y];
+    short2 *__restrict__ ref_net = refs.ref_net[blockIdx.y];
+    int *__restrict__ ref_Bdiff = refs.ref_Bdiff[blockIdx.y];
     __shared__ uint8_t s_win[14][16];      // ref pixels rows/cols [base-3, base+11), clamp-to-edge
     __shared__ uint32_t s_h[5][14][2];     // horizontally filtered + saturated lines, 8 px per row
     __shared__ uint32_t s_cur[8][2];
@@ -323,19 +340,46 @@ extern "C" int vp8b200_downsample_x2(void *stream, const uint8_t *src, uint8_t *
 
 extern "C" int vp8b200_luma_search_1step(void *stream, const uint8_t *cur, const uint8_t *prev, const int16_t *src_net,
                                          int16_t *dst_net, int net_width, int width, int height, int rate) {
+    return vp8b200_luma_search_1step_multi(stream, cur, 1, &prev, &src_net, &dst_net, net_width, width, height, rate);
+}
+
+extern "C" int vp8b200_luma_search_1step_multi(void *stream, const uint8_t *cur, int nrefs, const uint8_t *const *prev,
+                                               const int16_t *const *src_net, int16_t *const *dst_net, int net_width,
+                                               int width, int height, int rate) {
     const int nblocks = (width / 8) * (height / 8);
-    if (nblocks <= 0) return 0;
-    k_luma_search_1step<<<(nblocks + S1_BLOCKS - 1) / S1_BLOCKS, S1_THREADS, 0, (cudaStream_t)stream>>>(
-        cur, prev, (const short2 *)src_net, (short2 *)dst_net, net_width, width, height, rate, nblocks);
+    if (nblocks <= 0 || nrefs <= 0) return 0;
+    if (nrefs > 3) return -(int)cudaErrorInvalidValue;
+    Search1Refs r = {};
+    for (int i = 0; i < nrefs; ++i) {
+        r.prev[i] = prev[i];
+        r.src_net[i] = (const short2 *)src_net[i];
+        r.dst_net[i] = (short2 *)dst_net[i];
+    }
+    dim3 grid((nblocks + S1_BLOCKS - 1) / S1_BLOCKS, nrefs);
+    k_luma_search_1step<<<grid, S1_THREADS, 0, (cudaStream_t)stream>>>(cur, r, net_width, width, height, rate, nblocks);
     VP8_LAUNCH_CHECK();
 }
 
 extern "C" int vp8b200_luma_search_2step(void *stream, const uint8_t *cur, const uint8_t *ref, const int16_t *net,
                                          int16_t *ref_net, int32_t *ref_Bdiff, int width, int height) {
+    return vp8b200_luma_search_2step_multi(stream, cur, 1, &ref, &net, &ref_net, &ref_Bdiff, width, height);
+}
+
+extern "C" int vp8b200_luma_search_2step_multi(void *stream, const uint8_t *cur, int nrefs, const uint8_t *const *ref,
+                                               const int16_t *const *net, int16_t *const *ref_net,
+                                               int32_t *const *ref_Bdiff, int width, int height) {
     const int nblocks = width * height / 64;
-    if (nblocks <= 0) return 0;
-    k_luma_search_2step<<<nblocks, S2_THREADS, 0, (cudaStream_t)stream>>>(cur, ref, (const short2 *)net,
-                                                                         (short2 *)ref_net, ref_Bdiff, width, height);
+    if (nblocks <= 0 || nrefs <= 0) return 0;
+    if (nrefs > 3) return -(int)cudaErrorInvalidValue;
+    Search2Refs r = {};
+    for (int i = 0; i < nrefs; ++i) {
+        r.ref[i] = ref[i];
+        r.net[i] = (const short2 *)net[i];
+        r.ref_net[i] = (short2 *)ref_net[i];
+        r.ref_Bdiff[i] = ref_Bdiff[i];
+    }
+    dim3 grid(nblocks, nrefs);
+    k_luma_search_2step<<<grid, S2_THREADS, 0, (cudaStream_t)stream>>>(cur, r, width, height);
     VP8_LAUNCH_CHECK();
 }
 
