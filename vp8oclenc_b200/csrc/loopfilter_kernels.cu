@@ -27,25 +27,29 @@ namespace vp8 {
 
 __device__ __forceinline__ int c128(int v) { return min(max(v, -128), 127); }
 
-__device__ __forceinline__ bool lf_mask(int p3, int p2, int p1, int p0, int q0, int q1, int q2, int q3, int e_lim,
-                                        int i_lim) {
-    return !(abs(p3 - p2) > i_lim || abs(p2 - p1) > i_lim || abs(p1 - p0) > i_lim || abs(q1 - q0) > i_lim ||
-             abs(q2 - q1) > i_lim || abs(q3 - q2) > i_lim || (abs(p0 - q0) * 2 + (abs(p1 - q1) >> 1)) > e_lim);
+// branch-free on purpose: the lanes of the filtering warp take different decisions per pixel line,
+// short-circuit evaluation would serialise them
+__device__ __forceinline__ int lf_over(int a, int b, int lim) { return abs(a - b) > lim; }
+
+__device__ __forceinline__ int lf_filter_off(int p3, int p2, int p1, int p0, int q0, int q1, int q2, int q3, int e_lim,
+                                             int i_lim) {
+    return lf_over(p3, p2, i_lim) | lf_over(p2, p1, i_lim) | lf_over(p1, p0, i_lim) | lf_over(q1, q0, i_lim) |
+           lf_over(q2, q1, i_lim) | lf_over(q3, q2, i_lim) | ((abs(p0 - q0) * 2 + (abs(p1 - q1) >> 1)) > e_lim);
 }
 
 // macroblock edge (filter_mb_edge8, src/CPU_kernels.cl:829-883), one lane
 __device__ __forceinline__ void filter_mb_edge(int p3, int &p2, int &p1, int &p0, int &q0, int &q1, int &q2, int q3,
                                                int mb_lim, int int_lim, int hev_thr) {
-    const bool mask = lf_mask(p3, p2, p1, p0, q0, q1, q2, q3, mb_lim, int_lim);
-    const bool hev = abs(p1 - p0) > hev_thr || abs(q1 - q0) > hev_thr;
+    const int off = lf_filter_off(p3, p2, p1, p0, q0, q1, q2, q3, mb_lim, int_lim);
+    const int hev = lf_over(p1, p0, hev_thr) | lf_over(q1, q0, hev_thr);
     int w = c128(c128(p1 - q1) + 3 * (q0 - p0));
-    if (!mask) w = 0;
+    w = off ? 0 : w;
     int a = hev ? w : 0;
     const int b = c128(a + 3) >> 3;
     a = c128(a + 4) >> 3;
     q0 -= a;
     p0 += b;
-    if (hev) w = 0;
+    w = hev ? 0 : w;
     a = c128((27 * w + 63) >> 7);
     q0 -= a;
     p0 += a;
@@ -60,17 +64,17 @@ __device__ __forceinline__ void filter_mb_edge(int p3, int &p2, int &p1, int &p0
 // inner (sub-block) edge (filter_b_edge8, src/CPU_kernels.cl:885-926), one lane
 __device__ __forceinline__ void filter_b_edge(int p3, int p2, int &p1, int &p0, int &q0, int &q1, int q2, int q3,
                                               int b_lim, int int_lim, int hev_thr) {
-    const bool mask = lf_mask(p3, p2, p1, p0, q0, q1, q2, q3, b_lim, int_lim);
-    const bool hev = abs(p1 - p0) > hev_thr || abs(q1 - q0) > hev_thr;
+    const int off = lf_filter_off(p3, p2, p1, p0, q0, q1, q2, q3, b_lim, int_lim);
+    const int hev = lf_over(p1, p0, hev_thr) | lf_over(q1, q0, hev_thr);
     int a = hev ? c128(p1 - q1) : 0;
     a = c128(a + 3 * (q0 - p0));
-    if (!mask) a = 0;
+    a = off ? 0 : a;
     const int b = c128(a + 3) >> 3;
     a = c128(a + 4) >> 3;
     q0 -= a;
     p0 += b;
     a = (a + 1) >> 1;
-    if (hev) a = 0;
+    a = hev ? 0 : a;
     q1 -= a;
     p1 += a;
 }
@@ -90,10 +94,16 @@ __device__ __forceinline__ void filter_line(int (&v)[N + 4], bool mb_edge, bool 
     }
 }
 
+// four (pixel-128) values -> four saturated pixels: sat_s8 then flip the sign bits
+// (cvt.pack.sat.s8.s32: d = c<<16 | sat(a)<<8 | sat(b))
 __device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d) {
-    return (uint32_t)sat8(a + 128) | ((uint32_t)sat8(b + 128) << 8) | ((uint32_t)sat8(c + 128) << 16) |
-           ((uint32_t)sat8(d + 128) << 24);
+    uint32_t hi, r;
+    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(d), "r"(c), "r"(0));
+    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(b), "r"(a), "r"(hi));
+    return r ^ 0x80808080u;
 }
+// byte k of a word of pixels -> pixel-128 (flip the sign bit, sign-extend)
+__device__ __forceinline__ int unpack1(uint32_t w_flipped, int k) { return (int)(signed char)(w_flipped >> (8 * k)); }
 
 __device__ __forceinline__ int ld_acquire(const int *p) {
     int v;
@@ -114,104 +124,119 @@ struct LFPlanes {
     uint8_t *ptr[3];
 };
 
-constexpr int LF_THREADS = 128;
+// warps: 3 per plane slot (filter, receiver, sender); up to 3 plane slots per CTA
+constexpr int LF_THREADS = 288;
+constexpr int LF_TOPQ = 8;  // depth of the top-line ring
 
-// one macroblock row of one plane; smem = strip of N rows, stride S = width + 4 (word stride
-// odd -> the row-per-lane accesses of the horizontal pass are bank-conflict free), then the
-// per-macroblock limits
+// shared-memory layout of one plane slot
+struct LFSlot {
+    uint8_t *strip;        // N rows, stride S = width + 4 (word stride odd: pass 1 is bank-conflict free)
+    int4 *lims;            // per macroblock {mb_lim, b_lim, int_lim, hev_thr | inner<<16}
+    uint32_t *topq;        // [LF_TOPQ][4 lines][N/4 words]: the four pixel lines above each macroblock
+    volatile int *flags;   // h_done, v_done, top_ready
+};
+__host__ __device__ inline size_t lf_slot_bytes(int n, int width) {
+    return (((size_t)n * (width + 4) + 15) & ~(size_t)15) + (size_t)(width / n) * 16 + (size_t)LF_TOPQ * n * 4 + 16;
+}
+__device__ inline LFSlot lf_slot(unsigned char *base, int n, int width) {
+    LFSlot s;
+    s.strip = base;
+    s.lims = reinterpret_cast<int4 *>(base + (((size_t)n * (width + 4) + 15) & ~(size_t)15));
+    s.topq = reinterpret_cast<uint32_t *>(s.lims + width / n);
+    s.flags = reinterpret_cast<volatile int *>(s.topq + LF_TOPQ * n);
+    return s;
+}
+
+// Rows hand their bottom pixel lines to the row below through a "tagged mailbox" in global memory:
+// 32 words per macroblock, each carrying two pixels and a 16-bit launch tag.  A word is written
+// atomically, so a reader that sees the current tag in a word also sees that word's pixels: one
+// round trip, no fence, no separate flag.  Tags differ from launch to launch (the host wraps them
+// safely), every slot that is read in a launch is written in the same launch.
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 template <int N>
-__device__ void lf_row(uint8_t *__restrict__ frame, const int *__restrict__ seg, const int *__restrict__ mb_mask,
-                       const vp8b200_segment_data *__restrict__ SD, int width, int height, int r, int stop,
-                       int *progress, unsigned char *smem) {
-    const int mbw = width / N, mbh = height / N;
+__device__ void lf_plane_roles(uint8_t *__restrict__ frame, int width, int r, int ncols, bool row_below_exists,
+                               int stop_below_cols, LFSlot sl, uint32_t *mail_row, const uint32_t *mail_above,
+                               unsigned tag, int role, int lane) {
     const int S = width + 4;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int ncols = max(0, min(mbw, stop - r * mbw));  // macroblocks of this row before the Q6 stop
-    if (ncols == 0) return;
-    uint8_t *strip = smem;
-    int4 *lims = reinterpret_cast<int4 *>(smem + ((N * S + 15) & ~15));  // {mb_lim, b_lim, int_lim, hev_thr | inner<<16}
     const int y0 = r * N;
+    uint8_t *strip = sl.strip;
+    volatile int *flags = sl.flags;
+    uint32_t *topq = sl.topq;
+    constexpr int TOPQ = LF_TOPQ;
 
-    // ---- stage the strip and the per-macroblock limits ----
-    // 8-byte chunks: plane widths are multiples of 8 (chroma of a 16-aligned luma), rows 8-byte aligned
-    const int chunks = width / 8;
-    for (int i = tid; i < N * chunks; i += LF_THREADS) {
-        const int row = i / chunks, xc = i % chunks;
-        const uint2 v = *reinterpret_cast<const uint2 *>(frame + (size_t)(y0 + row) * width + 8 * xc);
-        uint32_t *d = reinterpret_cast<uint32_t *>(strip + row * S + 4 + 8 * xc);
-        d[0] = v.x; d[1] = v.y;
-    }
-    for (int c = tid; c < ncols; c += LF_THREADS) {
-        const int mb = r * mbw + c;
-        const vp8b200_segment_data *sd = SD + seg[mb];
-        lims[c] = make_int4((short)sd->mbedge_limit, (short)sd->sub_bedge_limit, (short)sd->interior_limit,
-                            ((short)sd->hev_threshold & 0xffff) | (mb_mask[mb] != 0 ? 0x10000 : 0));
-    }
-    __syncthreads();
-
-    // ---- the serial walk, warp-specialised so that warp 0 never waits for global memory ----
-    //   warp 0  filters: pass 1 (vertical edges) + pass 2 (horizontal edges) per macroblock, shared memory only
-    //   warp 1  prefetches the four pixel lines above each macroblock once the row above has finalised them
-    //   warp 2  publishes the bottom four lines of every finalised macroblock and the progress counter
-    // hand-offs between the three are counters in shared memory.
-    constexpr int TOPQ = 8;  // depth of the top-line ring
-    uint32_t *topq = reinterpret_cast<uint32_t *>(lims + mbw);             // [TOPQ][4 lines][N/4 words]
-    volatile int *flags = reinterpret_cast<volatile int *>(topq + TOPQ * N);  // h_done, v_done, top_ready
-    if (tid < 3) flags[tid] = 0;
-    __syncthreads();
-    const int *above = progress - 1;  // progress counter of row r-1 (only read when r > 0)
-
-    if (warp == 0) {
+    if (role == 0) {
+        // ---- filter warp: pass 1 (vertical edges) + pass 2 (horizontal edges), shared memory only ----
         for (int c = 0; c < ncols; ++c) {
-            const int4 lm = lims[c];
+            const int4 lm = sl.lims[c];
             const int mb_lim = lm.x, b_lim = lm.y, int_lim = lm.z, hev_thr = lm.w & 0xffff;
             const bool inner = (lm.w >> 16) != 0;
             const int x0 = c * N;
-            // pass 1: vertical edges, one lane per pixel row
-            if (lane < N) {
+            // Both passes walk the N/4 four-pixel groups of a line with a sliding window p3..p0 | q0..q3
+            // kept in registers: the unclamped q's of one edge are the p's of the next (Q7).
+            if (lane < N) {  // pass 1: one lane per pixel row
                 uint32_t *row = reinterpret_cast<uint32_t *>(strip + lane * S + 4 + x0);
-                uint32_t words[N / 4 + 1];
-                words[0] = c > 0 ? row[-1] : 0;
+                int p3, p2, p1, p0, q0, q1, q2, q3;
+                uint32_t w = row[0] ^ 0x80808080u;
+                q0 = unpack1(w, 0); q1 = unpack1(w, 1); q2 = unpack1(w, 2); q3 = unpack1(w, 3);
+                if (c > 0) {
+                    w = row[-1] ^ 0x80808080u;
+                    p3 = unpack1(w, 0); p2 = unpack1(w, 1); p1 = unpack1(w, 2); p0 = unpack1(w, 3);
+                    filter_mb_edge(p3, p2, p1, p0, q0, q1, q2, q3, mb_lim, int_lim, hev_thr);
+                    row[-1] = pack4(p3, p2, p1, p0);
+                }
 #pragma unroll
-                for (int k = 0; k < N / 4; ++k) words[k + 1] = row[k];
-                int v[N + 4];
-#pragma unroll
-                for (int k = 0; k < N + 4; ++k) v[k] = (int)((words[k >> 2] >> (8 * (k & 3))) & 255) - 128;
-                filter_line<N>(v, c > 0, inner, mb_lim, b_lim, int_lim, hev_thr);
-                if (c > 0) row[-1] = pack4(v[0], v[1], v[2], v[3]);
-#pragma unroll
-                for (int k = 0; k < N / 4; ++k) row[k] = pack4(v[4 * k + 4], v[4 * k + 5], v[4 * k + 6], v[4 * k + 7]);
+                for (int e = 1; e < N / 4; ++e) {
+                    p3 = q0; p2 = q1; p1 = q2; p0 = q3;
+                    w = row[e] ^ 0x80808080u;
+                    q0 = unpack1(w, 0); q1 = unpack1(w, 1); q2 = unpack1(w, 2); q3 = unpack1(w, 3);
+                    if (inner) filter_b_edge(p3, p2, p1, p0, q0, q1, q2, q3, b_lim, int_lim, hev_thr);
+                    row[e - 1] = pack4(p3, p2, p1, p0);
+                }
+                row[N / 4 - 1] = pack4(q0, q1, q2, q3);
             }
             __syncwarp();
             if (lane == 0) {
                 __threadfence_block();
                 flags[0] = c + 1;  // h_done: macroblock c-1 is final now
             }
-            // pass 2: horizontal edges, one lane per pixel column
             if (r > 0) {
-                while (flags[2] < c + 1) {}  // top lines of macroblock c are in the ring
+                while (flags[2] < c + 1) {}  // the lines above macroblock c are in the ring
                 __threadfence_block();
             }
-            if (lane < N) {
-                int v[N + 4];
+            if (lane < N) {  // pass 2: one lane per pixel column
+                uint8_t *scol = strip + 4 + x0 + lane;
+                int p3, p2, p1, p0, q0, q1, q2, q3;
+                q0 = (int)scol[0] - 128; q1 = (int)scol[S] - 128; q2 = (int)scol[2 * S] - 128; q3 = (int)scol[3 * S] - 128;
                 if (r > 0) {
                     const uint8_t *tq = reinterpret_cast<const uint8_t *>(topq + (c % TOPQ) * N) + lane;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) v[k] = (int)tq[k * N] - 128;
-                } else {
-                    v[0] = v[1] = v[2] = v[3] = 0;
-                }
-                uint8_t *scol = strip + 4 + x0 + lane;
-#pragma unroll
-                for (int k = 0; k < N; ++k) v[k + 4] = (int)scol[k * S] - 128;
-                filter_line<N>(v, r > 0, inner, mb_lim, b_lim, int_lim, hev_thr);
-                if (r > 0) {  // three lines of the row above now belong to this row: straight to global memory
+                    p3 = (int)tq[0] - 128; p2 = (int)tq[N] - 128; p1 = (int)tq[2 * N] - 128; p0 = (int)tq[3 * N] - 128;
+                    filter_mb_edge(p3, p2, p1, p0, q0, q1, q2, q3, mb_lim, int_lim, hev_thr);
+                    // the three lines above now belong to this row: straight to the frame
                     uint8_t *gcol = frame + (size_t)y0 * width + x0 + lane;
-#pragma unroll
-                    for (int k = 1; k < 4; ++k) gcol[(ptrdiff_t)(k - 4) * width] = (uint8_t)sat8(v[k] + 128);
+                    const uint32_t t = pack4(p3, p2, p1, p0);
+                    gcol[-3 * (ptrdiff_t)width] = (uint8_t)(t >> 8);
+                    gcol[-2 * (ptrdiff_t)width] = (uint8_t)(t >> 16);
+                    gcol[-1 * (ptrdiff_t)width] = (uint8_t)(t >> 24);
                 }
 #pragma unroll
-                for (int k = 0; k < N; ++k) scol[k * S] = (uint8_t)sat8(v[k + 4] + 128);
+                for (int e = 1; e < N / 4; ++e) {
+                    p3 = q0; p2 = q1; p1 = q2; p0 = q3;
+                    uint8_t *g = scol + 4 * e * S;
+                    q0 = (int)g[0] - 128; q1 = (int)g[S] - 128; q2 = (int)g[2 * S] - 128; q3 = (int)g[3 * S] - 128;
+                    if (inner) filter_b_edge(p3, p2, p1, p0, q0, q1, q2, q3, b_lim, int_lim, hev_thr);
+                    const uint32_t t = pack4(p3, p2, p1, p0);
+                    g[-4 * S] = (uint8_t)t; g[-3 * S] = (uint8_t)(t >> 8); g[-2 * S] = (uint8_t)(t >> 16); g[-S] = (uint8_t)(t >> 24);
+                }
+                {
+                    uint8_t *g = scol + (N - 4) * S;
+                    const uint32_t t = pack4(q0, q1, q2, q3);
+                    g[0] = (uint8_t)t; g[S] = (uint8_t)(t >> 8); g[2 * S] = (uint8_t)(t >> 16); g[3 * S] = (uint8_t)(t >> 24);
+                }
             }
             __syncwarp();
             if (lane == 0) {
@@ -219,19 +244,23 @@ __device__ void lf_row(uint8_t *__restrict__ frame, const int *__restrict__ seg,
                 flags[1] = c + 1;  // v_done
             }
         }
-    } else if (warp == 1) {
+    } else if (role == 1) {
+        // ---- receiver warp: the four lines above each macroblock, from the mailbox of the row above ----
         if (r > 0) {
             for (int c = 0; c < ncols; ++c) {
-                while (c - flags[1] >= TOPQ) __nanosleep(40);  // ring slot free again
-                if (lane == 0)
-                    while (ld_acquire(above) < c + 1) __nanosleep(20);  // MB(r-1,c) final <=> MB(r-1,c+1) edge-filtered
-                __syncwarp();
-                if (lane < N) {  // 4 lines x N/4 words
-                    const int line = lane / (N / 4), wd = lane % (N / 4);
-                    uint32_t w;
-                    const uint8_t *g = frame + (size_t)(y0 - 4 + line) * width + c * N + 4 * wd;
-                    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(w) : "l"(g) : "memory");
-                    topq[(c % TOPQ) * N + line * (N / 4) + wd] = w;
+                while (c - flags[1] >= TOPQ) {}  // ring slot free again
+                const uint32_t *m = mail_above + (size_t)c * 32 + lane;
+                uint32_t w;
+                do {
+                    w = ld_volatile_u32(m);
+                } while (!__all_sync(0xffffffffu, (w >> 16) == tag));
+                // lane = 2*k + h holds pixels (2h, 2h+1) of word k of the 4 x N/4 word block (N=16),
+                // see the sender; reassemble whole words
+                const uint32_t other = __shfl_xor_sync(0xffffffffu, w, 1);
+                if (N == 16) {
+                    if ((lane & 1) == 0) topq[(c % TOPQ) * N + (lane >> 1)] = (w & 0xffffu) | (other << 16);
+                } else {
+                    if ((lane & 1) == 0 && lane < 16) topq[(c % TOPQ) * N + (lane >> 1)] = (w & 0xffffu) | (other << 16);
                 }
                 __syncwarp();
                 if (lane == 0) {
@@ -240,46 +269,48 @@ __device__ void lf_row(uint8_t *__restrict__ frame, const int *__restrict__ seg,
                 }
             }
         }
-    } else if (warp == 2) {
+    } else {
+        // ---- sender warp: bottom lines of every finalised macroblock ----
         for (int c = 0; c < ncols; ++c) {
             // macroblock c is final once pass 1 of macroblock c+1 ran, the last one after its own pass 2
             if (c + 1 < ncols) {
-                while (flags[0] < c + 2) __nanosleep(40);
+                while (flags[0] < c + 2) {}
             } else {
-                while (flags[1] < ncols) __nanosleep(40);
+                while (flags[1] < ncols) {}
             }
             __threadfence_block();
-            if (lane < N) {
-                const int line = N - 4 + lane / (N / 4), wd = lane % (N / 4);
+            const bool consumer = row_below_exists && c < stop_below_cols;
+            if (consumer) {
+                // 4 lines x N/4 words, split in halves: word k -> lanes 2k, 2k+1 (N=8 uses lanes 0..15)
+                const int k = lane >> 1, h = lane & 1;
+                if (N == 16 || lane < 16) {
+                    const int line = N - 4 + k / (N / 4), wd = k % (N / 4);
+                    const uint32_t w = *reinterpret_cast<const uint32_t *>(strip + line * S + 4 + c * N + 4 * wd);
+                    mail_row[(size_t)c * 32 + lane] = ((w >> (16 * h)) & 0xffffu) | (tag << 16);
+                } else {
+                    mail_row[(size_t)c * 32 + lane] = tag << 16;  // unused half of a chroma slot: tag only
+                }
+            } else if (lane < 3 * (N / 4)) {
+                // nobody below will touch these lines: lines N-3..N-1 go to the frame from here
+                const int line = N - 3 + lane / (N / 4), wd = lane % (N / 4);
                 const uint32_t w = *reinterpret_cast<const uint32_t *>(strip + line * S + 4 + c * N + 4 * wd);
                 *reinterpret_cast<uint32_t *>(frame + (size_t)(y0 + line) * width + c * N + 4 * wd) = w;
             }
-            __syncwarp();
-            if (lane == 0) st_release(progress, c + 1 < ncols ? c + 1 : mbw + 1);
         }
     }
-    __syncthreads();
-    // ---- write back lines 0..N-5 of the filtered range (the last four lines are already out,
-    // and the row below may have rewritten three of them since) ----
-    const int out_chunks = ncols * N / 8;
-    for (int i = tid; i < (N - 4) * out_chunks; i += LF_THREADS) {
-        const int row = i / out_chunks, xc = i % out_chunks;
-        const uint32_t *s = reinterpret_cast<const uint32_t *>(strip + row * S + 4 + 8 * xc);
-        *reinterpret_cast<uint2 *>(frame + (size_t)(y0 + row) * width + 8 * xc) = make_uint2(s[0], s[1]);
-    }
-    (void)mbh;
 }
 
-// ctrl[0] = ticket counter, ctrl[1 + plane*max_rows + row] = progress of that row
+// ctrl[0] = ticket counter.  One CTA = macroblock row r of every plane in the launch.
 __global__ void __launch_bounds__(LF_THREADS)
 k_loop_filter(LFPlanes planes, int first_plane, int num_planes, const int *__restrict__ seg,
               const int *__restrict__ mb_mask, const vp8b200_segment_data *__restrict__ SD, int luma_width,
-              int luma_height, int *ctrl, int max_rows) {
+              int luma_height, int *ctrl, uint32_t *mail, unsigned tag) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_ticket, s_stop;
     const int mbw = luma_width / 16, mbh = luma_height / 16, mb_count = mbw * mbh;
-    if (threadIdx.x == 0) {
-        s_ticket = atomicAdd(&ctrl[0], 1);
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        s_ticket = atomicAdd(&ctrl[0], 1);  // rows start in ticket order: a row's predecessor is always running
         s_stop = mb_count;
     }
     __syncthreads();
@@ -290,19 +321,80 @@ k_loop_filter(LFPlanes planes, int first_plane, int num_planes, const int *__res
     for (int sgm = 0; sgm < 4; ++sgm) zero_mask |= (SD[sgm].loop_filter_level == 0) << sgm;
     if (zero_mask) {  // rare: scan the segment map for the first such macroblock
         int first = mb_count;
-        for (int mb = threadIdx.x; mb < mb_count && first == mb_count; mb += LF_THREADS)
+        for (int mb = tid; mb < mb_count && first == mb_count; mb += LF_THREADS)
             if ((zero_mask >> seg[mb]) & 1) first = mb;
         if (first < mb_count) atomicMin(&s_stop, first);
     }
     __syncthreads();
-    const int t = s_ticket;
-    const int plane = first_plane + t % num_planes, r = t / num_planes;
+    const int r = s_ticket, stop = s_stop;
     if (r >= mbh) return;
-    int *progress = ctrl + 1 + (plane - first_plane) * max_rows + r;
-    if (plane == 0)
-        lf_row<16>(planes.ptr[0], seg, mb_mask, SD, luma_width, luma_height, r, s_stop, progress, smem);
-    else
-        lf_row<8>(planes.ptr[plane], seg, mb_mask, SD, luma_width / 2, luma_height / 2, r, s_stop, progress, smem);
+    const int ncols = max(0, min(mbw, stop - r * mbw));  // macroblocks of this row before the Q6 stop
+    if (ncols == 0) return;
+    const int below_cols = max(0, min(mbw, stop - (r + 1) * mbw));
+    const bool row_below = r + 1 < mbh;
+
+    // ---- stage the strips and the per-macroblock limits of every plane ----
+    unsigned char *base = smem;
+    LFSlot slots[3];
+    for (int ps = 0; ps < num_planes; ++ps) {
+        const int plane = first_plane + ps;
+        const int n = plane == 0 ? 16 : 8;
+        const int width = plane == 0 ? luma_width : luma_width / 2;
+        slots[ps] = lf_slot(base, n, width);
+        base += lf_slot_bytes(n, width);
+        const uint8_t *frame = planes.ptr[plane];
+        const int S = width + 4, chunks = width / 8, y0 = r * n;
+        // 8-byte chunks: plane widths are multiples of 8 (chroma of a 16-aligned luma), rows 8-byte aligned
+        for (int i = tid; i < n * chunks; i += LF_THREADS) {
+            const int row = i / chunks, xc = i % chunks;
+            const uint2 v = *reinterpret_cast<const uint2 *>(frame + (size_t)(y0 + row) * width + 8 * xc);
+            uint32_t *d = reinterpret_cast<uint32_t *>(slots[ps].strip + row * S + 4 + 8 * xc);
+            d[0] = v.x; d[1] = v.y;
+        }
+        for (int c = tid; c < ncols; c += LF_THREADS) {
+            const int mb = r * mbw + c;
+            const vp8b200_segment_data *sd = SD + seg[mb];
+            slots[ps].lims[c] = make_int4((short)sd->mbedge_limit, (short)sd->sub_bedge_limit, (short)sd->interior_limit,
+                                          ((short)sd->hev_threshold & 0xffff) | (mb_mask[mb] != 0 ? 0x10000 : 0));
+        }
+        if (tid < 3) slots[ps].flags[tid] = 0;
+    }
+    __syncthreads();
+
+    // ---- the serial walk: warp w serves plane slot w/3 in role w%3 ----
+    {
+        const int warp = tid >> 5, lane = tid & 31;
+        const int ps = warp / 3, role = warp % 3;
+        if (ps < num_planes) {
+            const int plane = first_plane + ps;
+            uint32_t *mail_plane = mail + (size_t)ps * mbh * mbw * 32;
+            uint32_t *mail_row = mail_plane + (size_t)r * mbw * 32;
+            const uint32_t *mail_above = mail_plane + (size_t)(r - 1) * mbw * 32;  // only read when r > 0
+            if (plane == 0)
+                lf_plane_roles<16>(planes.ptr[0], luma_width, r, ncols, row_below, below_cols, slots[ps], mail_row,
+                                   mail_above, tag, role, lane);
+            else
+                lf_plane_roles<8>(planes.ptr[plane], luma_width / 2, r, ncols, row_below, below_cols, slots[ps], mail_row,
+                                  mail_above, tag, role, lane);
+        }
+    }
+    __syncthreads();
+
+    // ---- write back lines 0..N-4 of the filtered range.  Lines N-3..N-1 reach the frame through the
+    // row below (which rewrites them) or through the sender warp when there is no such row ----
+    for (int ps = 0; ps < num_planes; ++ps) {
+        const int plane = first_plane + ps;
+        const int n = plane == 0 ? 16 : 8;
+        const int width = plane == 0 ? luma_width : luma_width / 2;
+        uint8_t *frame = planes.ptr[plane];
+        const int S = width + 4, y0 = r * n;
+        const int out_chunks = ncols * n / 8;
+        for (int i = tid; i < (n - 3) * out_chunks; i += LF_THREADS) {
+            const int row = i / out_chunks, xc = i % out_chunks;
+            const uint32_t *s = reinterpret_cast<const uint32_t *>(slots[ps].strip + row * S + 4 + 8 * xc);
+            *reinterpret_cast<uint2 *>(frame + (size_t)(y0 + row) * width + 8 * xc) = make_uint2(s[0], s[1]);
+        }
+    }
 }
 
 // one warp per macroblock: sum of |coefficient| over the positions the entropy coder will
@@ -338,33 +430,51 @@ __global__ void k_prepare_filter_mask(const int *__restrict__ MB, int *__restric
 
 }  // namespace vp8
 
+
 using namespace vp8;
 
-// ticket + progress counters, one allocation per process (launches on different streams must
-// not overlap; the engine and the shim use a single stream)
+// ticket counter and mailbox, one allocation per process (launches on different streams must not
+// overlap; the engine and the shim use a single stream)
 static int *g_lf_ctrl = nullptr;
-static const int LF_MAX_ROWS = 2048;
+static uint32_t *g_lf_mail = nullptr;
+static size_t g_lf_mail_words = 0;
+static unsigned g_lf_tag = 0;
 
 static int launch_loop_filter(void *stream, LFPlanes p, int first_plane, int num_planes, const int32_t *seg,
                               const int32_t *mb_mask, const vp8b200_segment_data *SD, int luma_w, int luma_h) {
     cudaStream_t st = (cudaStream_t)stream;
-    const int mbh = luma_h / 16;
-    if (mbh > LF_MAX_ROWS) return -(int)cudaErrorInvalidValue;
-    if (!g_lf_ctrl && cudaMalloc((void **)&g_lf_ctrl, sizeof(int) * (1 + 3 * LF_MAX_ROWS)) != cudaSuccess)
+    const int mbw = luma_w / 16, mbh = luma_h / 16;
+    if (!g_lf_ctrl && cudaMalloc((void **)&g_lf_ctrl, sizeof(int) * 4) != cudaSuccess)
         return -(int)cudaErrorMemoryAllocation;
-    cudaMemsetAsync(g_lf_ctrl, 0, sizeof(int) * (1 + (size_t)num_planes * LF_MAX_ROWS), st);
-    const int strip_w = first_plane == 0 ? luma_w : luma_w / 2;
-    const int strip_n = first_plane == 0 ? 16 : 8;
-    const size_t smem = (((size_t)strip_n * (strip_w + 4) + 15) & ~(size_t)15) + (size_t)(luma_w / 16) * sizeof(int4) +
-                        8 * 16 * sizeof(uint32_t) + 16;  // strip + limits + top-line ring + flags
+    const size_t need = (size_t)num_planes * mbh * mbw * 32;
+    if (need > g_lf_mail_words) {
+        cudaStreamSynchronize(st);
+        if (g_lf_mail) cudaFree(g_lf_mail);
+        g_lf_mail = nullptr;
+        if (cudaMalloc((void **)&g_lf_mail, need * 4) != cudaSuccess) return -(int)cudaErrorMemoryAllocation;
+        g_lf_mail_words = need;
+        g_lf_tag = 0;
+    }
+    // 16-bit launch tags; when they wrap (or the mailbox is new) clear it so that no stale tag can match
+    g_lf_tag = (g_lf_tag + 1) & 0xffffu;
+    if (g_lf_tag == 0 || g_lf_tag == 1) {
+        cudaMemsetAsync(g_lf_mail, 0, g_lf_mail_words * 4, st);
+        g_lf_tag = 1;
+    }
+    cudaMemsetAsync(g_lf_ctrl, 0, sizeof(int) * 4, st);
+    size_t smem = 0;
+    for (int ps = 0; ps < num_planes; ++ps) {
+        const int plane = first_plane + ps;
+        smem += lf_slot_bytes(plane == 0 ? 16 : 8, plane == 0 ? luma_w : luma_w / 2);
+    }
     static size_t configured = 0;
     if (smem > configured) {
         if (cudaFuncSetAttribute(k_loop_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return -(int)cudaGetLastError();
         configured = smem;
     }
-    k_loop_filter<<<mbh * num_planes, LF_THREADS, smem, st>>>(p, first_plane, num_planes, seg, mb_mask, SD, luma_w, luma_h,
-                                                             g_lf_ctrl, LF_MAX_ROWS);
+    k_loop_filter<<<mbh, LF_THREADS, smem, st>>>(p, first_plane, num_planes, seg, mb_mask, SD, luma_w, luma_h, g_lf_ctrl,
+                                                 g_lf_mail, g_lf_tag);
     VP8_LAUNCH_CHECK();
 }
 
