@@ -42,6 +42,10 @@ def probe(w, h, reps=20, luma_only=False):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1:  # "WxH [mode]": a few launches of one shape (for ncu)
+        w, h = map(int, sys.argv[1].split("x"))
+        print(probe(w, h, reps=3, luma_only=int(sys.argv[2]) if len(sys.argv) > 2 else 0))
+        sys.exit(0)
     for w, h in ((1920, 16), (1920, 32), (1920, 64), (1920, 128), (1920, 256), (1920, 544), (1920, 1088), (32, 1088), (3840, 2160)):
         t = probe(w, h)
         t2 = probe(w, h, luma_only=True)

@@ -334,30 +334,33 @@ k_loop_filter(LFPlanes planes, int first_plane, int num_planes, const int *__res
     const bool row_below = r + 1 < mbh;
 
     // ---- stage the strips and the per-macroblock limits of every plane ----
-    unsigned char *base = smem;
-    LFSlot slots[3];
+    // slot ps starts after the slots before it (no pointer table: the accesses stay LDS/STS)
+    auto slot_of = [&](int ps) {
+        size_t off = 0;
+        for (int i = 0; i < ps; ++i) off += lf_slot_bytes(first_plane + i == 0 ? 16 : 8, first_plane + i == 0 ? luma_width : luma_width / 2);
+        return lf_slot(smem + off, first_plane + ps == 0 ? 16 : 8, first_plane + ps == 0 ? luma_width : luma_width / 2);
+    };
     for (int ps = 0; ps < num_planes; ++ps) {
         const int plane = first_plane + ps;
         const int n = plane == 0 ? 16 : 8;
         const int width = plane == 0 ? luma_width : luma_width / 2;
-        slots[ps] = lf_slot(base, n, width);
-        base += lf_slot_bytes(n, width);
+        const LFSlot slot = slot_of(ps);
         const uint8_t *frame = planes.ptr[plane];
         const int S = width + 4, chunks = width / 8, y0 = r * n;
         // 8-byte chunks: plane widths are multiples of 8 (chroma of a 16-aligned luma), rows 8-byte aligned
         for (int i = tid; i < n * chunks; i += LF_THREADS) {
             const int row = i / chunks, xc = i % chunks;
             const uint2 v = *reinterpret_cast<const uint2 *>(frame + (size_t)(y0 + row) * width + 8 * xc);
-            uint32_t *d = reinterpret_cast<uint32_t *>(slots[ps].strip + row * S + 4 + 8 * xc);
+            uint32_t *d = reinterpret_cast<uint32_t *>(slot.strip + row * S + 4 + 8 * xc);
             d[0] = v.x; d[1] = v.y;
         }
         for (int c = tid; c < ncols; c += LF_THREADS) {
             const int mb = r * mbw + c;
             const vp8b200_segment_data *sd = SD + seg[mb];
-            slots[ps].lims[c] = make_int4((short)sd->mbedge_limit, (short)sd->sub_bedge_limit, (short)sd->interior_limit,
+            slot.lims[c] = make_int4((short)sd->mbedge_limit, (short)sd->sub_bedge_limit, (short)sd->interior_limit,
                                           ((short)sd->hev_threshold & 0xffff) | (mb_mask[mb] != 0 ? 0x10000 : 0));
         }
-        if (tid < 3) slots[ps].flags[tid] = 0;
+        if (tid < 3) slot.flags[tid] = 0;
     }
     __syncthreads();
 
@@ -370,11 +373,12 @@ k_loop_filter(LFPlanes planes, int first_plane, int num_planes, const int *__res
             uint32_t *mail_plane = mail + (size_t)ps * mbh * mbw * 32;
             uint32_t *mail_row = mail_plane + (size_t)r * mbw * 32;
             const uint32_t *mail_above = mail_plane + (size_t)(r - 1) * mbw * 32;  // only read when r > 0
+            const LFSlot slot = slot_of(ps);
             if (plane == 0)
-                lf_plane_roles<16>(planes.ptr[0], luma_width, r, ncols, row_below, below_cols, slots[ps], mail_row,
+                lf_plane_roles<16>(planes.ptr[0], luma_width, r, ncols, row_below, below_cols, slot, mail_row,
                                    mail_above, tag, role, lane);
             else
-                lf_plane_roles<8>(planes.ptr[plane], luma_width / 2, r, ncols, row_below, below_cols, slots[ps], mail_row,
+                lf_plane_roles<8>(planes.ptr[plane], luma_width / 2, r, ncols, row_below, below_cols, slot, mail_row,
                                   mail_above, tag, role, lane);
         }
     }
@@ -388,10 +392,11 @@ k_loop_filter(LFPlanes planes, int first_plane, int num_planes, const int *__res
         const int width = plane == 0 ? luma_width : luma_width / 2;
         uint8_t *frame = planes.ptr[plane];
         const int S = width + 4, y0 = r * n;
+        const LFSlot slot = slot_of(ps);
         const int out_chunks = ncols * n / 8;
         for (int i = tid; i < (n - 3) * out_chunks; i += LF_THREADS) {
             const int row = i / out_chunks, xc = i % out_chunks;
-            const uint32_t *s = reinterpret_cast<const uint32_t *>(slots[ps].strip + row * S + 4 + 8 * xc);
+            const uint32_t *s = reinterpret_cast<const uint32_t *>(slot.strip + row * S + 4 + 8 * xc);
             *reinterpret_cast<uint2 *>(frame + (size_t)(y0 + row) * width + 8 * xc) = make_uint2(s[0], s[1]);
         }
     }
