@@ -17,6 +17,7 @@
 //    flags; map/unmap and the host-executed kernels use the mirror, everything else the device.
 #include <CL/cl.h>
 #include <cuda_runtime.h>
+#include <time.h>
 
 #include <cstdio>
 #include <cstdlib>
@@ -76,12 +77,29 @@ static unsigned g_next_index = 0;
 static FILE *g_trace = nullptr;
 // statistics, written as JSON to $VP8B200_STATS at exit (bench.py reads them)
 static unsigned long long g_h2d_bytes = 0, g_d2h_bytes = 0, g_kernel_launches = 0, g_host_kernels = 0;
+// wall-clock time the calling thread spent inside the entry points, by kind
+enum TimedKind { T_LAUNCH, T_HOST_KERNEL, T_READ, T_WRITE, T_MAP, T_FINISH, T_KINDS };
+static const char *const kTimedNames[T_KINDS] = {"launch", "host_kernel", "read", "write", "map", "finish"};
+static unsigned long long g_ns[T_KINDS] = {0}, g_ns_start = 0;
+static inline unsigned long long now_ns() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (unsigned long long)ts.tv_sec * 1000000000ull + (unsigned long long)ts.tv_nsec;
+}
+struct ScopedTimer {
+    TimedKind kind;
+    unsigned long long t0;
+    explicit ScopedTimer(TimedKind k) : kind(k), t0(now_ns()) {}
+    ~ScopedTimer() { g_ns[kind] += now_ns() - t0; }
+};
 static void write_stats() {
     const char *p = getenv("VP8B200_STATS");
     if (!p || !*p) return;
     if (FILE *f = fopen(p, "w")) {
-        fprintf(f, "{\"h2d_bytes\": %llu, \"d2h_bytes\": %llu, \"kernel_launches\": %llu, \"host_kernels\": %llu}\n",
+        fprintf(f, "{\"h2d_bytes\": %llu, \"d2h_bytes\": %llu, \"kernel_launches\": %llu, \"host_kernels\": %llu",
                 g_h2d_bytes, g_d2h_bytes, g_kernel_launches, g_host_kernels);
+        for (int i = 0; i < T_KINDS; ++i) fprintf(f, ", \"ms_%s\": %.3f", kTimedNames[i], g_ns[i] * 1e-6);
+        fprintf(f, ", \"ms_total\": %.3f}\n", (now_ns() - g_ns_start) * 1e-6);
         fclose(f);
     }
 }
@@ -101,11 +119,18 @@ static bool cuda_init() {
     }
     const char *dev_env = getenv("VP8B200_DEVICE");
     if (dev_env) cudaSetDevice(atoi(dev_env));
+    // how a waiting host thread waits: spin (default, lowest latency), yield, or block (frees the core for
+    // the other encoder instances when more instances than cores share the machine)
+    if (const char *sync = getenv("VP8B200_SYNC")) {
+        if (!strcmp(sync, "block")) cudaSetDeviceFlags(cudaDeviceScheduleBlockingSync);
+        else if (!strcmp(sync, "yield")) cudaSetDeviceFlags(cudaDeviceScheduleYield);
+    }
     if (cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking) != cudaSuccess) return false;
     vp8b200_device_info(g_dev_name, sizeof(g_dev_name), &g_sm_count, nullptr, nullptr);
     const char *tr = getenv("VP8CL_TRACE");
     if (tr && *tr) g_trace = fopen(tr, "wb");
     atexit(write_stats);
+    g_ns_start = now_ns();
     g_cuda_ok = true;
     return true;
 }
@@ -488,12 +513,14 @@ cl_int clEnqueueNDRangeKernel(cl_command_queue, cl_kernel k, cl_uint dim, const 
     if (dim != 1 || !gsz) return CL_INVALID_WORK_DIMENSION;
     for (int i = 0; i < kKernels[k->id].nargs; ++i)
         if (!k->set[i]) return CL_INVALID_KERNEL_ARGS;
+    ScopedTimer timer(k->id >= K_COUNT_PROBS ? T_HOST_KERNEL : T_LAUNCH);
     return dispatch(k, gsz[0]);
 }
 
 cl_int clEnqueueReadBuffer(cl_command_queue, cl_mem m, cl_bool blocking, size_t off, size_t size, void *ptr, cl_uint,
                            const cl_event *, cl_event *) {
     if (!m || off + size > m->size) return CL_INVALID_VALUE;
+    ScopedTimer timer(T_READ);
     flush_pending();
     if (m->dev_valid) {
         cudaError_t e = cudaMemcpyAsync(ptr, (char *)m->dev + off, size, cudaMemcpyDeviceToHost, g_stream);
@@ -510,6 +537,7 @@ cl_int clEnqueueReadBuffer(cl_command_queue, cl_mem m, cl_bool blocking, size_t 
 cl_int clEnqueueWriteBuffer(cl_command_queue, cl_mem m, cl_bool blocking, size_t off, size_t size, const void *ptr,
                             cl_uint, const cl_event *, cl_event *) {
     if (!m || off + size > m->size) return CL_INVALID_VALUE;
+    ScopedTimer timer(T_WRITE);
     flush_pending();
     trace_rec(2, m->index, off, size, ptr);
     if (m->host && ptr == (char *)m->host + off) {
@@ -547,6 +575,7 @@ cl_int clEnqueueCopyBuffer(cl_command_queue, cl_mem s, cl_mem d, size_t so, size
 cl_int clEnqueueWriteImage(cl_command_queue, cl_mem img, cl_bool blocking, const size_t *origin, const size_t *region,
                            size_t row_pitch, size_t, const void *ptr, cl_uint, const cl_event *, cl_event *) {
     if (!img || !img->is_image) return CL_INVALID_MEM_OBJECT;
+    ScopedTimer timer(T_WRITE);
     flush_pending();
     const size_t pitch = row_pitch ? row_pitch : region[0];
     char *dst = (char *)dev_ptr(img, true) + origin[1] * img->width + origin[0];
@@ -572,6 +601,7 @@ void *clEnqueueMapBuffer(cl_command_queue, cl_mem m, cl_bool, cl_map_flags flags
         if (err) *err = CL_INVALID_VALUE;
         return nullptr;
     }
+    ScopedTimer timer(T_MAP);
     flush_pending();
     const bool discard = (flags & CL_MAP_WRITE_INVALIDATE_REGION) && off == 0 && size == m->size;
     const bool writes = (flags & (CL_MAP_WRITE | CL_MAP_WRITE_INVALIDATE_REGION)) != 0;
@@ -610,6 +640,7 @@ cl_int clFlush(cl_command_queue) {
     return CL_SUCCESS;
 }
 cl_int clFinish(cl_command_queue) {
+    ScopedTimer timer(T_FINISH);
     flush_pending();
     if (g_trace) fflush(g_trace);
     return cuda_rc(cudaStreamSynchronize(g_stream));
