@@ -1,9 +1,21 @@
 // See entropy_host.h.  VP8 coefficient token coding (RFC 6386 section 13) written as one block
 // walker with pluggable sinks: a statistics sink (count_probs) and a boolean-coder sink
 // (encode_coefficients).
+//
+// Inter frames are sparse (at 1080p, q=24: ~55 k non-zero coefficients in 204 k blocks), so the
+// cost is per BLOCK, not per coefficient.  Each block is therefore summarised first with two SSE2
+// compares (a 16-bit "which positions are non-zero" mask: x86-64 baseline, no -m flags), the walk
+// visits only the positions up to the last non-zero one, and the reference's habit of counting an
+// end-of-block decision at EVERY position after the end of the block is kept as a small histogram
+// of "where the tail starts" that is expanded once per partition.
 #include "entropy_host.h"
 
+#include <emmintrin.h>
+
+#include <condition_variable>
 #include <cstring>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -55,43 +67,54 @@ inline Token classify(int mag) {
 
 inline int ctx_index(int type, int band, int ctx, int slot) { return (((type << 3) + band) * 3 + ctx) * 11 + slot; }
 
+inline const int16_t *block(const int16_t *MB, int mb, int b) { return MB + (size_t)mb * 400 + b * 16; }
+
+// bit i set <=> coefficient i of the block is non-zero
+inline unsigned nonzero_mask(const int16_t *c) {
+    const __m128i z = _mm_setzero_si128();
+    const __m128i a = _mm_cmpeq_epi16(_mm_loadu_si128(reinterpret_cast<const __m128i *>(c)), z);
+    const __m128i b = _mm_cmpeq_epi16(_mm_loadu_si128(reinterpret_cast<const __m128i *>(c + 8)), z);
+    return ~(unsigned)_mm_movemask_epi8(_mm_packs_epi16(a, b)) & 0xffffu;
+}
+
 // Walks one block.  type: 0 = Y after Y2 (starts at coefficient 1), 1 = Y2, 2 = chroma,
-// 3 = Y without Y2.  ctx = number of non-empty neighbour blocks (above, left).
-// When keep_counting_after_eob is set the walk does what the reference's count_probs_in_block
-// does (src/CPU_kernels.cl:503-538): it does NOT stop at the end-of-block token but goes on
-// to visit an end-of-block decision for every remaining position, with context 2.
+// 3 = Y without Y2.  ctx = number of non-empty neighbour blocks (above, left).  mask = the
+// block's non-zero mask.  Returns the position of the end-of-block token (16: none, the block is
+// full).  The reference's count_probs_in_block (src/CPU_kernels.cl:503-538) does NOT stop there:
+// it visits an end-of-block decision with context 2 at every later position; the caller accounts
+// for those from the returned position.
 template <class Sink>
-inline void walk_block(const int16_t *coef, int type, int ctx, bool keep_counting_after_eob, Sink &sink) {
-    int last = 15;
-    while (last >= 0 && coef[last] == 0) --last;  // positions > last are end-of-block tokens
+inline int walk_block(const int16_t *coef, int type, int ctx, unsigned mask, Sink &sink) {
+    const int first = (type == 0) ? 1 : 0;
+    if (first) mask &= ~1u;
+    const int last = mask ? 31 - __builtin_clz(mask) : -1;  // positions > last are end-of-block tokens
     bool prev_zero = false;
-    for (int i = (type == 0) ? 1 : 0; i < 16; ++i) {
+    int i = first;
+    for (; i <= last; ++i) {
         const int band = kBand[i];
         const int v = coef[i];
-        const int mag = v < 0 ? -v : v;
-        const Token t = (i > last) ? T_EOB : classify(mag);
-        const Path &p = kPath[t];
-        // after a ZERO token an end-of-block cannot follow, so the first decision is implicit
-        for (int k = prev_zero ? 1 : 0; k < p.n; ++k) sink.decision(ctx_index(type, band, ctx, p.slot[k]), p.bit[k]);
-        if (t == T_EOB) {
-            if (!keep_counting_after_eob) return;
-            ctx = 2;
-            prev_zero = false;
+        if (v == 0) {
+            // after a ZERO token an end-of-block cannot follow, so the first decision is implicit
+            if (!prev_zero) sink.decision(ctx_index(type, band, ctx, 0), 1);
+            sink.decision(ctx_index(type, band, ctx, 1), 0);
+            prev_zero = true;
+            ctx = 0;
             continue;
         }
+        const int mag = v < 0 ? -v : v;
+        const Token t = classify(mag);
+        const Path &p = kPath[t];
+        for (int k = prev_zero ? 1 : 0; k < p.n; ++k) sink.decision(ctx_index(type, band, ctx, p.slot[k]), p.bit[k]);
         if (t >= T_CAT1) {
             const int c = t - T_CAT1, extra = mag - kCatBase[c];
             for (int b = 0; b < kCatBits[c]; ++b) sink.literal(kCatProb[c][b], (extra >> (kCatBits[c] - 1 - b)) & 1);
         }
-        if (t == T_ZERO) {
-            prev_zero = true;
-            ctx = 0;
-        } else {
-            sink.literal(128, v < 0);  // sign
-            prev_zero = false;
-            ctx = (t == T_ONE) ? 1 : 2;
-        }
+        sink.literal(128, v < 0);  // sign
+        prev_zero = false;
+        ctx = (t == T_ONE) ? 1 : 2;
     }
+    if (i < 16) sink.decision(ctx_index(type, kBand[i], ctx, 0), 0);  // end of block (never right after a ZERO)
+    return i;
 }
 
 struct StatSink {
@@ -115,23 +138,31 @@ struct BoolSink {
     }
     inline void put(int prob, int bit) {
         const uint32_t split = 1 + (((range - 1) * (uint32_t)prob) >> 8);
-        if (bit) {
-            bottom += split;
-            range -= split;
-        } else {
-            range = split;
+        const uint32_t r = bit ? range - split : split;
+        bottom += bit ? split : 0u;
+        if (r >= 128) {
+            range = r;
+            return;
         }
-        while (range < 128) {
-            range <<= 1;
-            if (bottom & (1u << 31)) carry(out);
-            bottom <<= 1;
-            if (!--bit_count) {
-                *out++ = (uint8_t)(bottom >> 24);
-                ++count;
-                bottom &= (1u << 24) - 1;
-                bit_count = 8;
-            }
+        // The RFC renormalises bit by bit: before each of the s shifts a set top bit of `bottom` is a
+        // carry into the bytes already written, and every time bit_count reaches 0 a byte leaves.
+        // Same thing in at most two strides (s <= 7, so at most one byte leaves).
+        int s = __builtin_clz(r) - 24;
+        range = r << s;
+        if (s >= bit_count) {
+            const int c = bit_count;
+            for (uint32_t t = bottom >> (32 - c); t; t &= t - 1) carry(out);
+            bottom <<= c;
+            *out++ = (uint8_t)(bottom >> 24);
+            ++count;
+            bottom &= (1u << 24) - 1;
+            bit_count = 8;
+            s -= c;
+            if (s == 0) return;
         }
+        for (uint32_t t = bottom >> (32 - s); t; t &= t - 1) carry(out);
+        bottom <<= s;
+        bit_count -= s;
     }
     inline void decision(int idx, int bit) { put((uint8_t)probs[idx], bit); }
     inline void literal(int prob, int bit) { put(prob, bit); }
@@ -150,76 +181,118 @@ struct BoolSink {
     }
 };
 
-inline const int16_t *block(const int16_t *MB, int mb, int b) { return MB + (size_t)mb * 400 + b * 16; }
-
-inline int nonzero_from(const int16_t *c, int first) {
-    for (int i = first; i < 16; ++i)
-        if (c[i]) return 1;
-    return 0;
-}
-
-// number of non-empty neighbour blocks (above + left) of every block of one macroblock
+// number of non-empty neighbour blocks (above + left) of every block of one macroblock.
+// own[b] = non-zero masks of this macroblock's blocks.
 void neighbour_contexts(const int16_t *MB, const int32_t *parts, int mb, int mb_row, int mb_col, int mb_width,
-                        uint8_t *ctx /* [25] */) {
+                        const unsigned *own, uint8_t *ctx /* [25] */) {
+    const int row_start = mb_row * mb_width;
     if (parts[mb] == 0) {
         // Y2: the neighbours are the nearest macroblocks above / to the left that have a Y2 block
         int n = 0;
         if (mb_row > 0) {
             int p = mb - mb_width;
             while (p >= 0 && parts[p] != 0) p -= mb_width;
-            if (p >= 0) n += nonzero_from(block(MB, p, 24), 0);
+            if (p >= 0) n += nonzero_mask(block(MB, p, 24)) != 0;
         }
         if (mb_col > 0) {
             int p = mb - 1;
-            while (p >= mb_row * mb_width && parts[p] != 0) --p;
-            if (p >= mb_row * mb_width) n += nonzero_from(block(MB, p, 24), 0);
+            while (p >= row_start && parts[p] != 0) --p;
+            if (p >= row_start) n += nonzero_mask(block(MB, p, 24)) != 0;
         }
         ctx[24] = (uint8_t)n;
     }
-    for (int b = 0; b < 16; ++b) {
-        int n = 0, pm = -1, pb = 0;
-        if ((b >> 2) > 0) { pm = mb; pb = b - 4; } else if (mb_row > 0) { pm = mb - mb_width; pb = b + 12; }
-        if (pm >= 0) n += nonzero_from(block(MB, pm, pb), parts[pm] == 0 ? 1 : 0);  // DC lives in Y2 there
-        pm = -1;
-        if ((b & 3) > 0) { pm = mb; pb = b - 1; } else if (mb_col > 0) { pm = mb - 1; pb = b + 3; }
-        if (pm >= 0) n += nonzero_from(block(MB, pm, pb), parts[pm] == 0 ? 1 : 0);
-        ctx[b] = (uint8_t)n;
+    // "non-empty" ignores the DC of a Y block whose macroblock has a Y2 block (the DC lives there)
+    const unsigned own_y = parts[mb] == 0 ? 0xfffeu : 0xffffu;
+    unsigned above_y[4] = {0, 0, 0, 0}, left_y[4] = {0, 0, 0, 0}, above_c[4] = {0, 0, 0, 0}, left_c[4] = {0, 0, 0, 0};
+    if (mb_row > 0) {
+        const int pm = mb - mb_width;
+        const unsigned keep = parts[pm] == 0 ? 0xfffeu : 0xffffu;
+        for (int k = 0; k < 4; ++k) above_y[k] = nonzero_mask(block(MB, pm, 12 + k)) & keep;
+        above_c[0] = nonzero_mask(block(MB, pm, 18));
+        above_c[1] = nonzero_mask(block(MB, pm, 19));
+        above_c[2] = nonzero_mask(block(MB, pm, 22));
+        above_c[3] = nonzero_mask(block(MB, pm, 23));
     }
-    for (int base = 16; base <= 20; base += 4)
+    if (mb_col > 0) {
+        const int pm = mb - 1;
+        const unsigned keep = parts[pm] == 0 ? 0xfffeu : 0xffffu;
+        for (int k = 0; k < 4; ++k) left_y[k] = nonzero_mask(block(MB, pm, 4 * k + 3)) & keep;
+        left_c[0] = nonzero_mask(block(MB, pm, 17));
+        left_c[1] = nonzero_mask(block(MB, pm, 19));
+        left_c[2] = nonzero_mask(block(MB, pm, 21));
+        left_c[3] = nonzero_mask(block(MB, pm, 23));
+    }
+    for (int b = 0; b < 16; ++b) {
+        const unsigned up = (b >> 2) > 0 ? (own[b - 4] & own_y) : above_y[b & 3];
+        const unsigned lf = (b & 3) > 0 ? (own[b - 1] & own_y) : left_y[b >> 2];
+        ctx[b] = (uint8_t)((up != 0) + (lf != 0));
+    }
+    for (int pl = 0; pl < 2; ++pl) {
+        const int base = 16 + 4 * pl;
         for (int k = 0; k < 4; ++k) {
-            const int b = base + k;
-            int n = 0, pm = -1, pb = 0;
-            if ((k >> 1) > 0) { pm = mb; pb = b - 2; } else if (mb_row > 0) { pm = mb - mb_width; pb = b + 2; }
-            if (pm >= 0) n += nonzero_from(block(MB, pm, pb), 0);
-            pm = -1;
-            if ((k & 1) > 0) { pm = mb; pb = b - 1; } else if (mb_col > 0) { pm = mb - 1; pb = b + 1; }
-            if (pm >= 0) n += nonzero_from(block(MB, pm, pb), 0);
-            ctx[b] = (uint8_t)n;
+            const unsigned up = (k >> 1) > 0 ? own[base + k - 2] : above_c[2 * pl + (k & 1)];
+            const unsigned lf = (k & 1) > 0 ? own[base + k - 1] : left_c[2 * pl + (k >> 1)];
+            ctx[base + k] = (uint8_t)((up != 0) + (lf != 0));
         }
+    }
 }
 
-template <class Sink>
-inline void walk_macroblock(const int16_t *MB, const int32_t *parts, int mb, const uint8_t *ctx, bool counting, Sink &sink) {
-    int type = 3;
-    if (parts[mb] == 0) {
-        walk_block(block(MB, mb, 24), 1, ctx[24], counting, sink);
-        type = 0;
+// ---- persistent helper threads, one job at a time (the shim is driven by a single host thread) ----
+class Pool {
+  public:
+    void run(int n, const std::function<void(int)> &f) {
+        if (n <= 1) {
+            f(0);
+            return;
+        }
+        {
+            std::unique_lock<std::mutex> lk(m_);
+            while ((int)threads_.size() < n - 1) {
+                const int id = (int)threads_.size() + 1;
+                threads_.emplace_back([this, id] { worker(id); });
+                threads_.back().detach();  // they sleep on the condition variable until the process ends
+            }
+            job_ = &f;
+            n_ = n;
+            pending_ = n - 1;
+            ++generation_;
+        }
+        wake_.notify_all();
+        f(0);
+        std::unique_lock<std::mutex> lk(m_);
+        done_.wait(lk, [this] { return pending_ == 0; });
+        job_ = nullptr;
     }
-    for (int b = 0; b < 16; ++b) walk_block(block(MB, mb, b), type, ctx[b], counting, sink);
-    for (int b = 16; b < 24; ++b) walk_block(block(MB, mb, b), 2, ctx[b], counting, sink);
-}
+
+  private:
+    void worker(int id) {
+        unsigned long seen = 0;
+        for (;;) {
+            const std::function<void(int)> *job;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                wake_.wait(lk, [&] { return generation_ != seen; });
+                seen = generation_;
+                if (id >= n_) continue;
+                job = job_;
+            }
+            (*job)(id);
+            std::unique_lock<std::mutex> lk(m_);
+            if (--pending_ == 0) done_.notify_one();
+        }
+    }
+    std::mutex m_;
+    std::condition_variable wake_, done_;
+    std::vector<std::thread> threads_;
+    const std::function<void(int)> *job_ = nullptr;
+    int n_ = 0, pending_ = 0;
+    unsigned long generation_ = 0;
+};
 
 template <class F>
 void for_each_partition(int n, F f) {
-    if (n <= 1) {
-        f(0);
-        return;
-    }
-    std::vector<std::thread> th;
-    th.reserve(n - 1);
-    for (int p = 1; p < n; ++p) th.emplace_back(f, p);
-    f(0);
-    for (auto &t : th) t.join();
+    static Pool *pool = new Pool;  // never destroyed: its threads outlive static destruction
+    pool->run(n, std::function<void(int)>(f));
 }
 
 }  // namespace
@@ -232,14 +305,43 @@ void count_probs(const int16_t *MB, const int32_t *nz, const int32_t *parts, uin
             s.num[i] = 0;
             s.den[i] = 1;
         }
+        // tail[type][i]: blocks of that type whose end-of-block token sat at position i-1, i.e. whose
+        // context-2 end-of-block run starts at position i
+        uint32_t tail[4][17];
+        memset(tail, 0, sizeof(tail));
         for (int row = p; row < mb_height; row += P)
             for (int col = 0; col < mb_width; ++col) {
                 const int mb = row * mb_width + col;
                 if (nz[mb] == 0) continue;  // skipped macroblock: nothing is coded, contexts stay as they were
                 uint8_t *ctx = third_context + (size_t)mb * 25;
-                neighbour_contexts(MB, parts, mb, row, col, mb_width, ctx);
-                walk_macroblock(MB, parts, mb, ctx, true, s);
+                unsigned own[25];
+                for (int b = 0; b < 25; ++b) own[b] = nonzero_mask(block(MB, mb, b));
+                neighbour_contexts(MB, parts, mb, row, col, mb_width, own, ctx);
+                int type = 3;
+                if (parts[mb] == 0) {
+                    const int e = walk_block(block(MB, mb, 24), 1, ctx[24], own[24], s);
+                    ++tail[1][e < 16 ? e + 1 : 16];
+                    type = 0;
+                }
+                for (int b = 0; b < 16; ++b) {
+                    const int e = walk_block(block(MB, mb, b), type, ctx[b], own[b], s);
+                    ++tail[type][e < 16 ? e + 1 : 16];
+                }
+                for (int b = 16; b < 24; ++b) {
+                    const int e = walk_block(block(MB, mb, b), 2, ctx[b], own[b], s);
+                    ++tail[2][e < 16 ? e + 1 : 16];
+                }
             }
+        // positions start..15 of each such block: one end-of-block decision with context 2 each
+        for (int type = 0; type < 4; ++type) {
+            uint32_t running = 0;
+            for (int i = 1; i < 16; ++i) {
+                running += tail[type][i];
+                const int idx = ctx_index(type, kBand[i], 2, 0);
+                s.num[idx] += running;
+                s.den[idx] += running;
+            }
+        }
     });
 }
 
@@ -266,7 +368,14 @@ void encode_coefficients(const int16_t *MB, const int32_t *nz, const int32_t *pa
             for (int col = 0; col < mb_width; ++col) {
                 const int mb = row * mb_width + col;
                 if (nz[mb] == 0) continue;
-                walk_macroblock(MB, parts, mb, third_context + (size_t)mb * 25, false, s);
+                const uint8_t *ctx = third_context + (size_t)mb * 25;
+                int type = 3;
+                if (parts[mb] == 0) {
+                    walk_block(block(MB, mb, 24), 1, ctx[24], nonzero_mask(block(MB, mb, 24)), s);
+                    type = 0;
+                }
+                for (int b = 0; b < 16; ++b) walk_block(block(MB, mb, b), type, ctx[b], nonzero_mask(block(MB, mb, b)), s);
+                for (int b = 16; b < 24; ++b) walk_block(block(MB, mb, b), 2, ctx[b], nonzero_mask(block(MB, mb, b)), s);
             }
         s.finish();
         partition_sizes[p] = (int32_t)s.count;
