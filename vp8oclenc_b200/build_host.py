@@ -29,7 +29,7 @@ def build(verbose=False):
     if os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in deps):
         return OUT
     gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    cmd = [gxx, "-std=gnu++17", "-O2", "-w", "-I", os.path.join(ROOT, "include")] + srcs + \
+    cmd = [gxx, "-std=gnu++17", "-O3", "-w", "-I", os.path.join(ROOT, "include")] + srcs + \
           ["-o", OUT, "-L", os.path.join(PKG, "lib"), "-lOpenCL"]
     if verbose:
         print(" ".join(cmd))
