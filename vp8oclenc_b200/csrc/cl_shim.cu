@@ -15,6 +15,14 @@
 //    platform discovery fails.
 //  * Every buffer has a device allocation and, on demand, a pinned host mirror with validity
 //    flags; map/unmap and the host-executed kernels use the mirror, everything else the device.
+//  * Kernel enqueues and device-to-device copies are DEFERRED: they collect in a command list that
+//    is executed when the host does something that can observe or feed device memory (a read,
+//    write, map, a host-executed kernel).  clFlush/clFinish do not drain it -- a kernel's results
+//    are only reachable through those calls.  When the list is executed, the launch sequences the
+//    reference host always emits are recognised and replaced by the engine's fused launches
+//    (one search launch for all references of a level, one launch for the whole predict /
+//    transform / SSIM ladder, one for the three loop-filter planes); anything that does not
+//    match exactly runs kernel by kernel.  VP8B200_FUSED=0 turns the replacement off.
 #include <CL/cl.h>
 #include <cuda_runtime.h>
 #include <time.h>
@@ -65,6 +73,16 @@ struct _cl_kernel {
     bool set[12];
 };
 
+// one deferred command: a kernel with a snapshot of its arguments, or a device-to-device copy
+enum { C_COPY_BUFFER = K_COUNT, C_COPY_IMAGE };
+struct Cmd {
+    int id;
+    size_t global;
+    _cl_kernel k;
+    cl_mem src, dst;
+    size_t a[6];  // buffer copy: src offset, dst offset, bytes; image copy: sx, sy, dx, dy, w, h
+};
+
 // ------------------------------------------------------------------------------------------
 static _cl_platform_id g_platform;
 static _cl_device_id g_cpu_dev = {CL_DEVICE_TYPE_CPU};
@@ -104,10 +122,8 @@ static void write_stats() {
     }
 }
 
-// deferred luma / chroma-U loop filters, so that the three planes go out as ONE launch
-struct PendingLF { cl_mem frame, seg, mask, sd; int w, h; };
-static PendingLF g_pending_lf[2];
-static int g_num_pending_lf = 0;
+static std::vector<Cmd> g_cmds;  // the deferred command list
+static bool g_fuse = true;       // VP8B200_FUSED=0: execute the list kernel by kernel
 
 static bool cuda_init() {
     if (g_cuda_tried) return g_cuda_ok;
@@ -127,6 +143,7 @@ static bool cuda_init() {
     }
     if (cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking) != cudaSuccess) return false;
     vp8b200_device_info(g_dev_name, sizeof(g_dev_name), &g_sm_count, nullptr, nullptr);
+    if (const char *f = getenv("VP8B200_FUSED")) g_fuse = f[0] != '0';
     const char *tr = getenv("VP8CL_TRACE");
     if (tr && *tr) g_trace = fopen(tr, "wb");
     atexit(write_stats);
@@ -189,9 +206,9 @@ static void *host_ptr(cl_mem m, bool will_write, bool discard = false) {
     return m->host;
 }
 
-static void launch_lf(int count);
+static void run_cmds();
 static inline void flush_pending() {
-    if (g_num_pending_lf) launch_lf(g_num_pending_lf);
+    if (!g_cmds.empty()) run_cmds();
 }
 
 // ---- kernel argument access ----------------------------------------------------------------
@@ -215,24 +232,12 @@ template <class T> static inline T *out(cl_kernel k, int i) { return (T *)dev_pt
 template <class T> static inline T *hin(cl_kernel k, int i) { return (T *)host_ptr(arg_mem(k, i), false); }
 template <class T> static inline T *hout(cl_kernel k, int i) { return (T *)host_ptr(arg_mem(k, i), true); }
 
-static void launch_lf(int count) {
-    // count pending planes (luma [, chroma U]) that could not be fused: launch them one by one
-    for (int i = 0; i < count; ++i) {
-        PendingLF &p = g_pending_lf[i];
-        ++g_kernel_launches;
-        vp8b200_loop_filter_frame(g_stream, (uint8_t *)dev_ptr(p.frame, true), (const int32_t *)dev_ptr(p.seg, false),
-                                  (const int32_t *)dev_ptr(p.mask, false),
-                                  (const vp8b200_segment_data *)dev_ptr(p.sd, false), p.w, p.h, i == 0 ? 16 : 8);
-    }
-    g_num_pending_lf = 0;
-}
-
-static cl_int dispatch(cl_kernel k, size_t global) {
+// executes one kernel now (GPU kernels: launches on the stream; entropy kernels: runs on host threads)
+static cl_int dispatch_now(cl_kernel k, size_t global) {
     void *s = g_stream;
     int rc = 0;
-    if (k->id != K_LF_CHROMA) flush_pending();
     if (k->id >= K_COUNT_PROBS) ++g_host_kernels;
-    else if (k->id != K_LF_LUMA && k->id != K_LF_CHROMA) ++g_kernel_launches;
+    else ++g_kernel_launches;
     switch (k->id) {
         case K_RESET_VECTORS:
             rc = vp8b200_reset_vectors(s, out<int16_t>(k, 0), out<int16_t>(k, 1), out<int16_t>(k, 2), out<int16_t>(k, 3),
@@ -306,34 +311,11 @@ static cl_int dispatch(cl_kernel k, size_t global) {
                                              out<int32_t>(k, 3), arg_int(k, 4), arg_int(k, 5));
             break;
         case K_LF_LUMA:
-            g_pending_lf[0] = {arg_mem(k, 0), arg_mem(k, 1), arg_mem(k, 2), arg_mem(k, 3), arg_int(k, 4), arg_int(k, 5)};
-            g_num_pending_lf = 1;
+        case K_LF_CHROMA:
+            rc = vp8b200_loop_filter_frame(s, out<uint8_t>(k, 0), in<int32_t>(k, 1), in<int32_t>(k, 2),
+                                           in<vp8b200_segment_data>(k, 3), arg_int(k, 4), arg_int(k, 5),
+                                           k->id == K_LF_LUMA ? 16 : 8);
             break;
-        case K_LF_CHROMA: {
-            PendingLF p = {arg_mem(k, 0), arg_mem(k, 1), arg_mem(k, 2), arg_mem(k, 3), arg_int(k, 4), arg_int(k, 5)};
-            const PendingLF &y = g_pending_lf[0];
-            const bool same = g_num_pending_lf >= 1 && p.seg == y.seg && p.mask == y.mask && p.sd == y.sd &&
-                              p.w * 2 == y.w && p.h * 2 == y.h;
-            if (same && g_num_pending_lf == 1) {
-                g_pending_lf[1] = p;
-                g_num_pending_lf = 2;
-            } else if (same && g_num_pending_lf == 2) {
-                const PendingLF &u = g_pending_lf[1];
-                ++g_kernel_launches;
-                rc = vp8b200_loop_filter_planes(s, (uint8_t *)dev_ptr(y.frame, true), (uint8_t *)dev_ptr(u.frame, true),
-                                                (uint8_t *)dev_ptr(p.frame, true), (const int32_t *)dev_ptr(y.seg, false),
-                                                (const int32_t *)dev_ptr(y.mask, false),
-                                                (const vp8b200_segment_data *)dev_ptr(y.sd, false), y.w, y.h);
-                g_num_pending_lf = 0;
-            } else {
-                flush_pending();
-                ++g_kernel_launches;
-                rc = vp8b200_loop_filter_frame(s, (uint8_t *)dev_ptr(p.frame, true), (const int32_t *)dev_ptr(p.seg, false),
-                                               (const int32_t *)dev_ptr(p.mask, false),
-                                               (const vp8b200_segment_data *)dev_ptr(p.sd, false), p.w, p.h, 8);
-            }
-            break;
-        }
         case K_COUNT_PROBS:
             vp8host::count_probs(hin<int16_t>(k, 0), hin<int32_t>(k, 1), hin<int32_t>(k, 2), hout<uint32_t>(k, 3),
                                  hout<uint32_t>(k, 4), hout<uint8_t>(k, 5), arg_int(k, 6), arg_int(k, 7), arg_int(k, 8));
@@ -350,6 +332,239 @@ static cl_int dispatch(cl_kernel k, size_t global) {
             return CL_INVALID_KERNEL;
     }
     return rc == 0 ? CL_SUCCESS : CL_OUT_OF_RESOURCES;
+}
+
+// ---- the deferred command list --------------------------------------------------------------
+static inline bool same_mem(const Cmd &a, int ia, const Cmd &b, int ib) {
+    return arg_mem(const_cast<cl_kernel>(&a.k), ia) == arg_mem(const_cast<cl_kernel>(&b.k), ib);
+}
+static inline cl_kernel ck(const Cmd &c) { return const_cast<cl_kernel>(&c.k); }
+
+// luma_search_1step of the same level for up to three references (src/inter_part.h:121-205):
+// the launches are independent of each other -> one launch with grid.y = reference
+static size_t try_multi_search1(size_t i) {
+    const Cmd &c0 = g_cmds[i];
+    if (c0.id != K_SEARCH1) return 0;
+    size_t n = 1;
+    while (n < 3 && i + n < g_cmds.size()) {
+        const Cmd &c = g_cmds[i + n];
+        if (c.id != K_SEARCH1 || !same_mem(c, 0, c0, 0) || c.global != c0.global) break;
+        bool ok = true;
+        for (int a = 4; a < 8; ++a) ok = ok && arg_int(ck(c), a) == arg_int(ck(c0), a);
+        for (size_t j = 0; j < n && ok; ++j) {  // no launch of the group may feed or overwrite another
+            const Cmd &o = g_cmds[i + j];
+            ok = !same_mem(c, 3, o, 3) && !same_mem(c, 3, o, 2) && !same_mem(c, 2, o, 3) && !same_mem(c, 3, o, 1) &&
+                 !same_mem(c, 1, o, 3);
+        }
+        if (!ok) break;
+        ++n;
+    }
+    if (n < 2) return 0;
+    const uint8_t *prev[3];
+    const int16_t *src[3];
+    int16_t *dst[3];
+    for (size_t j = 0; j < n; ++j) {
+        cl_kernel k = ck(g_cmds[i + j]);
+        prev[j] = in<uint8_t>(k, 1);
+        src[j] = in<int16_t>(k, 2);
+        dst[j] = out<int16_t>(k, 3);
+    }
+    cl_kernel k0 = ck(c0);
+    ++g_kernel_launches;
+    vp8b200_luma_search_1step_multi(g_stream, in<uint8_t>(k0, 0), (int)n, prev, src, dst, arg_int(k0, 4), arg_int(k0, 5),
+                                    arg_int(k0, 6), arg_int(k0, 7));
+    return n;
+}
+
+// luma_search_2step for up to three references (src/inter_part.h:207-221)
+static size_t try_multi_search2(size_t i) {
+    const Cmd &c0 = g_cmds[i];
+    if (c0.id != K_SEARCH2) return 0;
+    size_t n = 1;
+    while (n < 3 && i + n < g_cmds.size()) {
+        const Cmd &c = g_cmds[i + n];
+        if (c.id != K_SEARCH2 || !same_mem(c, 0, c0, 0) || c.global != c0.global ||
+            arg_int(ck(c), 5) != arg_int(ck(c0), 5) || arg_int(ck(c), 6) != arg_int(ck(c0), 6))
+            break;
+        bool ok = true;
+        for (size_t j = 0; j < n && ok; ++j) {
+            const Cmd &o = g_cmds[i + j];
+            for (int w = 3; w <= 4 && ok; ++w)
+                for (int r = 1; r <= 4 && ok; ++r) ok = !same_mem(c, w, o, r) && !same_mem(o, w, c, r);
+        }
+        if (!ok) break;
+        ++n;
+    }
+    if (n < 2) return 0;
+    const uint8_t *ref[3];
+    const int16_t *net[3];
+    int16_t *ref_net[3];
+    int32_t *diff[3];
+    for (size_t j = 0; j < n; ++j) {
+        cl_kernel k = ck(g_cmds[i + j]);
+        ref[j] = in<uint8_t>(k, 1);
+        net[j] = in<int16_t>(k, 2);
+        ref_net[j] = out<int16_t>(k, 3);
+        diff[j] = out<int32_t>(k, 4);
+    }
+    cl_kernel k0 = ck(c0);
+    ++g_kernel_launches;
+    vp8b200_luma_search_2step_multi(g_stream, in<uint8_t>(k0, 0), (int)n, ref, net, ref_net, diff, arg_int(k0, 5),
+                                    arg_int(k0, 6));
+    return n;
+}
+
+// The tail of inter_transform() (src/inter_part.h:268-378): prepare_predictors_and_residual for
+// every plane and reference in use, then for segment 3,2,1,0: dct4x4 Y,U,V; wht4x4_iwht4x4;
+// idct4x4 Y,U,V; count_SSIM luma, U, V; gather_SSIM.  Matched exactly (kernels, order, buffers,
+// scalars) it becomes ONE launch; the predictor / residual / SSIM scratch buffers, which the host
+// never reads, are then left untouched.
+static size_t try_fused_tail(size_t i) {
+    if (g_cmds[i].id != K_PREDICT) return 0;
+    const size_t n = g_cmds.size();
+    cl_mem img[9] = {nullptr}, cur[3] = {nullptr}, pred[3] = {nullptr}, res[3] = {nullptr}, recon[3] = {nullptr};
+    int pw[3] = {0, 0, 0};
+    cl_mem ref_frame = nullptr, vectors = nullptr;
+    size_t j = i;
+    for (; j < n && g_cmds[j].id == K_PREDICT; ++j) {
+        cl_kernel k = ck(g_cmds[j]);
+        const int plane = arg_int(k, 7), ref = arg_int(k, 8);
+        if (plane < 0 || plane > 2 || ref < 0 || ref > 2 || img[3 * ref + plane]) return 0;
+        img[3 * ref + plane] = arg_mem(k, 1);
+        if (!img[3 * ref + plane] || !img[3 * ref + plane]->is_image) return 0;
+        if (cur[plane] && (cur[plane] != arg_mem(k, 0) || pred[plane] != arg_mem(k, 2) || res[plane] != arg_mem(k, 3) ||
+                           pw[plane] != arg_int(k, 6)))
+            return 0;
+        cur[plane] = arg_mem(k, 0);
+        pred[plane] = arg_mem(k, 2);
+        res[plane] = arg_mem(k, 3);
+        pw[plane] = arg_int(k, 6);
+        if (ref_frame && (ref_frame != arg_mem(k, 4) || vectors != arg_mem(k, 5))) return 0;
+        ref_frame = arg_mem(k, 4);
+        vectors = arg_mem(k, 5);
+    }
+    for (int r = 0; r < 3; ++r) {  // a reference is used for all planes or for none; LAST always
+        const int cnt = (img[3 * r] != nullptr) + (img[3 * r + 1] != nullptr) + (img[3 * r + 2] != nullptr);
+        if ((cnt != 0 && cnt != 3) || (r == 0 && cnt != 3)) return 0;
+    }
+    const int width = pw[0], height = img[0]->height;
+    if (pw[1] * 2 != width || pw[2] * 2 != width || img[0]->width != width || width % 16 || height % 16) return 0;
+    if (j + 44 > n) return 0;
+    static const int kStep[11] = {K_DCT, K_DCT, K_DCT, K_WHT, K_IDCT, K_IDCT, K_IDCT, K_SSIM_LUMA, K_SSIM_CHROMA,
+                                  K_SSIM_CHROMA, K_GATHER_SSIM};
+    cl_mem MB = nullptr, seg_id = nullptr, parts = nullptr, ssim = nullptr, SD = nullptr;
+    float target = 0.0f;
+    const size_t mbs = (size_t)(width / 16) * (height / 16);
+    for (int seg = 3; seg >= 0; --seg) {
+        const size_t base = j + (size_t)(3 - seg) * 11;
+        for (int t = 0; t < 11; ++t)
+            if (g_cmds[base + t].id != kStep[t]) return 0;
+        for (int p = 0; p < 3; ++p) {
+            cl_kernel d = ck(g_cmds[base + p]), id = ck(g_cmds[base + 4 + p]), ss = ck(g_cmds[base + 7 + p]);
+            if (seg == 3 && p == 0) {
+                MB = arg_mem(d, 1);
+                seg_id = arg_mem(d, 2);
+                parts = arg_mem(d, 3);
+                ssim = arg_mem(d, 4);
+                SD = arg_mem(d, 6);
+                target = arg_float(d, 8);
+            }
+            if (seg == 3) recon[p] = arg_mem(id, 0);
+            const bool ok =
+                arg_mem(d, 0) == res[p] && arg_mem(d, 1) == MB && arg_mem(d, 2) == seg_id && arg_mem(d, 3) == parts &&
+                arg_mem(d, 4) == ssim && arg_int(d, 5) == pw[p] && arg_mem(d, 6) == SD && arg_int(d, 7) == seg &&
+                arg_float(d, 8) == target && arg_int(d, 9) == p && g_cmds[base + p].global == mbs * (p ? 4 : 16) &&
+                arg_mem(id, 0) == recon[p] && arg_mem(id, 1) == pred[p] && arg_mem(id, 2) == MB && arg_mem(id, 3) == seg_id &&
+                arg_mem(id, 4) == parts && arg_int(id, 5) == pw[p] && arg_mem(id, 6) == SD && arg_int(id, 7) == seg &&
+                arg_int(id, 8) == p && g_cmds[base + 4 + p].global == mbs * (p ? 4 : 16) &&
+                arg_mem(ss, 0) == cur[p] && arg_mem(ss, 1) == recon[p] && arg_mem(ss, 2) == seg_id && arg_int(ss, 4) == pw[p] &&
+                arg_int(ss, 5) == seg && g_cmds[base + 7 + p].global == mbs;
+            if (!ok) return 0;
+        }
+        cl_kernel wh = ck(g_cmds[base + 3]), ga = ck(g_cmds[base + 10]);
+        if (arg_mem(wh, 0) != MB || arg_mem(wh, 2) != seg_id || arg_mem(wh, 3) != parts || arg_mem(wh, 4) != SD ||
+            arg_int(wh, 5) != seg || g_cmds[base + 3].global != mbs)
+            return 0;
+        if (arg_mem(ga, 0) != arg_mem(ck(g_cmds[base + 7]), 3) || arg_mem(ga, 1) != arg_mem(ck(g_cmds[base + 8]), 3) ||
+            arg_mem(ga, 2) != arg_mem(ck(g_cmds[base + 9]), 3) || arg_mem(ga, 3) != ssim || g_cmds[base + 10].global != mbs)
+            return 0;
+    }
+    if (!(target >= -2.0f) || !recon[0] || !recon[1] || !recon[2] || !MB || !seg_id || !parts || !ssim || !SD) return 0;
+    if (recon[0]->size < (size_t)width * height || MB->size < mbs * 800) return 0;
+    const uint8_t *imgp[9];
+    for (int q = 0; q < 9; ++q) imgp[q] = img[q] ? (const uint8_t *)dev_ptr(img[q], false) : nullptr;
+    ++g_kernel_launches;
+    vp8b200_mb_predict_transform_fused(
+        g_stream, (const uint8_t *)dev_ptr(cur[0], false), (const uint8_t *)dev_ptr(cur[1], false),
+        (const uint8_t *)dev_ptr(cur[2], false), imgp, (const int32_t *)dev_ptr(ref_frame, false),
+        (const int16_t *)dev_ptr(vectors, false), (const int32_t *)dev_ptr(parts, false), (int16_t *)dev_ptr(MB, true),
+        (int32_t *)dev_ptr(seg_id, true), (float *)dev_ptr(ssim, true), (uint8_t *)dev_ptr(recon[0], true),
+        (uint8_t *)dev_ptr(recon[1], true), (uint8_t *)dev_ptr(recon[2], true), (const vp8b200_segment_data *)dev_ptr(SD, false),
+        target, width, height);
+    return (j - i) + 44;
+}
+
+// loop_filter_frame_luma + loop_filter_frame_chroma U, V of one frame (src/loop_filter.h:140-183)
+static size_t try_lf_planes(size_t i) {
+    if (g_cmds[i].id != K_LF_LUMA || i + 2 >= g_cmds.size()) return 0;
+    const Cmd &y = g_cmds[i], &u = g_cmds[i + 1], &v = g_cmds[i + 2];
+    if (u.id != K_LF_CHROMA || v.id != K_LF_CHROMA) return 0;
+    for (const Cmd *c : {&u, &v}) {
+        if (!same_mem(*c, 1, y, 1) || !same_mem(*c, 2, y, 2) || !same_mem(*c, 3, y, 3) ||
+            arg_int(ck(*c), 4) * 2 != arg_int(ck(y), 4) || arg_int(ck(*c), 5) * 2 != arg_int(ck(y), 5))
+            return 0;
+    }
+    if (same_mem(u, 0, y, 0) || same_mem(v, 0, y, 0) || same_mem(u, 0, v, 0)) return 0;
+    cl_kernel ky = ck(y);
+    ++g_kernel_launches;
+    vp8b200_loop_filter_planes(g_stream, out<uint8_t>(ky, 0), out<uint8_t>(ck(u), 0), out<uint8_t>(ck(v), 0),
+                               in<int32_t>(ky, 1), in<int32_t>(ky, 2), in<vp8b200_segment_data>(ky, 3), arg_int(ky, 4),
+                               arg_int(ky, 5));
+    return 3;
+}
+
+static void run_cmds() {
+    // (commands executed here may not enqueue: the list is stable while it runs)
+    for (size_t i = 0; i < g_cmds.size();) {
+        size_t used = 0;
+        if (g_fuse) {
+            used = try_multi_search1(i);
+            if (!used) used = try_multi_search2(i);
+            if (!used) used = try_fused_tail(i);
+            if (!used) used = try_lf_planes(i);
+        }
+        if (!used) {
+            Cmd &c = g_cmds[i];
+            if (c.id == C_COPY_BUFFER) {
+                const char *sp = (const char *)dev_ptr(c.src, false);
+                char *dp = (char *)dev_ptr(c.dst, true);
+                cudaMemcpyAsync(dp + c.a[1], sp + c.a[0], c.a[2], cudaMemcpyDeviceToDevice, g_stream);
+            } else if (c.id == C_COPY_IMAGE) {
+                const char *sp = (const char *)dev_ptr(c.src, false) + c.a[1] * c.src->width + c.a[0];
+                char *dp = (char *)dev_ptr(c.dst, true) + c.a[3] * c.dst->width + c.a[2];
+                cudaMemcpy2DAsync(dp, c.dst->width, sp, c.src->width, c.a[4], c.a[5], cudaMemcpyDeviceToDevice, g_stream);
+            } else {
+                dispatch_now(&c.k, c.global);
+            }
+            used = 1;
+        }
+        i += used;
+    }
+    g_cmds.clear();
+}
+
+static cl_int dispatch(cl_kernel k, size_t global) {
+    if (k->id < K_COUNT_PROBS) {  // CUDA kernel: defer
+        Cmd c;
+        c.id = k->id;
+        c.global = global;
+        c.k = *k;
+        c.src = c.dst = nullptr;
+        g_cmds.push_back(c);
+        return CL_SUCCESS;
+    }
+    flush_pending();  // host-executed kernel: everything before it must have been issued
+    return dispatch_now(k, global);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -566,10 +781,14 @@ cl_int clEnqueueWriteBuffer(cl_command_queue, cl_mem m, cl_bool blocking, size_t
 cl_int clEnqueueCopyBuffer(cl_command_queue, cl_mem s, cl_mem d, size_t so, size_t dof, size_t size, cl_uint,
                            const cl_event *, cl_event *) {
     if (!s || !d || so + size > s->size || dof + size > d->size) return CL_INVALID_VALUE;
-    flush_pending();
-    const char *sp = (const char *)dev_ptr(s, false);
-    char *dp = (char *)dev_ptr(d, true);
-    return cuda_rc(cudaMemcpyAsync(dp + dof, sp + so, size, cudaMemcpyDeviceToDevice, g_stream));
+    Cmd c;
+    c.id = C_COPY_BUFFER;
+    c.global = 0;
+    c.src = s;
+    c.dst = d;
+    c.a[0] = so; c.a[1] = dof; c.a[2] = size;
+    g_cmds.push_back(c);
+    return CL_SUCCESS;
 }
 
 cl_int clEnqueueWriteImage(cl_command_queue, cl_mem img, cl_bool blocking, const size_t *origin, const size_t *region,
@@ -589,10 +808,14 @@ cl_int clEnqueueWriteImage(cl_command_queue, cl_mem img, cl_bool blocking, const
 cl_int clEnqueueCopyImage(cl_command_queue, cl_mem s, cl_mem d, const size_t *so, const size_t *dor,
                           const size_t *region, cl_uint, const cl_event *, cl_event *) {
     if (!s || !d || !s->is_image || !d->is_image) return CL_INVALID_MEM_OBJECT;
-    flush_pending();
-    const char *sp = (const char *)dev_ptr(s, false) + so[1] * s->width + so[0];
-    char *dp = (char *)dev_ptr(d, true) + dor[1] * d->width + dor[0];
-    return cuda_rc(cudaMemcpy2DAsync(dp, d->width, sp, s->width, region[0], region[1], cudaMemcpyDeviceToDevice, g_stream));
+    Cmd c;
+    c.id = C_COPY_IMAGE;
+    c.global = 0;
+    c.src = s;
+    c.dst = d;
+    c.a[0] = so[0]; c.a[1] = so[1]; c.a[2] = dor[0]; c.a[3] = dor[1]; c.a[4] = region[0]; c.a[5] = region[1];
+    g_cmds.push_back(c);
+    return CL_SUCCESS;
 }
 
 void *clEnqueueMapBuffer(cl_command_queue, cl_mem m, cl_bool, cl_map_flags flags, size_t off, size_t size, cl_uint,
@@ -635,13 +858,10 @@ cl_int clEnqueueUnmapMemObject(cl_command_queue, cl_mem m, void *, cl_uint, cons
     return CL_SUCCESS;
 }
 
-cl_int clFlush(cl_command_queue) {
-    flush_pending();
-    return CL_SUCCESS;
-}
+cl_int clFlush(cl_command_queue) { return CL_SUCCESS; }
 cl_int clFinish(cl_command_queue) {
     ScopedTimer timer(T_FINISH);
-    flush_pending();
+    // waits for the transfers already issued; deferred kernels stay deferred (see the header comment)
     if (g_trace) fflush(g_trace);
     return cuda_rc(cudaStreamSynchronize(g_stream));
 }
