@@ -158,6 +158,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ref-frames", type=int, default=6, help="timed frames of the CPU reference sample")
+    ap.add_argument("--segments", type=int, default=4, help="independent segments (engines, streams) per GPU in the `value` run")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-mps", action="store_true", help="do not start a CUDA MPS daemon for the multi-instance e2e run")
     ap.add_argument("--e2e-procs", type=int, default=0, help="encoder instances per GPU for the e2e run (0 = auto)")
@@ -171,7 +172,8 @@ def main():
     tmp = tempfile.mkdtemp(prefix="vp8bench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
     config = {"workload": "1920x1080 synthetic YUV420 (tools/gen_y4m.py), padded to 1920x1088, LAST+GOLDEN+ALTREF, "
                           "q=24, altref-range 5, 8 partitions, loop filter on the GPU",
-              "frame_size": [WIDTH, HEIGHT], "segments_per_gpu": 1}
+              "frame_size": [WIDTH, HEIGHT], "segments_per_gpu": max(1, args.segments),
+              "step": "one frame of each of the segments_per_gpu independent segments (one engine + stream per segment)"}
     try:
         if args.impl == "reference":
             if rank != 0:
@@ -212,35 +214,48 @@ def b200_arm(args, rank, world, local_rank, tmp, config):
     M = (WRK_W // 16) * (WRK_H // 16)
     N = WRK_W * WRK_H
 
-    # ---- synthetic frames: every rank encodes its own keyframe-delimited segment -----------------
+    # ---- synthetic frames: every rank encodes S keyframe-delimited segments of its own ----------
+    # The path shards by independent segments.  A step is one frame of EACH of the S
+    # segments resident on this GPU, each segment on its own engine and stream: the dependency-bound
+    # loop filter of one segment overlaps the motion search of the others.
+    S = max(1, args.segments)
     nframes = 1 + W + K
     clip = gen_y4m.Clip(WRK_W, WRK_H)
-    first = rank * nframes
-    host_frames = [clip.frame(first + i) for i in range(nframes)]
-    dev_frames = [[torch.from_numpy(np.ascontiguousarray(p)).cuda() for p in f] for f in host_frames]
+    dev_frames = []
+    for sgm in range(S):
+        first = (rank * S + sgm) * nframes
+        host_frames = [clip.frame(first + i) for i in range(nframes)]
+        dev_frames.append([[torch.from_numpy(np.ascontiguousarray(p)).cuda() for p in f] for f in host_frames])
     sd = make_segment_data(QI)
 
-    e = eng.Engine(WRK_W, WRK_H)
+    engines = [eng.Engine(WRK_W, WRK_H) for _ in range(S)]
+    e = engines[0]
     stream_ptr = e.stream
-    ext_stream = torch.cuda.ExternalStream(stream_ptr)
+    ext_streams = [torch.cuda.ExternalStream(x.stream) for x in engines]
+    ext_stream = ext_streams[0]
+    master = torch.cuda.Stream()
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
     torch.cuda.synchronize()
-    state = HostState(10 ** 6, ALTREF_RANGE)
-    state.next_frame()
-    e.set_reconstruction(*dev_frames[0])  # the key frame's reconstruction seeds LAST/GOLDEN/ALTREF
+    states = [HostState(10 ** 6, ALTREF_RANGE) for _ in range(S)]
+    for sgm in range(S):
+        states[sgm].next_frame()
+        engines[sgm].set_reconstruction(*dev_frames[sgm][0])  # the key frame's reconstruction seeds LAST/GOLDEN/ALTREF
 
-    def step(i):
-        st = state.next_frame()
-        y, u, v = dev_frames[i]
-        e.inter_frame(y, u, v, sd, -1.0, st["prev_golden"], st["prev_altref"], st["altref_differs"])
-        n1 = e.last_launch_count
-        e.loop_filter(None)
-        return n1 + e.last_launch_count, 1 + (not st["prev_golden"]) + (not st["prev_altref"] and st["altref_differs"])
+    def step(sgm, i):
+        st = states[sgm].next_frame()
+        y, u, v = dev_frames[sgm][i]
+        x = engines[sgm]
+        x.inter_frame(y, u, v, sd, -1.0, st["prev_golden"], st["prev_altref"], st["altref_differs"])
+        n1 = x.last_launch_count
+        x.loop_filter(None)
+        return n1 + x.last_launch_count, 1 + (not st["prev_golden"]) + (not st["prev_altref"] and st["altref_differs"])
 
     for i in range(1, 1 + W):
-        step(i)
-    e.synchronize()
+        for sgm in range(S):
+            step(sgm, i)
+    for x in engines:
+        x.synchronize()
     if dist:
         dist.barrier()
     torch.cuda.synchronize()
@@ -248,16 +263,23 @@ def b200_arm(args, rank, world, local_rank, tmp, config):
     if rank == 0:
         sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    done = [[torch.cuda.Event() for _ in range(S)] for _ in range(K)]
     launches, refs_searched = 0, 0
-    with torch.cuda.stream(ext_stream):
-        for k in range(K):
+    for k in range(K):
+        with torch.cuda.stream(master):
             flush_buf.fill_(k & 255)           # L2 flush between timed steps, outside the timed span
-            ev[k][0].record(ext_stream)
-            n, r = step(1 + W + k)
-            ev[k][1].record(ext_stream)
+            ev[k][0].record(master)
+        for sgm in range(S):
+            ext_streams[sgm].wait_event(ev[k][0])
+            n, r = step(sgm, 1 + W + k)
+            done[k][sgm].record(ext_streams[sgm])
             launches += n
             refs_searched += r
-    e.synchronize()
+        for sgm in range(S):
+            master.wait_event(done[k][sgm])
+        ev[k][1].record(master)
+    for x in engines:
+        x.synchronize()
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
@@ -268,7 +290,9 @@ def b200_arm(args, rank, world, local_rank, tmp, config):
         t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
-    value = world * K / (total_ms * 1e-3)
+    value = world * K * S / (total_ms * 1e-3)
+    refs_searched /= S
+    dev_frames = dev_frames[0]
 
     # ---- roofline of the dominant kernel, timed live on the stream it is launched on -------------
     roofline = roofline_hbm = None
@@ -327,7 +351,8 @@ def b200_arm(args, rank, world, local_rank, tmp, config):
                         "frac": gbs / hbm_peak, "traffic": None, "ms_per_launch": ms_lf,
                         "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                         "note": "dependency-bound wavefront of mb_w+2(mb_h-1)=%d stages, not bandwidth-bound" % (WRK_W // 16 + 2 * (WRK_H // 16 - 1))}
-    e.close()
+    for x in engines:
+        x.close()
 
     # ---- end to end: the unmodified reference host against our OpenCL shim -------------------------
     # Every rank runs `procs` encoder instances on its GPU, each on its own keyframe-delimited

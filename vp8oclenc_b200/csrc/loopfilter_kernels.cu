@@ -21,6 +21,8 @@
 // Arithmetic: the reference uses short8 lanes.  Every intermediate stays far inside int16
 // (pixels - 128 drift by at most a few dozen between the clamped stores, the largest product
 // is 27 * 127), so plain int arithmetic is bit-identical.
+#include <mutex>
+
 #include "common.cuh"
 
 namespace vp8 {
@@ -438,35 +440,53 @@ __global__ void k_prepare_filter_mask(const int *__restrict__ MB, int *__restric
 
 using namespace vp8;
 
-// ticket counter and mailbox, one allocation per process (launches on different streams must not
-// overlap; the engine and the shim use a single stream)
-static int *g_lf_ctrl = nullptr;
-static uint32_t *g_lf_mail = nullptr;
-static size_t g_lf_mail_words = 0;
-static unsigned g_lf_tag = 0;
+// ticket counter and mailbox of the launches of one stream (launches on the same stream are ordered, launches
+// on different streams may overlap and must not share them)
+struct LFContext {
+    cudaStream_t stream;
+    int *ctrl;
+    uint32_t *mail;
+    size_t mail_words;
+    unsigned tag;
+};
+static LFContext g_lf_ctx[64];
+static int g_lf_ctx_count = 0;
+static std::mutex g_lf_mutex;
+
+static LFContext *lf_context(cudaStream_t st) {
+    std::lock_guard<std::mutex> lock(g_lf_mutex);
+    for (int i = 0; i < g_lf_ctx_count; ++i)
+        if (g_lf_ctx[i].stream == st) return &g_lf_ctx[i];
+    if (g_lf_ctx_count == 64) return nullptr;
+    LFContext *c = &g_lf_ctx[g_lf_ctx_count];
+    *c = LFContext{st, nullptr, nullptr, 0, 0};
+    if (cudaMalloc((void **)&c->ctrl, sizeof(int) * 4) != cudaSuccess) return nullptr;
+    ++g_lf_ctx_count;
+    return c;
+}
 
 static int launch_loop_filter(void *stream, LFPlanes p, int first_plane, int num_planes, const int32_t *seg,
                               const int32_t *mb_mask, const vp8b200_segment_data *SD, int luma_w, int luma_h) {
     cudaStream_t st = (cudaStream_t)stream;
     const int mbw = luma_w / 16, mbh = luma_h / 16;
-    if (!g_lf_ctrl && cudaMalloc((void **)&g_lf_ctrl, sizeof(int) * 4) != cudaSuccess)
-        return -(int)cudaErrorMemoryAllocation;
+    LFContext *c = lf_context(st);
+    if (!c) return -(int)cudaErrorMemoryAllocation;
     const size_t need = (size_t)num_planes * mbh * mbw * 32;
-    if (need > g_lf_mail_words) {
+    if (need > c->mail_words) {
         cudaStreamSynchronize(st);
-        if (g_lf_mail) cudaFree(g_lf_mail);
-        g_lf_mail = nullptr;
-        if (cudaMalloc((void **)&g_lf_mail, need * 4) != cudaSuccess) return -(int)cudaErrorMemoryAllocation;
-        g_lf_mail_words = need;
-        g_lf_tag = 0;
+        if (c->mail) cudaFree(c->mail);
+        c->mail = nullptr;
+        if (cudaMalloc((void **)&c->mail, need * 4) != cudaSuccess) return -(int)cudaErrorMemoryAllocation;
+        c->mail_words = need;
+        c->tag = 0;
     }
     // 16-bit launch tags; when they wrap (or the mailbox is new) clear it so that no stale tag can match
-    g_lf_tag = (g_lf_tag + 1) & 0xffffu;
-    if (g_lf_tag == 0 || g_lf_tag == 1) {
-        cudaMemsetAsync(g_lf_mail, 0, g_lf_mail_words * 4, st);
-        g_lf_tag = 1;
+    c->tag = (c->tag + 1) & 0xffffu;
+    if (c->tag == 0 || c->tag == 1) {
+        cudaMemsetAsync(c->mail, 0, c->mail_words * 4, st);
+        c->tag = 1;
     }
-    cudaMemsetAsync(g_lf_ctrl, 0, sizeof(int) * 4, st);
+    cudaMemsetAsync(c->ctrl, 0, sizeof(int) * 4, st);
     size_t smem = 0;
     for (int ps = 0; ps < num_planes; ++ps) {
         const int plane = first_plane + ps;
@@ -478,8 +498,8 @@ static int launch_loop_filter(void *stream, LFPlanes p, int first_plane, int num
             return -(int)cudaGetLastError();
         configured = smem;
     }
-    k_loop_filter<<<mbh, LF_THREADS, smem, st>>>(p, first_plane, num_planes, seg, mb_mask, SD, luma_w, luma_h, g_lf_ctrl,
-                                                 g_lf_mail, g_lf_tag);
+    k_loop_filter<<<mbh, LF_THREADS, smem, st>>>(p, first_plane, num_planes, seg, mb_mask, SD, luma_w, luma_h, c->ctrl,
+                                                 c->mail, c->tag);
     VP8_LAUNCH_CHECK();
 }
 
