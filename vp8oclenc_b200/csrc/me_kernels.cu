@@ -6,14 +6,15 @@
 // cost, not a SAD, so packed-byte SAD intrinsics cannot be used).  Design:
 //   * the search window of every 8x8 block is staged ONCE in shared memory and shared by all
 //     candidates (the reference re-reads global memory / the image per candidate);
-//   * the work unit is (block, candidate, 4x4 sub-block): 100 units per block for the
-//     full-pel levels, 104 for the quarter-pel level, so warps are (almost) fully populated
-//     instead of 25/32 lanes;
-//   * the four sub-block costs of a candidate are combined with two warp shuffles and the
-//     winner is found with one shared-memory atomicMin on the key (cost << 8 | scan index),
-//     which reproduces the reference's "first candidate in scan order wins ties";
+//   * a thread owns a 4x4 sub-block and a line of five candidates (20 threads per block plus, in the
+//     quarter-pel kernel, 4 for the zero vector), so warps are fully populated instead of 25/32
+//     lanes and everything the five candidates share is loaded and unpacked once;
+//   * the four sub-block costs of a candidate are combined with two warp shuffles; a thread keeps
+//     the minimum of its candidates' keys (cost << 8 | scan index) and the block winner is one
+//     shared-memory atomicMin per thread, which reproduces "first candidate in scan order wins";
 //   * in the quarter-pel kernel the horizontal six-tap pass is computed once per x-phase
-//     (5 variants) and shared by the 5 y-phases, instead of once per candidate.
+//     (5 variants) and shared by the 5 y-phases, instead of once per candidate; a thread owns one
+//     x-phase of one 4x4 sub-block and walks its five y-phases with the lines held in registers.
 #include "common.cuh"
 
 namespace vp8 {
@@ -41,8 +42,22 @@ __global__ void k_downsample_x2(const uint8_t *__restrict__ src, uint8_t *__rest
 
 // ------------------------------------------------------------------------------------------
 // luma_search_1step (src/GPU_kernels.cl:459-560): +-2 full search around the parent vector.
-constexpr int S1_BLOCKS = 8;             // 8x8 blocks per CTA
-constexpr int S1_THREADS = S1_BLOCKS * 100;  // (25 candidates x 4 sub-blocks) per block = 25 full warps
+//
+// S1_BLOCKS 8x8 blocks per CTA, 20 threads per block: a thread owns one row of candidates (dy) of
+// one 4x4 sub-block (j) and walks the five dx.  The eight window bytes per line that those five
+// candidates cover are two aligned words held in registers; a candidate's four pixels are a funnel
+// shift away.  Residuals are formed two at a time in 16-bit lanes with a +256 bias per lane (no
+// borrow between lanes), and the bias is folded into the constants of the cost transform
+// (weight4x4_biased), so unpacking costs one AND / one shift per pixel.
+#ifndef VP8_S1_BLOCKS
+#define VP8_S1_BLOCKS 8
+#endif
+#ifndef VP8_S1_MINCTAS
+#define VP8_S1_MINCTAS 8
+#endif
+constexpr int S1_BLOCKS = VP8_S1_BLOCKS;
+static_assert(S1_BLOCKS % 8 == 0, "threads must fill whole warps (full-mask shuffles)");
+constexpr int S1_THREADS = S1_BLOCKS * 20;
 
 // up to three references (LAST / GOLDEN / ALTREF) searched by one launch: blockIdx.y picks the set
 struct Search1Refs {
@@ -57,21 +72,52 @@ struct Search2Refs {
     int *ref_Bdiff[3];
 };
 
-__global__ void __launch_bounds__(S1_THREADS)
+// weight4x4 of a residual whose 16 entries all carry a +256 bias.  Pass 1: the bias cancels in the
+// differences, becomes +4096 in rows 0 and 2 and is taken out of the two products' constants; pass 2:
+// rows 0 and 2 carry +8192 in both sums, which only the DC-like term sees.  Exact integer identities.
+__device__ __forceinline__ int weight4x4_biased(const int (&r)[16]) {
+    int o[16];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int a1 = (r[k] + r[12 + k]) << 3;
+        const int d1 = (r[k] - r[12 + k]) << 3;
+        const int c1 = (r[4 + k] - r[8 + k]) << 3;
+        const int x = r[8 + k];
+        o[k] = a1 + c1;
+        o[8 + k] = a1 - c1;
+        o[4 + k] = (x * 2217 + d1 * 5352 + (14500 - 256 * 2217)) >> 12;
+        o[12 + k] = (d1 * 2217 - x * 5352 + (7500 + 256 * 5352)) >> 12;
+    }
+    int sum = 0;
+#pragma unroll
+    for (int row = 0; row < 4; ++row) {
+        const int a = o[4 * row] + o[4 * row + 3], d = o[4 * row] - o[4 * row + 3];
+        const int b = o[4 * row + 1] + o[4 * row + 2], c = o[4 * row + 1] - o[4 * row + 2];
+        const int f0 = (a + b + ((row & 1) ? 7 : 7 - 16384)) >> 4;
+        const int f2 = (a - b + 7) >> 4;
+        const int f1 = ((c * 2217 + d * 5352 + 12000) >> 16) + (d != 0);
+        const int f3 = (d * 2217 - c * 5352 + 51000) >> 16;
+        sum += (row == 0 ? (abs(f0) >> 2) : abs(f0)) + abs(f1) + abs(f2) + abs(f3);
+    }
+    return sum;
+}
+
+__global__ void __launch_bounds__(S1_THREADS, VP8_S1_MINCTAS)
 k_luma_search_1step(const uint8_t *__restrict__ cur, Search1Refs refs, int net_width, int width, int height, int rate,
                     int nblocks) {
     const uint8_t *__restrict__ prev = refs.prev[blockIdx.y];
     const short2 *__restrict__ src_net = refs.src_net[blockIdx.y];
     short2 *__restrict__ dst_net = refs.dst_net[blockIdx.y];
-    __shared__ uint8_t s_win[S1_BLOCKS][12][12];   // prev pixels [c+v0-2, c+v0+10) in both axes
-    __shared__ uint8_t s_cur[S1_BLOCKS][8][8];
-    __shared__ int s_cx[S1_BLOCKS], s_cy[S1_BLOCKS], s_vx[S1_BLOCKS], s_vy[S1_BLOCKS];
+    __shared__ uint32_t s_win[S1_BLOCKS][12][4];   // prev pixels [c+v0-2, c+v0+10) in both axes, 16-byte lines
+    __shared__ uint32_t s_cur[S1_BLOCKS][8][2];
+    __shared__ int4 s_geo[S1_BLOCKS];              // cx, cy, vx, vy
     __shared__ unsigned s_key[S1_BLOCKS];
 
     const int tid = threadIdx.x;
     const int bw = width >> 3;  // == cut_width/8
+    const int n0 = blockIdx.x * S1_BLOCKS;
     if (tid < S1_BLOCKS) {
-        const int n = blockIdx.x * S1_BLOCKS + tid;
+        const int n = n0 + tid;
         int cx = 0, cy = 0, vx = 0, vy = 0;
         if (n < nblocks) {
             cx = (n % bw) * 8;
@@ -83,7 +129,7 @@ k_luma_search_1step(const uint8_t *__restrict__ cur, Search1Refs refs, int net_w
             vy = (short)((int)pv.y / (int)(short)rate);
             if (rate > 8) vx = vy = 0;
         }
-        s_cx[tid] = cx; s_cy[tid] = cy; s_vx[tid] = vx; s_vy[tid] = vy;
+        s_geo[tid] = make_int4(cx, cy, vx, vy);
         s_key[tid] = 0xffffffffu;
     }
     __syncthreads();
@@ -93,57 +139,79 @@ k_luma_search_1step(const uint8_t *__restrict__ cur, Search1Refs refs, int net_w
     // coordinates are simply clamped to keep the loads in bounds.
     for (int i = tid; i < S1_BLOCKS * 144; i += S1_THREADS) {
         const int b = i / 144, r = (i % 144) / 12, c = i % 12;
-        const int x = clampi(s_cx[b] + s_vx[b] - 2 + c, 0, width - 1);
-        const int y = clampi(s_cy[b] + s_vy[b] - 2 + r, 0, height - 1);
-        s_win[b][r][c] = __ldg(prev + (size_t)y * width + x);
+        const int4 g = s_geo[b];
+        const int x = clampi(g.x + g.z - 2 + c, 0, width - 1);
+        const int y = clampi(g.y + g.w - 2 + r, 0, height - 1);
+        reinterpret_cast<uint8_t *>(&s_win[b][r][0])[c] = __ldg(prev + (size_t)y * width + x);
     }
-    for (int i = tid; i < S1_BLOCKS * 64; i += S1_THREADS) {
-        const int b = i >> 6, r = (i >> 3) & 7, c = i & 7;
-        const int n = blockIdx.x * S1_BLOCKS + b;
-        s_cur[b][r][c] = (n < nblocks) ? __ldg(cur + (size_t)(s_cy[b] + r) * width + s_cx[b] + c) : 0;
+    if (tid < S1_BLOCKS * 16) {
+        const int b = tid >> 4, r = (tid >> 1) & 7, h = tid & 1;
+        const int4 g = s_geo[b];  // blocks past the end read block 0's pixels and are dropped below
+        s_cur[b][r][h] = __ldg(reinterpret_cast<const uint32_t *>(cur + (size_t)(g.y + r) * width + g.x) + h);
     }
     __syncthreads();
 
     {
-        const int b = tid / 100, u = tid % 100, k = u >> 2, j = u & 3;
-        const int dx = k % 5, dy = k / 5;               // window offset of the candidate
-        const int sx = (j >> 1) * 4, sy = (j & 1) * 4;  // sub-block order (0,0),(0,4),(4,0),(4,4) as (x,y)
-        int r[16];
+        const int b = tid / 20, u = tid % 20, dy = u >> 2, j = u & 3;  // 20 is a multiple of 4: j groups stay aligned
+        const int sxw = j >> 1, sy = (j & 1) * 4;  // sub-block order (0,0),(0,4),(4,0),(4,4) as (x,y)
+        const int4 g = s_geo[b];
+        const int cx = g.x, cy = g.y, vx = g.z, vy = g.w;
+        const bool live = n0 + b < nblocks;
+        uint32_t clo[4], chi[4], w0[4], w1[4];
 #pragma unroll
-        for (int y = 0; y < 4; ++y)
+        for (int y = 0; y < 4; ++y) {
+            const uint32_t cw = s_cur[b][sy + y][sxw];
+            clo[y] = __byte_perm(cw, 0, 0x4140) + 0x01000100u;  // (c0, c1) + bias
+            chi[y] = __byte_perm(cw, 0, 0x4342) + 0x01000100u;  // (c2, c3) + bias
+            w0[y] = s_win[b][dy + sy + y][sxw];
+            w1[y] = s_win[b][dy + sy + y][sxw + 1];
+        }
+        const int py = (short)(cy + vy + dy - 2);
+        const bool yok = py >= 0 && py <= height - 8;
+        const int ypen = abs(abs(py - cy) - vy);
+        unsigned best = 0xffffffffu;
 #pragma unroll
-            for (int x = 0; x < 4; ++x)
-                r[4 * y + x] = (int)s_cur[b][sy + y][sx + x] - (int)s_win[b][dy + sy + y][dx + sx + x];
-        int cost = weight4x4(r);
-        cost += __shfl_xor_sync(0xffffffffu, cost, 1);
-        cost += __shfl_xor_sync(0xffffffffu, cost, 2);
-        if (j == 0) {
-            const int cx = s_cx[b], cy = s_cy[b], vx = s_vx[b], vy = s_vy[b];
-            const int px = (short)(cx + vx + dx - 2), py = (short)(cy + vy + dy - 2);
-            const bool inside = px >= 0 && px <= width - 8 && py >= 0 && py <= height - 8;
+        for (int dx = 0; dx < 5; ++dx) {
+            int r[16];
+#pragma unroll
+            for (int y = 0; y < 4; ++y) {
+                const uint32_t pw = dx == 0 ? w0[y] : (dx == 4 ? w1[y] : __funnelshift_r(w0[y], w1[y], 8 * dx));
+                const uint32_t dlo = clo[y] - __byte_perm(pw, 0, 0x4140);
+                const uint32_t dhi = chi[y] - __byte_perm(pw, 0, 0x4342);
+                r[4 * y + 0] = (int)(dlo & 0xffffu);
+                r[4 * y + 1] = (int)(dlo >> 16);
+                r[4 * y + 2] = (int)(dhi & 0xffffu);
+                r[4 * y + 3] = (int)(dhi >> 16);
+            }
+            int cost = weight4x4_biased(r);
+            cost += __shfl_xor_sync(0xffffffffu, cost, 1);
+            cost += __shfl_xor_sync(0xffffffffu, cost, 2);
+            const int px = (short)(cx + vx + dx - 2);
+            const bool inside = yok && px >= 0 && px <= width - 8;
             // the reference accumulates in an unsigned short (Q2) and adds the neighbour-coherence
             // term only at rates 2 and 1 (Q3): (| |p.x-c.x| - v0.x | + | |p.y-c.y| - v0.y |) * 32
             unsigned diff = (unsigned)cost & 0xffffu;
-            if (rate < 4) diff = (diff + (unsigned)((abs(abs(px - cx) - vx) + abs(abs(py - cy) - vy)) * 32)) & 0xffffu;
-            if (inside && diff < 0x7fffu && blockIdx.x * S1_BLOCKS + b < nblocks)
-                atomicMin(&s_key[b], (diff << 8) | (unsigned)k);
+            if (rate < 4) diff = (diff + (unsigned)((abs(abs(px - cx) - vx) + ypen) * 32)) & 0xffffu;
+            if (inside && diff < 0x7fffu) best = min(best, (diff << 8) | (unsigned)(dy * 5 + dx));
         }
+        if (j == 0 && live && best != 0xffffffffu) atomicMin(&s_key[b], best);
     }
     __syncthreads();
 
     if (tid < S1_BLOCKS) {
-        const int n = blockIdx.x * S1_BLOCKS + tid;
+        const int n = n0 + tid;
         if (n < nblocks) {
             const unsigned key = s_key[tid];
-            const int cx = s_cx[tid], cy = s_cy[tid];
+            const int4 g = s_geo[tid];
+            const int cx = g.x, cy = g.y;
             int bx, by;  // "vector" of the reference: a position once a candidate has won, else v0 itself
             if (key == 0xffffffffu) {
-                bx = s_vx[tid];
-                by = s_vy[tid];
+                bx = g.z;
+                by = g.w;
             } else {
                 const int k = key & 255;
-                bx = (short)(cx + s_vx[tid] + (k % 5) - 2);
-                by = (short)(cy + s_vy[tid] + (k / 5) - 2);
+                bx = (short)(cx + g.z + (k % 5) - 2);
+                by = (short)(cy + g.w + (k / 5) - 2);
             }
             short2 out;
             out.x = (short)((int)(short)(bx - cx) * (int)(short)rate);
@@ -156,114 +224,194 @@ k_luma_search_1step(const uint8_t *__restrict__ cur, Search1Refs refs, int net_w
 // ------------------------------------------------------------------------------------------
 // luma_search_2step (src/GPU_kernels.cl:776-1203): 25 quarter-pel candidates around 4*v plus
 // the zero vector, six-tap interpolation of the "search flavour" (every horizontally filtered
-// line is saturated before the vertical pass, Q5).  One CTA per 8x8 block.
-constexpr int S2_THREADS = 128;
+// line is saturated before the vertical pass, Q5).
+//
+// S2_BLOCKS 8x8 blocks per CTA.  Per block 20 "six-tap" threads (x-phase xi, 4x4 sub-block j) that
+// each walk the five y-phases of their column of candidates, and 4 threads for the zero-vector
+// candidate.  The horizontally filtered lines are kept transposed (a word = four consecutive lines
+// of one column), so the vertical six taps are two dp4a; the twelve lines a thread needs are loaded
+// once for its five candidates (12 registers), the current sub-block once; the y-phase loop is
+// unrolled, so taps and alignment shifts are immediates and the full-pel phase has no filter at all.
+#ifndef VP8_S2_BLOCKS
+#define VP8_S2_BLOCKS 8
+#endif
+#ifndef VP8_S2_MINCTAS
+#define VP8_S2_MINCTAS 5
+#endif
+constexpr int S2_BLOCKS = VP8_S2_BLOCKS;
+static_assert(S2_BLOCKS % 8 == 0, "the six-tap threads must fill whole warps (full-mask shuffles)");
+constexpr int S2_SIX = S2_BLOCKS * 20;           // six-tap threads
+constexpr int S2_THREADS = S2_BLOCKS * 24;       // + zero-vector threads
 
 // x/y phase variants of the five offsets -2..+2 quarter pels around a full-pel position:
 // integer origin offset (-1,-1,0,0,0) and eighth-pel filter phase (4,6,0,2,4)
-__device__ __forceinline__ int s2_origin(int i) { return i < 2 ? -1 : 0; }
-__device__ __forceinline__ int s2_phase(int i) { return (0x46024 >> (4 * (4 - i))) & 15; }
+__device__ __forceinline__ constexpr int s2_origin(int i) { return i < 2 ? -1 : 0; }
+__device__ __forceinline__ constexpr int s2_phase(int i) { return (0x46024 >> (4 * (4 - i))) & 15; }
 
-__global__ void __launch_bounds__(S2_THREADS)
-k_luma_search_2step(const uint8_t *__restrict__ cur, Search2Refs refs, int width, int height) {
+// the six taps of eighth-pel phase PH as compile-time constants (c_sixtap, RFC 6386)
+__device__ __forceinline__ constexpr int six_tap(int ph, int t) {
+    return ph == 2   ? (t == 0 ? 2 : t == 1 ? -11 : t == 2 ? 108 : t == 3 ? 36 : t == 4 ? -8 : 1)
+           : ph == 4 ? (t == 0 ? 3 : t == 1 ? -16 : t == 2 ? 77 : t == 3 ? 77 : t == 4 ? -16 : 3)
+                     : (t == 0 ? 1 : t == 1 ? -8 : t == 2 ? 36 : t == 3 ? 108 : t == 4 ? -11 : 2);  // ph == 6
+}
+
+// unsigned pixels x signed taps
+__device__ __forceinline__ int dp4a_u8s8(uint32_t a, uint32_t b, int c) {
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ constexpr uint32_t pack_taps(int a, int b, int c, int d) {
+    return (uint32_t)(a & 255) | ((uint32_t)(b & 255) << 8) | ((uint32_t)(c & 255) << 16) | ((uint32_t)(d & 255) << 24);
+}
+
+// Residual of one candidate: cur - saturate((64 + sum taps * lines) >> 7).  tl[x] = the twelve lines
+// sy..sy+11 of column x as three words (line = byte), so that four taps are one dp4a; first = line of
+// tap 0 of output row 0.  All shifts are compile-time constants after unrolling.
+template <int PH>
+__device__ __forceinline__ void s2_residual(const uint32_t (&tl)[4][3], int first, const uint32_t (&cur)[4], int (&r)[16]) {
+    constexpr uint32_t lo = pack_taps(six_tap(PH, 0), six_tap(PH, 1), six_tap(PH, 2), six_tap(PH, 3));
+    constexpr uint32_t hi = pack_taps(six_tap(PH, 4), six_tap(PH, 5), 0, 0);
+#pragma unroll
+    for (int y = 0; y < 4; ++y)
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+            const int s0 = first + y, a = s0 >> 2, sh = 8 * (s0 & 3);
+            const uint32_t w_lo = sh ? __funnelshift_r(tl[x][a], tl[x][a + 1], sh) : tl[x][a];
+            const uint32_t w_hi = sh ? __funnelshift_r(tl[x][a + 1], tl[x][(a + 2) % 3], sh) : tl[x][a + 1];
+            const int s = dp4a_u8s8(w_hi, hi, dp4a_u8s8(w_lo, lo, 64));
+            r[4 * y + x] = (int)__byte_perm(cur[y], 0, 0x4440 + x) - sat8(s >> 7);
+        }
+}
+
+__global__ void __launch_bounds__(S2_THREADS, VP8_S2_MINCTAS)
+k_luma_search_2step(const uint8_t *__restrict__ cur, Search2Refs refs, int width, int height, int nblocks) {
     const uint8_t *__restrict__ ref = refs.ref[blockIdx.y];
     const short2 *__restrict__ net = refs.net[blockIdx.y];
     short2 *__restrict__ ref_net = refs.ref_net[blockIdx.y];
     int *__restrict__ ref_Bdiff = refs.ref_Bdiff[blockIdx.y];
-    __shared__ uint8_t s_win[14][16];      // ref pixels rows/cols [base-3, base+11), clamp-to-edge
-    __shared__ uint32_t s_h[5][14][2];     // horizontally filtered + saturated lines, 8 px per row
-    __shared__ uint32_t s_cur[8][2];
-    __shared__ uint32_t s_zero[8][2];      // co-located reference block (candidate #25)
-    __shared__ unsigned s_key;
+    __shared__ uint8_t s_win[S2_BLOCKS][14][16];   // ref pixels rows/cols [base-3, base+11), clamp-to-edge
+    // horizontally filtered + saturated lines, TRANSPOSED: [x-phase][column][line], 16 lines (14 used) per column
+    __shared__ __align__(4) uint8_t s_h[S2_BLOCKS][5][8][16];
+    __shared__ uint32_t s_cur[S2_BLOCKS][8][2];
+    __shared__ uint32_t s_zero[S2_BLOCKS][8][2];   // co-located reference block (candidate #25)
+    __shared__ unsigned s_key[S2_BLOCKS];
 
     const int tid = threadIdx.x;
-    const int n = blockIdx.x;
     const int bw = width >> 3;
-    const int bx = (n % bw) * 8, by = (n / bw) * 8;
-    const short2 v = net[n];
-    const int v0x = (short)(v.x * 4), v0y = (short)(v.y * 4);  // short lanes in the reference
-    const int basex = bx + (v0x >> 2), basey = by + (v0y >> 2);  // v0 is a multiple of 4
+    const int n0 = blockIdx.x * S2_BLOCKS;
 
-    if (tid == 0) s_key = 0xffffffffu;
-    for (int i = tid; i < 14 * 14; i += S2_THREADS) {
-        const int r = i / 14, c = i % 14;
-        const int x = clampi(basex - 3 + c, 0, width - 1), y = clampi(basey - 3 + r, 0, height - 1);
-        s_win[r][c] = __ldg(ref + (size_t)y * width + x);
+    __shared__ int4 s_geo[S2_BLOCKS];              // bx, by, v0x, v0y of every block
+    if (tid < S2_BLOCKS) {
+        const int n = min(n0 + tid, nblocks - 1);
+        const short2 v = __ldg(net + n);
+        // short lanes in the reference; v0 is a multiple of 4
+        s_geo[tid] = make_int4((n % bw) * 8, (n / bw) * 8, (short)(v.x * 4), (short)(v.y * 4));
+        s_key[tid] = 0xffffffffu;
     }
-    if (tid < 16) {
-        const int r = tid >> 1, h = tid & 1;
-        s_cur[r][h] = __ldg(reinterpret_cast<const uint32_t *>(cur + (size_t)(by + r) * width + bx) + h);
-        s_zero[r][h] = __ldg(reinterpret_cast<const uint32_t *>(ref + (size_t)(by + r) * width + bx) + h);
+    __syncthreads();
+    auto geometry = [&](int b, int &bx, int &by, int &v0x, int &v0y) {
+        const int4 g = s_geo[b];
+        bx = g.x; by = g.y; v0x = g.z; v0y = g.w;
+    };
+
+    for (int i = tid; i < S2_BLOCKS * 14 * 14; i += S2_THREADS) {
+        const int b = i / 196, r = (i % 196) / 14, c = i % 14;
+        const int4 g = s_geo[b];
+        const int x = clampi(g.x + (g.z >> 2) - 3 + c, 0, width - 1), y = clampi(g.y + (g.w >> 2) - 3 + r, 0, height - 1);
+        s_win[b][r][c] = __ldg(ref + (size_t)y * width + x);
+    }
+    if (tid < S2_BLOCKS * 16) {
+        const int b = tid >> 4, r = (tid >> 1) & 7, h = tid & 1;
+        const int4 g = s_geo[b];
+        s_cur[b][r][h] = __ldg(reinterpret_cast<const uint32_t *>(cur + (size_t)(g.y + r) * width + g.x) + h);
+        s_zero[b][r][h] = __ldg(reinterpret_cast<const uint32_t *>(ref + (size_t)(g.y + r) * width + g.x) + h);
     }
     __syncthreads();
 
-    // horizontal pass: 5 x-variants x 14 rows x 8 columns, four columns (one word) per item
-    for (int i = tid; i < 5 * 14 * 2; i += S2_THREADS) {
-        const int var = i / 28, r = (i % 28) >> 1, h = i & 1;
+    // horizontal pass: 5 x-variants x 14 rows x 8 columns per block, four columns (one word) per item
+    for (int i = tid; i < S2_BLOCKS * 140; i += S2_THREADS) {
+        const int b = i / 140, q = i % 140;
+        const int var = q / 28, r = (q % 28) >> 1, h = q & 1;
         const int ph = s2_phase(var), first = s2_origin(var) + 1 + 4 * h;  // window column of tap 0 of output 0
-        uint32_t packed = 0;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             int s = 64;
 #pragma unroll
-            for (int t = 0; t < 6; ++t) s += (int)c_sixtap[ph][t] * (int)s_win[r][first + c + t];
+            for (int t = 0; t < 6; ++t) s += (int)c_sixtap[ph][t] * (int)s_win[b][r][first + c + t];
             // (s/128 then saturate) == saturate(s>>7): the two only differ for -128<s<0, both give 0
-            packed |= (uint32_t)sat8(s >> 7) << (8 * c);
+            s_h[b][var][4 * h + c][r] = (uint8_t)sat8(s >> 7);
         }
-        s_h[var][r][h] = packed;
     }
     __syncthreads();
 
     {
-        // 104 work units; the 24 spare lanes of the last warp run the zero-vector path with
-        // valid=false so that the full-mask shuffles below are executed by whole warps
-        const int k = min(tid >> 2, 25), j = tid & 3;
-        const int sx = j >> 1, sy = (j & 1) * 4;  // sub-block (x word, y row offset); order as dx4/dy4
+        const bool six = tid < S2_SIX;
+        const int b = six ? tid / 20 : (tid - S2_SIX) >> 2;
+        const int u = six ? tid % 20 : 0;
+        const int xi = u >> 2, j = tid & 3;             // 20 and S2_SIX are multiples of 4
+        const int sx = j >> 1, sy = (j & 1) * 4;        // sub-block (x word, y row offset); order as dx4/dy4
+        const bool live = n0 + b < nblocks;
+        int bx, by, v0x, v0y;
+        geometry(b, bx, by, v0x, v0y);
+        uint32_t cu[4];  // the current sub-block stays packed: one PRMT per use is cheaper than 12 more registers
+#pragma unroll
+        for (int y = 0; y < 4; ++y) cu[y] = s_cur[b][sy + y][sx];
+        unsigned best = 0xffffffffu;
         int r[16];
-        bool valid = tid < 104;
-        int penalty = 0;
-        if (k < 25) {
-            const int xi = k % 5, yi = k / 5;
-            const int qx = (short)(bx * 4 + v0x + xi - 2), qy = (short)(by * 4 + v0y + yi - 2);
-            valid = qx >= 0 && qx <= width * 4 - 32 && qy >= 0 && qy <= height * 4 - 32;
-            penalty = (abs(xi - 2) + abs(yi - 2)) * 32;
-            const int ph = s2_phase(yi), row0 = s2_origin(yi) + 1 + sy;  // s_h row of tap 0 of output row 0
-            int col[9][4];
+        if (six) {
+            uint32_t tl[4][3];  // lines sy .. sy+11 of the four columns of this x-phase (lines >= 14 are never used)
 #pragma unroll
-            for (int t = 0; t < 9; ++t) {
-                const uint32_t w = s_h[xi][row0 + t][sx];
-                col[t][0] = w & 255; col[t][1] = (w >> 8) & 255; col[t][2] = (w >> 16) & 255; col[t][3] = w >> 24;
+            for (int x = 0; x < 4; ++x) {
+                const uint32_t *cw = reinterpret_cast<const uint32_t *>(&s_h[b][xi][4 * sx + x][sy]);
+                tl[x][0] = cw[0]; tl[x][1] = cw[1]; tl[x][2] = cw[2];
             }
-            const int f0 = c_sixtap[ph][0], f1 = c_sixtap[ph][1], f2 = c_sixtap[ph][2], f3 = c_sixtap[ph][3],
-                      f4 = c_sixtap[ph][4], f5 = c_sixtap[ph][5];
+            const int qx = (short)(bx * 4 + v0x + xi - 2);
+            const bool xok = qx >= 0 && qx <= width * 4 - 32;
 #pragma unroll
-            for (int y = 0; y < 4; ++y) {
-                const uint32_t cw = s_cur[sy + y][sx];
+            for (int yi = 0; yi < 5; ++yi) {
+                constexpr int kFirst[5] = {0, 0, 1, 1, 1};  // s2_origin(yi) + 1
+                if (yi == 0) s2_residual<4>(tl, kFirst[0], cu, r);
+                if (yi == 1) s2_residual<6>(tl, kFirst[1], cu, r);
+                if (yi == 2) {
 #pragma unroll
-                for (int x = 0; x < 4; ++x) {
-                    const int s = 64 + f0 * col[y][x] + f1 * col[y + 1][x] + f2 * col[y + 2][x] + f3 * col[y + 3][x] +
-                                  f4 * col[y + 4][x] + f5 * col[y + 5][x];
-                    r[4 * y + x] = (int)((cw >> (8 * x)) & 255) - sat8(s >> 7);
+                    for (int y = 0; y < 4; ++y)
+#pragma unroll
+                        for (int x = 0; x < 4; ++x)  // full-pel phase: line first+2+y itself
+                            r[4 * y + x] = (int)__byte_perm(cu[y], 0, 0x4440 + x) -
+                                           (int)__byte_perm(tl[x][(kFirst[2] + 2 + y) >> 2], 0, 0x4440 + ((kFirst[2] + 2 + y) & 3));
                 }
+                if (yi == 3) s2_residual<2>(tl, kFirst[3], cu, r);
+                if (yi == 4) s2_residual<4>(tl, kFirst[4], cu, r);
+                int cost = weight4x4(r);
+                cost += __shfl_xor_sync(0xffffffffu, cost, 1);
+                cost += __shfl_xor_sync(0xffffffffu, cost, 2);
+                cost += (abs(xi - 2) + abs(yi - 2)) * 32;
+                const int qy = (short)(by * 4 + v0y + yi - 2);
+                const bool valid = xok && qy >= 0 && qy <= height * 4 - 32;
+                if (valid && cost < 0x7fff) best = min(best, ((unsigned)cost << 5) | (unsigned)(yi * 5 + xi));
             }
         } else {  // candidate #25: the zero vector, full-pel, no penalty
 #pragma unroll
             for (int y = 0; y < 4; ++y) {
-                const uint32_t cw = s_cur[sy + y][sx], zw = s_zero[sy + y][sx];
+                const uint32_t zw = s_zero[b][sy + y][sx];
 #pragma unroll
-                for (int x = 0; x < 4; ++x) r[4 * y + x] = (int)((cw >> (8 * x)) & 255) - (int)((zw >> (8 * x)) & 255);
+                for (int x = 0; x < 4; ++x) r[4 * y + x] = (int)__byte_perm(cu[y], 0, 0x4440 + x) - (int)((zw >> (8 * x)) & 255);
             }
+            int cost = weight4x4(r);
+            cost += __shfl_xor_sync(0xffffffffu, cost, 1);
+            cost += __shfl_xor_sync(0xffffffffu, cost, 2);
+            if (cost < 0x7fff) best = ((unsigned)cost << 5) | 25u;
         }
-        int cost = weight4x4(r);
-        cost += __shfl_xor_sync(0xffffffffu, cost, 1);
-        cost += __shfl_xor_sync(0xffffffffu, cost, 2);
-        cost += penalty;
-        if (j == 0 && valid && cost < 0x7fff) atomicMin(&s_key, ((unsigned)cost << 5) | (unsigned)k);
+        if (j == 0 && live && best != 0xffffffffu) atomicMin(&s_key[b], best);
     }
     __syncthreads();
 
-    if (tid == 0) {
-        const unsigned key = s_key;
+    if (tid < S2_BLOCKS && n0 + tid < nblocks) {
+        const int n = n0 + tid;
+        int bx, by, v0x, v0y;
+        geometry(tid, bx, by, v0x, v0y);
+        const unsigned key = s_key[tid];
         int qx = (short)(width * 4 - 32), qy = (short)(height * 4 - 32), best = 0x7fff;
         if (key != 0xffffffffu) {
             const int k = key & 31;
@@ -378,8 +526,8 @@ extern "C" int vp8b200_luma_search_2step_multi(void *stream, const uint8_t *cur,
         r.ref_net[i] = (short2 *)ref_net[i];
         r.ref_Bdiff[i] = ref_Bdiff[i];
     }
-    dim3 grid(nblocks, nrefs);
-    k_luma_search_2step<<<grid, S2_THREADS, 0, (cudaStream_t)stream>>>(cur, r, width, height);
+    dim3 grid((nblocks + S2_BLOCKS - 1) / S2_BLOCKS, nrefs);
+    k_luma_search_2step<<<grid, S2_THREADS, 0, (cudaStream_t)stream>>>(cur, r, width, height, nblocks);
     VP8_LAUNCH_CHECK();
 }
 
