@@ -66,7 +66,7 @@ def test_reset_vectors(eng):
 
 
 @pytest.mark.parametrize("rate", [16, 8, 4, 2, 1])
-@pytest.mark.parametrize("w,h", [(64, 48), (120, 68), (88, 72), (352, 288)])
+@pytest.mark.parametrize("w,h", [(64, 48), (120, 68), (88, 72), (352, 288), (22, 18), (11, 9), (45, 27)])
 def test_luma_search_1step(eng, rate, w, h):
     o = oracle()
     for seed, lim in ((10, 6), (11, 40), (12, 0)):

@@ -144,10 +144,18 @@ k_luma_search_1step(const uint8_t *__restrict__ cur, Search1Refs refs, int net_w
         const int y = clampi(g.y + g.w - 2 + r, 0, height - 1);
         reinterpret_cast<uint8_t *>(&s_win[b][r][0])[c] = __ldg(prev + (size_t)y * width + x);
     }
-    if (tid < S1_BLOCKS * 16) {
-        const int b = tid >> 4, r = (tid >> 1) & 7, h = tid & 1;
-        const int4 g = s_geo[b];  // blocks past the end read block 0's pixels and are dropped below
-        s_cur[b][r][h] = __ldg(reinterpret_cast<const uint32_t *>(cur + (size_t)(g.y + r) * width + g.x) + h);
+    if ((width & 3) == 0) {
+        if (tid < S1_BLOCKS * 16) {
+            const int b = tid >> 4, r = (tid >> 1) & 7, h = tid & 1;
+            const int4 g = s_geo[b];  // blocks past the end read block 0's pixels and are dropped below
+            s_cur[b][r][h] = __ldg(reinterpret_cast<const uint32_t *>(cur + (size_t)(g.y + r) * width + g.x) + h);
+        }
+    } else {  // pyramid planes of frames whose width is not a multiple of 64: lines are not word aligned
+        for (int i = tid; i < S1_BLOCKS * 64; i += S1_THREADS) {
+            const int b = i >> 6, r = (i >> 3) & 7, c = i & 7;
+            const int4 g = s_geo[b];
+            reinterpret_cast<uint8_t *>(&s_cur[b][r][0])[c] = __ldg(cur + (size_t)(g.y + r) * width + g.x + c);
+        }
     }
     __syncthreads();
 
