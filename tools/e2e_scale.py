@@ -54,12 +54,17 @@ if __name__ == "__main__":
         for P in Ps:
             u = Util()
             procs = [segments.EncoderProcess(y4m, os.path.join(tmp, "o%d.ivf" % p), ENC_ARGS, os.path.join(tmp, "run%d" % p),
-                                             env_extra=extra) for p in range(P)]
+                                             env_extra=dict(extra, VP8B200_STATS=os.path.join(tmp, "stats%d.json" % p)))
+                     for p in range(P)]
             stamps = [pr.wait() for pr in procs]
             util = u.stop()
             t0 = max(st[4] for st in stamps)
             t1 = max(st[-1] for st in stamps)
             count = sum(1 for st in stamps for x in st if x > t0)
             la = os.getloadavg()[0]
+            import json
+            st = [json.load(open(os.path.join(tmp, "stats%d.json" % p))) for p in range(P)]
+            keys = [k for k in st[0] if k.startswith(("ms_", "cpu_"))]
+            print("      per frame per instance: " + "  ".join("%s %.2f" % (k, sum(x[k] for x in st) / P / n) for k in keys), flush=True)
             print("P=%2d  %7.1f frames/s  (%.2f ms/frame aggregate)  gpu util median %s%%  loadavg %.1f" %
                   (P, count / (t1 - t0), 1000.0 * (t1 - t0) / count, util, la), flush=True)

@@ -25,6 +25,7 @@
 //    match exactly runs kernel by kernel.  VP8B200_FUSED=0 turns the replacement off.
 #include <CL/cl.h>
 #include <cuda_runtime.h>
+#include <sys/resource.h>
 #include <time.h>
 
 #include <cstdio>
@@ -117,6 +118,10 @@ static void write_stats() {
         fprintf(f, "{\"h2d_bytes\": %llu, \"d2h_bytes\": %llu, \"kernel_launches\": %llu, \"host_kernels\": %llu",
                 g_h2d_bytes, g_d2h_bytes, g_kernel_launches, g_host_kernels);
         for (int i = 0; i < T_KINDS; ++i) fprintf(f, ", \"ms_%s\": %.3f", kTimedNames[i], g_ns[i] * 1e-6);
+        rusage ru;
+        getrusage(RUSAGE_SELF, &ru);  // all threads of the encoder instance
+        fprintf(f, ", \"cpu_user_ms\": %.3f, \"cpu_sys_ms\": %.3f", ru.ru_utime.tv_sec * 1e3 + ru.ru_utime.tv_usec * 1e-3,
+                ru.ru_stime.tv_sec * 1e3 + ru.ru_stime.tv_usec * 1e-3);
         fprintf(f, ", \"ms_total\": %.3f}\n", (now_ns() - g_ns_start) * 1e-6);
         fclose(f);
     }
@@ -124,6 +129,9 @@ static void write_stats() {
 
 static std::vector<Cmd> g_cmds;  // the deferred command list
 static bool g_fuse = true;       // VP8B200_FUSED=0: execute the list kernel by kernel
+
+static int g_sync_sleep_us = 0;  // VP8B200_SYNC=sleep<us>
+static cudaEvent_t g_sync_event = nullptr;
 
 static bool cuda_init() {
     if (g_cuda_tried) return g_cuda_ok;
@@ -140,6 +148,7 @@ static bool cuda_init() {
     if (const char *sync = getenv("VP8B200_SYNC")) {
         if (!strcmp(sync, "block")) cudaSetDeviceFlags(cudaDeviceScheduleBlockingSync);
         else if (!strcmp(sync, "yield")) cudaSetDeviceFlags(cudaDeviceScheduleYield);
+        else if (!strncmp(sync, "sleep", 5)) g_sync_sleep_us = sync[5] ? atoi(sync + 5) : 20;
     }
     if (cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking) != cudaSuccess) return false;
     vp8b200_device_info(g_dev_name, sizeof(g_dev_name), &g_sm_count, nullptr, nullptr);
@@ -150,6 +159,23 @@ static bool cuda_init() {
     g_ns_start = now_ns();
     g_cuda_ok = true;
     return true;
+}
+
+// Waits for everything issued on the stream.  VP8B200_SYNC=sleep polls an event with short sleeps in
+// between instead of spinning: when more encoder instances than cores share the machine, the cores go
+// to the instances that have host work to do.
+static cudaError_t stream_sync() {
+    if (g_sync_sleep_us <= 0) return cudaStreamSynchronize(g_stream);
+    if (!g_sync_event) cudaEventCreateWithFlags(&g_sync_event, cudaEventDisableTiming);
+    cudaError_t e = cudaEventRecord(g_sync_event, g_stream);
+    if (e != cudaSuccess) return e;
+    for (int spins = 0;; ++spins) {
+        e = cudaEventQuery(g_sync_event);
+        if (e != cudaErrorNotReady) return e;
+        if (spins < 20) continue;  // short waits are cheaper spun
+        timespec ts = {0, g_sync_sleep_us * 1000L};
+        nanosleep(&ts, nullptr);
+    }
 }
 
 static void trace_rec(unsigned kind, unsigned idx, size_t off, size_t size, const void *payload) {
@@ -198,7 +224,7 @@ static void *host_ptr(cl_mem m, bool will_write, bool discard = false) {
         if (!discard) {
             cudaMemcpyAsync(m->host, m->dev, m->size, cudaMemcpyDeviceToHost, g_stream);
             g_d2h_bytes += m->size;
-            cudaStreamSynchronize(g_stream);
+            stream_sync();
         }
         m->host_valid = true;
     }
@@ -628,7 +654,7 @@ cl_command_queue clCreateCommandQueue(cl_context ctx, cl_device_id, cl_command_q
 }
 cl_int clReleaseCommandQueue(cl_command_queue q) {
     flush_pending();
-    cudaStreamSynchronize(g_stream);
+    stream_sync();
     delete q;
     return CL_SUCCESS;
 }
@@ -676,7 +702,7 @@ cl_mem clCreateImage2D(cl_context, cl_mem_flags, const cl_image_format *fmt, siz
 cl_int clReleaseMemObject(cl_mem m) {
     if (!m) return CL_INVALID_MEM_OBJECT;
     flush_pending();
-    cudaStreamSynchronize(g_stream);
+    stream_sync();
     cudaFree(m->dev);
     if (m->host) cudaFreeHost(m->host);
     delete m;
@@ -741,7 +767,7 @@ cl_int clEnqueueReadBuffer(cl_command_queue, cl_mem m, cl_bool blocking, size_t 
         cudaError_t e = cudaMemcpyAsync(ptr, (char *)m->dev + off, size, cudaMemcpyDeviceToHost, g_stream);
         g_d2h_bytes += size;
         if (e != cudaSuccess) return cuda_rc(e);
-        if (blocking || g_trace) cudaStreamSynchronize(g_stream);
+        if (blocking || g_trace) stream_sync();
     } else {
         memcpy(ptr, (char *)m->host + off, size);
     }
@@ -774,7 +800,7 @@ cl_int clEnqueueWriteBuffer(cl_command_queue, cl_mem m, cl_bool blocking, size_t
     cudaError_t e = cudaMemcpyAsync((char *)m->dev + off, ptr, size, cudaMemcpyHostToDevice, g_stream);
     g_h2d_bytes += size;
     m->host_valid = false;
-    if (blocking) cudaStreamSynchronize(g_stream);
+    if (blocking) stream_sync();
     return cuda_rc(e);
 }
 
@@ -801,7 +827,7 @@ cl_int clEnqueueWriteImage(cl_command_queue, cl_mem img, cl_bool blocking, const
     cudaError_t e = cudaMemcpy2DAsync(dst, img->width, ptr, pitch, region[0], region[1], cudaMemcpyHostToDevice, g_stream);
     g_h2d_bytes += region[0] * region[1];
     if (pitch == region[0]) trace_rec(4, img->index, 0, region[0] * region[1], ptr);
-    if (blocking) cudaStreamSynchronize(g_stream);
+    if (blocking) stream_sync();
     return cuda_rc(e);
 }
 
@@ -834,7 +860,7 @@ void *clEnqueueMapBuffer(cl_command_queue, cl_mem m, cl_bool, cl_map_flags flags
         return nullptr;
     }
     // in-flight asynchronous reads into other mapped buffers must have landed before the host looks
-    cudaStreamSynchronize(g_stream);
+    stream_sync();
     m->mapped_for_write = writes;
     if (writes) m->dev_valid = false;  // the host owns the contents until the unmap
     if (err) *err = CL_SUCCESS;
@@ -844,7 +870,7 @@ void *clEnqueueMapBuffer(cl_command_queue, cl_mem m, cl_bool, cl_map_flags flags
 cl_int clEnqueueUnmapMemObject(cl_command_queue, cl_mem m, void *, cl_uint, const cl_event *, cl_event *) {
     if (!m) return CL_INVALID_MEM_OBJECT;
     if (g_trace) {
-        cudaStreamSynchronize(g_stream);
+        stream_sync();
         trace_rec(5, m->index, 0, m->size, m->host);
     }
     if (m->mapped_for_write) {
@@ -863,7 +889,7 @@ cl_int clFinish(cl_command_queue) {
     ScopedTimer timer(T_FINISH);
     // waits for the transfers already issued; deferred kernels stay deferred (see the header comment)
     if (g_trace) fflush(g_trace);
-    return cuda_rc(cudaStreamSynchronize(g_stream));
+    return cuda_rc(stream_sync());
 }
 
 }  // extern "C"
