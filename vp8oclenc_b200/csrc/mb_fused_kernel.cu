@@ -80,7 +80,10 @@ __device__ __forceinline__ void predict4x4(const uint8_t *__restrict__ ref, int 
         }
 }
 
-__global__ void __launch_bounds__(FUSED_WARPS * 32)
+#ifndef VP8_FUSED_MINCTAS
+#define VP8_FUSED_MINCTAS 8
+#endif
+__global__ void __launch_bounds__(FUSED_WARPS * 32, VP8_FUSED_MINCTAS)
 k_mb_fused(const uint8_t *__restrict__ cur_y, const uint8_t *__restrict__ cur_u, const uint8_t *__restrict__ cur_v,
            FusedRefs refs, const int *__restrict__ MB_ref, const short2 *__restrict__ MB_vec,
            const int *__restrict__ MB_parts, short *__restrict__ MB, int *__restrict__ MB_seg,

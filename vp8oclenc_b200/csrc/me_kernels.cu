@@ -137,12 +137,25 @@ k_luma_search_1step(const uint8_t *__restrict__ cur, Search1Refs refs, int net_w
     // stage windows and current blocks.  Pixels outside the plane are only ever used by
     // candidates that are not fully inside it, and those can never win (Q2), so the
     // coordinates are simply clamped to keep the loads in bounds.
-    for (int i = tid; i < S1_BLOCKS * 144; i += S1_THREADS) {
-        const int b = i / 144, r = (i % 144) / 12, c = i % 12;
+    // One window line per thread: four aligned words cover its 12 pixels wherever they start; lines
+    // that touch the left/right edge of the plane (or an unaligned plane) take the clamped byte path.
+    for (int i = tid; i < S1_BLOCKS * 12; i += S1_THREADS) {
+        const int b = i / 12, r = i % 12;
         const int4 g = s_geo[b];
-        const int x = clampi(g.x + g.z - 2 + c, 0, width - 1);
-        const int y = clampi(g.y + g.w - 2 + r, 0, height - 1);
-        reinterpret_cast<uint8_t *>(&s_win[b][r][0])[c] = __ldg(prev + (size_t)y * width + x);
+        const int x0 = g.x + g.z - 2, y = clampi(g.y + g.w - 2 + r, 0, height - 1);
+        const uint8_t *line = prev + (size_t)y * width;
+        const int xa = x0 & ~3;
+        if (x0 >= 0 && xa + 16 <= width && ((reinterpret_cast<uintptr_t>(prev) | (unsigned)width) & 3) == 0) {
+            const uint32_t *wp = reinterpret_cast<const uint32_t *>(line + xa);
+            const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2), w3 = __ldg(wp + 3);
+            const int sh = 8 * (x0 & 3);
+            s_win[b][r][0] = __funnelshift_r(w0, w1, sh);
+            s_win[b][r][1] = __funnelshift_r(w1, w2, sh);
+            s_win[b][r][2] = __funnelshift_r(w2, w3, sh);
+        } else {
+            uint8_t *dst = reinterpret_cast<uint8_t *>(&s_win[b][r][0]);
+            for (int c = 0; c < 12; ++c) dst[c] = __ldg(line + clampi(x0 + c, 0, width - 1));
+        }
     }
     if ((width & 3) == 0) {
         if (tid < S1_BLOCKS * 16) {
@@ -246,6 +259,9 @@ k_luma_search_1step(const uint8_t *__restrict__ cur, Search1Refs refs, int net_w
 #ifndef VP8_S2_MINCTAS
 #define VP8_S2_MINCTAS 5
 #endif
+#ifndef VP8_S2_UNROLL
+#define VP8_S2_UNROLL 1
+#endif
 constexpr int S2_BLOCKS = VP8_S2_BLOCKS;
 static_assert(S2_BLOCKS % 8 == 0, "the six-tap threads must fill whole warps (full-mask shuffles)");
 constexpr int S2_SIX = S2_BLOCKS * 20;           // six-tap threads
@@ -276,10 +292,13 @@ __device__ __forceinline__ constexpr uint32_t pack_taps(int a, int b, int c, int
 // Residual of one candidate: cur - saturate((64 + sum taps * lines) >> 7).  tl[x] = the twelve lines
 // sy..sy+11 of column x as three words (line = byte), so that four taps are one dp4a; first = line of
 // tap 0 of output row 0.  All shifts are compile-time constants after unrolling.
-template <int PH>
-__device__ __forceinline__ void s2_residual(const uint32_t (&tl)[4][3], int first, const uint32_t (&cur)[4], int (&r)[16]) {
-    constexpr uint32_t lo = pack_taps(six_tap(PH, 0), six_tap(PH, 1), six_tap(PH, 2), six_tap(PH, 3));
-    constexpr uint32_t hi = pack_taps(six_tap(PH, 4), six_tap(PH, 5), 0, 0);
+__device__ __forceinline__ constexpr uint32_t taps_lo(int ph) {
+    return pack_taps(six_tap(ph, 0), six_tap(ph, 1), six_tap(ph, 2), six_tap(ph, 3));
+}
+__device__ __forceinline__ constexpr uint32_t taps_hi(int ph) { return pack_taps(six_tap(ph, 4), six_tap(ph, 5), 0, 0); }
+
+__device__ __forceinline__ void s2_residual(const uint32_t (&tl)[4][3], int first, uint32_t lo, uint32_t hi,
+                                            const uint32_t (&cur)[4], int (&r)[16]) {
 #pragma unroll
     for (int y = 0; y < 4; ++y)
 #pragma unroll
@@ -298,7 +317,7 @@ k_luma_search_2step(const uint8_t *__restrict__ cur, Search2Refs refs, int width
     const short2 *__restrict__ net = refs.net[blockIdx.y];
     short2 *__restrict__ ref_net = refs.ref_net[blockIdx.y];
     int *__restrict__ ref_Bdiff = refs.ref_Bdiff[blockIdx.y];
-    __shared__ uint8_t s_win[S2_BLOCKS][14][16];   // ref pixels rows/cols [base-3, base+11), clamp-to-edge
+    __shared__ uint32_t s_win[S2_BLOCKS][14][5];   // ref pixels rows/cols [base-3, base+11), clamp-to-edge; 20-byte lines
     // horizontally filtered + saturated lines, TRANSPOSED: [x-phase][column][line], 16 lines (14 used) per column
     __shared__ __align__(4) uint8_t s_h[S2_BLOCKS][5][8][16];
     __shared__ uint32_t s_cur[S2_BLOCKS][8][2];
@@ -323,11 +342,26 @@ k_luma_search_2step(const uint8_t *__restrict__ cur, Search2Refs refs, int width
         bx = g.x; by = g.y; v0x = g.z; v0y = g.w;
     };
 
-    for (int i = tid; i < S2_BLOCKS * 14 * 14; i += S2_THREADS) {
-        const int b = i / 196, r = (i % 196) / 14, c = i % 14;
+    // one window line per thread: five aligned words cover its 14 pixels wherever they start; lines that
+    // touch the left/right frame edge (or an unaligned plane) take the clamped byte path
+    for (int i = tid; i < S2_BLOCKS * 14; i += S2_THREADS) {
+        const int b = i / 14, r = i % 14;
         const int4 g = s_geo[b];
-        const int x = clampi(g.x + (g.z >> 2) - 3 + c, 0, width - 1), y = clampi(g.y + (g.w >> 2) - 3 + r, 0, height - 1);
-        s_win[b][r][c] = __ldg(ref + (size_t)y * width + x);
+        const int x0 = g.x + (g.z >> 2) - 3, y = clampi(g.y + (g.w >> 2) - 3 + r, 0, height - 1);
+        const uint8_t *line = ref + (size_t)y * width;
+        const int xa = x0 & ~3;
+        if (x0 >= 0 && xa + 20 <= width && ((reinterpret_cast<uintptr_t>(ref) | (unsigned)width) & 3) == 0) {
+            const uint32_t *wp = reinterpret_cast<const uint32_t *>(line + xa);
+            const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2), w3 = __ldg(wp + 3), w4 = __ldg(wp + 4);
+            const int sh = 8 * (x0 & 3);
+            s_win[b][r][0] = __funnelshift_r(w0, w1, sh);
+            s_win[b][r][1] = __funnelshift_r(w1, w2, sh);
+            s_win[b][r][2] = __funnelshift_r(w2, w3, sh);
+            s_win[b][r][3] = __funnelshift_r(w3, w4, sh);
+        } else {
+            uint8_t *dst = reinterpret_cast<uint8_t *>(&s_win[b][r][0]);
+            for (int c = 0; c < 14; ++c) dst[c] = __ldg(line + clampi(x0 + c, 0, width - 1));
+        }
     }
     if (tid < S2_BLOCKS * 16) {
         const int b = tid >> 4, r = (tid >> 1) & 7, h = tid & 1;
@@ -346,7 +380,7 @@ k_luma_search_2step(const uint8_t *__restrict__ cur, Search2Refs refs, int width
         for (int c = 0; c < 4; ++c) {
             int s = 64;
 #pragma unroll
-            for (int t = 0; t < 6; ++t) s += (int)c_sixtap[ph][t] * (int)s_win[b][r][first + c + t];
+            for (int t = 0; t < 6; ++t) s += (int)c_sixtap[ph][t] * (int)reinterpret_cast<const uint8_t *>(&s_win[b][r][0])[first + c + t];
             // (s/128 then saturate) == saturate(s>>7): the two only differ for -128<s<0, both give 0
             s_h[b][var][4 * h + c][r] = (uint8_t)sat8(s >> 7);
         }
@@ -376,21 +410,26 @@ k_luma_search_2step(const uint8_t *__restrict__ cur, Search2Refs refs, int width
             }
             const int qx = (short)(bx * 4 + v0x + xi - 2);
             const bool xok = qx >= 0 && qx <= width * 4 - 32;
+            // y-phases 4,6,0,2,4 with first line 0,0,1,1,1 (s2_origin + 1).  The loop is kept rolled (the
+            // branches are warp-uniform): unrolled, the five bodies get interleaved and spill.
+#if VP8_S2_UNROLL
 #pragma unroll
+#else
+#pragma unroll 1
+#endif
             for (int yi = 0; yi < 5; ++yi) {
-                constexpr int kFirst[5] = {0, 0, 1, 1, 1};  // s2_origin(yi) + 1
-                if (yi == 0) s2_residual<4>(tl, kFirst[0], cu, r);
-                if (yi == 1) s2_residual<6>(tl, kFirst[1], cu, r);
-                if (yi == 2) {
+                if (yi < 2) {
+                    s2_residual(tl, 0, yi == 0 ? taps_lo(4) : taps_lo(6), yi == 0 ? taps_hi(4) : taps_hi(6), cu, r);
+                } else if (yi == 2) {
 #pragma unroll
                     for (int y = 0; y < 4; ++y)
 #pragma unroll
-                        for (int x = 0; x < 4; ++x)  // full-pel phase: line first+2+y itself
+                        for (int x = 0; x < 4; ++x)  // full-pel phase: line 1+2+y itself
                             r[4 * y + x] = (int)__byte_perm(cu[y], 0, 0x4440 + x) -
-                                           (int)__byte_perm(tl[x][(kFirst[2] + 2 + y) >> 2], 0, 0x4440 + ((kFirst[2] + 2 + y) & 3));
+                                           (int)__byte_perm(tl[x][(3 + y) >> 2], 0, 0x4440 + ((3 + y) & 3));
+                } else {
+                    s2_residual(tl, 1, yi == 3 ? taps_lo(2) : taps_lo(4), yi == 3 ? taps_hi(2) : taps_hi(4), cu, r);
                 }
-                if (yi == 3) s2_residual<2>(tl, kFirst[3], cu, r);
-                if (yi == 4) s2_residual<4>(tl, kFirst[4], cu, r);
                 int cost = weight4x4(r);
                 cost += __shfl_xor_sync(0xffffffffu, cost, 1);
                 cost += __shfl_xor_sync(0xffffffffu, cost, 2);
