@@ -105,9 +105,11 @@ __device__ __forceinline__ int weight4x4_biased(const int (&r)[16]) {
 __global__ void __launch_bounds__(S1_THREADS, VP8_S1_MINCTAS)
 k_luma_search_1step(const uint8_t *__restrict__ cur, Search1Refs refs, int net_width, int width, int height, int rate,
                     int nblocks) {
-    const uint8_t *__restrict__ prev = refs.prev[blockIdx.y];
-    const short2 *__restrict__ src_net = refs.src_net[blockIdx.y];
-    short2 *__restrict__ dst_net = refs.dst_net[blockIdx.y];
+    // (selects, not refs.x[blockIdx.y]: indexing a kernel parameter dynamically copies it to local memory)
+    const int ri = blockIdx.y;
+    const uint8_t *__restrict__ prev = ri == 0 ? refs.prev[0] : ri == 1 ? refs.prev[1] : refs.prev[2];
+    const short2 *__restrict__ src_net = ri == 0 ? refs.src_net[0] : ri == 1 ? refs.src_net[1] : refs.src_net[2];
+    short2 *__restrict__ dst_net = ri == 0 ? refs.dst_net[0] : ri == 1 ? refs.dst_net[1] : refs.dst_net[2];
     __shared__ uint32_t s_win[S1_BLOCKS][12][4];   // prev pixels [c+v0-2, c+v0+10) in both axes, 16-byte lines
     __shared__ uint32_t s_cur[S1_BLOCKS][8][2];
     __shared__ int4 s_geo[S1_BLOCKS];              // cx, cy, vx, vy
@@ -257,7 +259,7 @@ k_luma_search_1step(const uint8_t *__restrict__ cur, Search1Refs refs, int net_w
 #define VP8_S2_BLOCKS 8
 #endif
 #ifndef VP8_S2_MINCTAS
-#define VP8_S2_MINCTAS 5
+#define VP8_S2_MINCTAS 4
 #endif
 #ifndef VP8_S2_UNROLL
 #define VP8_S2_UNROLL 1
@@ -313,10 +315,11 @@ __device__ __forceinline__ void s2_residual(const uint32_t (&tl)[4][3], int firs
 
 __global__ void __launch_bounds__(S2_THREADS, VP8_S2_MINCTAS)
 k_luma_search_2step(const uint8_t *__restrict__ cur, Search2Refs refs, int width, int height, int nblocks) {
-    const uint8_t *__restrict__ ref = refs.ref[blockIdx.y];
-    const short2 *__restrict__ net = refs.net[blockIdx.y];
-    short2 *__restrict__ ref_net = refs.ref_net[blockIdx.y];
-    int *__restrict__ ref_Bdiff = refs.ref_Bdiff[blockIdx.y];
+    const int ri = blockIdx.y;
+    const uint8_t *__restrict__ ref = ri == 0 ? refs.ref[0] : ri == 1 ? refs.ref[1] : refs.ref[2];
+    const short2 *__restrict__ net = ri == 0 ? refs.net[0] : ri == 1 ? refs.net[1] : refs.net[2];
+    short2 *__restrict__ ref_net = ri == 0 ? refs.ref_net[0] : ri == 1 ? refs.ref_net[1] : refs.ref_net[2];
+    int *__restrict__ ref_Bdiff = ri == 0 ? refs.ref_Bdiff[0] : ri == 1 ? refs.ref_Bdiff[1] : refs.ref_Bdiff[2];
     __shared__ uint32_t s_win[S2_BLOCKS][14][5];   // ref pixels rows/cols [base-3, base+11), clamp-to-edge; 20-byte lines
     // horizontally filtered + saturated lines, TRANSPOSED: [x-phase][column][line], 16 lines (14 used) per column
     __shared__ __align__(4) uint8_t s_h[S2_BLOCKS][5][8][16];
