@@ -318,12 +318,26 @@ def b200_arm(args, rank, world, local_rank, tmp, config):
                 b.record(ext_stream)
         torch.cuda.synchronize()
         ms = sum(a.elapsed_time(b) for a, b in evs) / reps
-        ops = 1381.0 * N  # algorithmic int-ops of the quarter-pel level per reference
+        # Per-unit figure: thread-instructions this kernel executes per luma pixel per reference, from the ncu
+        # capture committed under profiles/ (tools/ncu_summary.py units).  The reference's scalar formulation is
+        # 1381 int-ops per pixel; the kernel needs fewer (dp4a six-tap, packed lanes, shared loads),
+        # so counting 1381 against the issue peak would overstate the fraction.
+        units = {}
+        try:
+            units = json.load(open(os.path.join(ROOT, "profiles", "r01_roofline_units.json")))
+        except Exception:
+            pass
+        per_px = float(units.get("thread_instr_per_pixel_per_ref", 1381.0))
+        ops = per_px * N
         roofline = {"kernel": "luma_search_2step", "bound": "int_alu", "achieved": ops / (ms * 1e-3) / 1e12,
                     "peak": int_peak / 1e12, "unit": "Tiop/s", "frac": (ops / (ms * 1e-3)) / int_peak,
-                    "traffic": None, "ms_per_launch": ms,
-                    "note": "algorithmic = 1381 int-ops per luma pixel per reference (SURVEY 8d); peak = measured "
-                            "IMAD:add/logic 1:2 issue rate of this device (vp8b200_measure_int_ops_per_second)"}
+                    "traffic": units.get("dram_bytes_per_ref"), "ms_per_launch": ms,
+                    "ops_per_pixel": per_px, "reference_ops_per_pixel": 1381.0,
+                    "reference_formulation_tiops": 1381.0 * N / (ms * 1e-3) / 1e12,
+                    "note": "int-ALU issue roofline: achieved = executed thread-instructions per pixel (ncu, "
+                            "profiles/r01_roofline_units.json) x pixels / live CUDA-event time of one launch for one "
+                            "reference; peak = measured IMAD:add/logic 1:2 issue rate of this device "
+                            "(vp8b200_measure_int_ops_per_second); traffic = ncu DRAM bytes per reference-launch"}
         # loop filter: HBM line (3N bytes read + written once each -> 3N algorithmic bytes per SURVEY 8d)
         peaks = {}
         try:

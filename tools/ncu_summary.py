@@ -56,5 +56,31 @@ def full(path):
                 print("    %-82s %14s %s" % (m, r[h.index(m)], units[h.index(m)]))
 
 
+def units(path, out_json=None):
+    """per-unit figures of the dominant kernel for bench.py's roofline: executed thread-instructions per luma
+    pixel per reference and DRAM bytes per launch of luma_search_2step (1080p, averaged over the captures)"""
+    import json
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    h, un = rows[0], rows[1]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    inst, dram, launches_, refs = 0.0, 0.0, 0, 0
+    for r in rows[2:]:
+        if "k_luma_search_2step" not in r[h.index("Kernel Name")]:
+            continue
+        g = [int(x) for x in r[h.index("Grid Size")].strip("() ").split(",")]
+        inst += float(r[h.index("smsp__inst_executed.sum")])
+        for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            dram += float(r[h.index(m)]) * scale.get(un[h.index(m)], 1.0)
+        launches_ += 1
+        refs += g[1]
+    res = {"kernel": "luma_search_2step", "captures": launches_, "reference_launch_units": refs,
+           "thread_instr_per_pixel_per_ref": inst * 32 / refs / (1920 * 1088),
+           "dram_bytes_per_ref": dram / refs, "source": path.split("/")[-1]}
+    print(json.dumps(res, indent=1))
+    if out_json:
+        json.dump(res, open(out_json, "w"), indent=1)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "units": units}[sys.argv[1]](*sys.argv[2:])

@@ -55,32 +55,49 @@ __device__ __forceinline__ int sat8(int v) { return min(max(v, 0), 255); }
 // Pass 1 runs down the columns with the reference's register clobber (Q1): the "b1" term is
 // overwritten by c1 and the odd outputs use the RAW third row in place of c1.  Pass 2 is the
 // regular VP8 second pass along the rows.  Result = |DC|/4 + sum of the other magnitudes.
-__device__ __forceinline__ int weight4x4(const int (&r)[16]) {
+//
+// The reference scales the pass-1 sums by 8 ((r0+r3)<<3 ...).  Here the factor is folded into what
+// follows, which is exact: d1*5352 = (r0-r3)*42816, d1*2217 = (r0-r3)*17736; rows 0 and 2 of the
+// intermediate are 8*p with p = (r0+r3) +- (r1-r2), and for them (8m+7)>>4 == m>>1 for every
+// integer m, (8c*2217 + 8d*5352 + k)>>16 == (c*17736 + d*42816 + k)>>16, (8d != 0) == (d != 0).
+// BIAS = 0: plain residual.  BIAS = 256: every r[i] carries +256 (16-bit lane arithmetic of
+// luma_search_1step); the bias cancels in all differences, adds 512 to p (1024 to the row sums, an
+// even number, so it comes out of (A+B)>>1 exactly as 1024) and is taken out of the two pass-1
+// products' constants.
+template <int BIAS>
+__device__ __forceinline__ int weight4x4_t(const int (&r)[16]) {
     int o[16];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const int a1 = (r[k] + r[12 + k]) << 3;
-        const int d1 = (r[k] - r[12 + k]) << 3;
-        const int c1 = (r[4 + k] - r[8 + k]) << 3;
+        const int s = r[k] + r[12 + k], t = r[k] - r[12 + k], u = r[4 + k] - r[8 + k];
         const int x = r[8 + k];
-        o[k] = a1 + c1;
-        o[8 + k] = a1 - c1;
-        o[4 + k] = (x * 2217 + d1 * 5352 + 14500) >> 12;
-        o[12 + k] = (d1 * 2217 - x * 5352 + 7500) >> 12;
+        o[k] = s + u;      // = reference value / 8 (+ 2*BIAS)
+        o[8 + k] = s - u;  // = reference value / 8 (+ 2*BIAS)
+        o[4 + k] = (x * 2217 + t * 42816 + (14500 - BIAS * 2217)) >> 12;
+        o[12 + k] = (t * 17736 - x * 5352 + (7500 + BIAS * 5352)) >> 12;
     }
     int sum = 0;
 #pragma unroll
     for (int row = 0; row < 4; ++row) {
         const int a = o[4 * row] + o[4 * row + 3], d = o[4 * row] - o[4 * row + 3];
         const int b = o[4 * row + 1] + o[4 * row + 2], c = o[4 * row + 1] - o[4 * row + 2];
-        const int f0 = (a + b + 7) >> 4;
-        const int f2 = (a - b + 7) >> 4;
-        const int f1 = ((c * 2217 + d * 5352 + 12000) >> 16) + (d != 0);
-        const int f3 = (d * 2217 - c * 5352 + 51000) >> 16;
+        int f0, f1, f2, f3;
+        if (row & 1) {
+            f0 = (a + b + 7) >> 4;
+            f2 = (a - b + 7) >> 4;
+            f1 = ((c * 2217 + d * 5352 + 12000) >> 16) + (d != 0);
+            f3 = (d * 2217 - c * 5352 + 51000) >> 16;
+        } else {  // a, b, c, d are the reference's values / 8 (a, b carry + 4*BIAS each)
+            f0 = ((a + b) >> 1) - 4 * BIAS;
+            f2 = (a - b) >> 1;
+            f1 = ((c * 17736 + d * 42816 + 12000) >> 16) + (d != 0);
+            f3 = (d * 17736 - c * 42816 + 51000) >> 16;
+        }
         sum += (row == 0 ? (abs(f0) >> 2) : abs(f0)) + abs(f1) + abs(f2) + abs(f3);
     }
     return sum;
 }
+__device__ __forceinline__ int weight4x4(const int (&r)[16]) { return weight4x4_t<0>(r); }
 
 // quantisers of one segment, derived exactly as the device code of the reference does it
 // in three places (Q11; src/GPU_kernels.cl:1394-1408, 1515-1524, 1568-1582)

@@ -48,7 +48,7 @@ __global__ void k_downsample_x2(const uint8_t *__restrict__ src, uint8_t *__rest
 // candidates cover are two aligned words held in registers; a candidate's four pixels are a funnel
 // shift away.  Residuals are formed two at a time in 16-bit lanes with a +256 bias per lane (no
 // borrow between lanes), and the bias is folded into the constants of the cost transform
-// (weight4x4_biased), so unpacking costs one AND / one shift per pixel.
+// (weight4x4_t<256>), so unpacking costs one AND / one shift per pixel.
 #ifndef VP8_S1_BLOCKS
 #define VP8_S1_BLOCKS 8
 #endif
@@ -71,36 +71,6 @@ struct Search2Refs {
     short2 *ref_net[3];
     int *ref_Bdiff[3];
 };
-
-// weight4x4 of a residual whose 16 entries all carry a +256 bias.  Pass 1: the bias cancels in the
-// differences, becomes +4096 in rows 0 and 2 and is taken out of the two products' constants; pass 2:
-// rows 0 and 2 carry +8192 in both sums, which only the DC-like term sees.  Exact integer identities.
-__device__ __forceinline__ int weight4x4_biased(const int (&r)[16]) {
-    int o[16];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int a1 = (r[k] + r[12 + k]) << 3;
-        const int d1 = (r[k] - r[12 + k]) << 3;
-        const int c1 = (r[4 + k] - r[8 + k]) << 3;
-        const int x = r[8 + k];
-        o[k] = a1 + c1;
-        o[8 + k] = a1 - c1;
-        o[4 + k] = (x * 2217 + d1 * 5352 + (14500 - 256 * 2217)) >> 12;
-        o[12 + k] = (d1 * 2217 - x * 5352 + (7500 + 256 * 5352)) >> 12;
-    }
-    int sum = 0;
-#pragma unroll
-    for (int row = 0; row < 4; ++row) {
-        const int a = o[4 * row] + o[4 * row + 3], d = o[4 * row] - o[4 * row + 3];
-        const int b = o[4 * row + 1] + o[4 * row + 2], c = o[4 * row + 1] - o[4 * row + 2];
-        const int f0 = (a + b + ((row & 1) ? 7 : 7 - 16384)) >> 4;
-        const int f2 = (a - b + 7) >> 4;
-        const int f1 = ((c * 2217 + d * 5352 + 12000) >> 16) + (d != 0);
-        const int f3 = (d * 2217 - c * 5352 + 51000) >> 16;
-        sum += (row == 0 ? (abs(f0) >> 2) : abs(f0)) + abs(f1) + abs(f2) + abs(f3);
-    }
-    return sum;
-}
 
 __global__ void __launch_bounds__(S1_THREADS, VP8_S1_MINCTAS)
 k_luma_search_1step(const uint8_t *__restrict__ cur, Search1Refs refs, int net_width, int width, int height, int rate,
@@ -206,7 +176,7 @@ k_luma_search_1step(const uint8_t *__restrict__ cur, Search1Refs refs, int net_w
                 r[4 * y + 2] = (int)(dhi & 0xffffu);
                 r[4 * y + 3] = (int)(dhi >> 16);
             }
-            int cost = weight4x4_biased(r);
+            int cost = weight4x4_t<256>(r);  // see common.cuh for the bias algebra
             cost += __shfl_xor_sync(0xffffffffu, cost, 1);
             cost += __shfl_xor_sync(0xffffffffu, cost, 2);
             const int px = (short)(cx + vx + dx - 2);
