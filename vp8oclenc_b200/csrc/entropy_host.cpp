@@ -101,17 +101,50 @@ inline int walk_block(const int16_t *coef, int type, int ctx, unsigned mask, Sin
             ctx = 0;
             continue;
         }
+        // the token tree of RFC 6386 13.2 written out (same decisions as kPath, no per-token loop)
         const int mag = v < 0 ? -v : v;
-        const Token t = classify(mag);
-        const Path &p = kPath[t];
-        for (int k = prev_zero ? 1 : 0; k < p.n; ++k) sink.decision(ctx_index(type, band, ctx, p.slot[k]), p.bit[k]);
-        if (t >= T_CAT1) {
-            const int c = t - T_CAT1, extra = mag - kCatBase[c];
-            for (int b = 0; b < kCatBits[c]; ++b) sink.literal(kCatProb[c][b], (extra >> (kCatBits[c] - 1 - b)) & 1);
+        const int base = ctx_index(type, band, ctx, 0);
+        if (!prev_zero) sink.decision(base, 1);  // not end-of-block
+        sink.decision(base + 1, 1);              // not ZERO
+        if (mag == 1) {
+            sink.decision(base + 2, 0);
+            ctx = 1;
+        } else {
+            sink.decision(base + 2, 1);
+            if (mag <= 4) {
+                sink.decision(base + 3, 0);
+                if (mag == 2) {
+                    sink.decision(base + 4, 0);
+                } else {
+                    sink.decision(base + 4, 1);
+                    sink.decision(base + 5, mag == 4);
+                }
+            } else {
+                sink.decision(base + 3, 1);
+                int c;  // value category
+                if (mag <= 10) {
+                    sink.decision(base + 6, 0);
+                    sink.decision(base + 7, mag > 6);
+                    c = mag > 6;
+                } else {
+                    sink.decision(base + 6, 1);
+                    if (mag <= 34) {
+                        sink.decision(base + 8, 0);
+                        sink.decision(base + 9, mag > 18);
+                        c = 2 + (mag > 18);
+                    } else {
+                        sink.decision(base + 8, 1);
+                        sink.decision(base + 10, mag > 66);
+                        c = 4 + (mag > 66);
+                    }
+                }
+                const int extra = mag - kCatBase[c];
+                for (int b = 0; b < kCatBits[c]; ++b) sink.literal(kCatProb[c][b], (extra >> (kCatBits[c] - 1 - b)) & 1);
+            }
+            ctx = 2;
         }
         sink.literal(128, v < 0);  // sign
         prev_zero = false;
-        ctx = (t == T_ONE) ? 1 : 2;
     }
     if (i < 16) sink.decision(ctx_index(type, kBand[i], ctx, 0), 0);  // end of block (never right after a ZERO)
     return i;
@@ -140,13 +173,10 @@ struct BoolSink {
         const uint32_t split = 1 + (((range - 1) * (uint32_t)prob) >> 8);
         const uint32_t r = bit ? range - split : split;
         bottom += bit ? split : 0u;
-        if (r >= 128) {
-            range = r;
-            return;
-        }
         // The RFC renormalises bit by bit: before each of the s shifts a set top bit of `bottom` is a
         // carry into the bytes already written, and every time bit_count reaches 0 a byte leaves.
-        // Same thing in at most two strides (s <= 7, so at most one byte leaves).
+        // Same thing in at most two strides (s <= 7, so at most one byte leaves); s == 0 falls
+        // through the first stride as a no-op, so there is no "needs renormalisation" branch.
         int s = __builtin_clz(r) - 24;
         range = r << s;
         if (s >= bit_count) {
@@ -158,10 +188,10 @@ struct BoolSink {
             bottom &= (1u << 24) - 1;
             bit_count = 8;
             s -= c;
-            if (s == 0) return;
         }
-        for (uint32_t t = bottom >> (32 - s); t; t &= t - 1) carry(out);
-        bottom <<= s;
+        const uint64_t wide = (uint64_t)bottom << s;
+        for (uint32_t t = (uint32_t)(wide >> 32); t; t &= t - 1) carry(out);
+        bottom = (uint32_t)wide;
         bit_count -= s;
     }
     inline void decision(int idx, int bit) { put((uint8_t)probs[idx], bit); }
