@@ -430,7 +430,7 @@ def b200_arm(args, rank, world, local_rank, tmp, config):
                 daemon.active = os.path.exists(os.path.join(daemon.pipe, "control"))
             cores = os.cpu_count() or 2
             if daemon.active:
-                P = args.e2e_procs or max(1, min(16, cores // world))
+                P = args.e2e_procs or max(1, min(24, (3 * cores) // (2 * world)))
             else:
                 P = args.e2e_procs or max(1, min(8, cores // max(2, 2 * world)))
             try:

@@ -25,7 +25,10 @@
 //    match exactly runs kernel by kernel.  VP8B200_FUSED=0 turns the replacement off.
 #include <CL/cl.h>
 #include <cuda_runtime.h>
+#include <signal.h>
+#include <sys/mman.h>
 #include <sys/resource.h>
+#include <unistd.h>
 #include <time.h>
 
 #include <cstdio>
@@ -52,6 +55,14 @@ struct _cl_mem {
     void *host;          // pinned mirror (lazily)
     bool dev_valid, host_valid;
     bool mapped_for_write;
+    // transfer elision (see "transfer elision" below)
+    unsigned long dev_version;   // bumped whenever the device copy may change
+    bool dev_matches_mirror;     // while mapped for writing: the (formally stale) device copy still equals the mirror
+    _cl_mem *twin;               // the whole mirror was last filled by a read of twin's device copy ...
+    unsigned long twin_version;  // ... at this version of it
+    size_t host_bytes;           // size of the mirror's mapping (whole pages)
+    volatile bool guarded;       // mirror is write-protected: a host store faults and sets host_dirty
+    volatile bool host_dirty;    // the host has stored into the mirror since the guard was set
 };
 
 enum KernelId {
@@ -95,7 +106,7 @@ static int g_sm_count = 0;
 static unsigned g_next_index = 0;
 static FILE *g_trace = nullptr;
 // statistics, written as JSON to $VP8B200_STATS at exit (bench.py reads them)
-static unsigned long long g_h2d_bytes = 0, g_d2h_bytes = 0, g_kernel_launches = 0, g_host_kernels = 0;
+static unsigned long long g_h2d_bytes = 0, g_d2h_bytes = 0, g_kernel_launches = 0, g_host_kernels = 0, g_elided_bytes = 0;
 // wall-clock time the calling thread spent inside the entry points, by kind
 enum TimedKind { T_LAUNCH, T_HOST_KERNEL, T_READ, T_WRITE, T_MAP, T_FINISH, T_KINDS };
 static const char *const kTimedNames[T_KINDS] = {"launch", "host_kernel", "read", "write", "map", "finish"};
@@ -115,8 +126,8 @@ static void write_stats() {
     const char *p = getenv("VP8B200_STATS");
     if (!p || !*p) return;
     if (FILE *f = fopen(p, "w")) {
-        fprintf(f, "{\"h2d_bytes\": %llu, \"d2h_bytes\": %llu, \"kernel_launches\": %llu, \"host_kernels\": %llu",
-                g_h2d_bytes, g_d2h_bytes, g_kernel_launches, g_host_kernels);
+        fprintf(f, "{\"h2d_bytes\": %llu, \"d2h_bytes\": %llu, \"elided_bytes\": %llu, \"kernel_launches\": %llu, \"host_kernels\": %llu",
+                g_h2d_bytes, g_d2h_bytes, g_elided_bytes, g_kernel_launches, g_host_kernels);
         for (int i = 0; i < T_KINDS; ++i) fprintf(f, ", \"ms_%s\": %.3f", kTimedNames[i], g_ns[i] * 1e-6);
         rusage ru;
         getrusage(RUSAGE_SELF, &ru);  // all threads of the encoder instance
@@ -127,11 +138,15 @@ static void write_stats() {
     }
 }
 
+static int g_elide = 2;                // transfer elision: 0 off, 1 assume, 2 track (see "transfer elision" below)
+static std::vector<cl_mem> g_mirrors;  // objects that own a pinned mirror
 static std::vector<Cmd> g_cmds;  // the deferred command list
 static bool g_fuse = true;       // VP8B200_FUSED=0: execute the list kernel by kernel
 
 static int g_sync_sleep_us = 0;  // VP8B200_SYNC=sleep<us>
 static cudaEvent_t g_sync_event = nullptr;
+
+static void install_guard_handler();
 
 static bool cuda_init() {
     if (g_cuda_tried) return g_cuda_ok;
@@ -153,6 +168,8 @@ static bool cuda_init() {
     if (cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking) != cudaSuccess) return false;
     vp8b200_device_info(g_dev_name, sizeof(g_dev_name), &g_sm_count, nullptr, nullptr);
     if (const char *f = getenv("VP8B200_FUSED")) g_fuse = f[0] != '0';
+    if (const char *f = getenv("VP8B200_ELIDE")) g_elide = !strcmp(f, "assume") ? 1 : (!strcmp(f, "track") ? 2 : 0);
+    if (g_elide == 2) install_guard_handler();
     const char *tr = getenv("VP8CL_TRACE");
     if (tr && *tr) g_trace = fopen(tr, "wb");
     atexit(write_stats);
@@ -198,22 +215,137 @@ static cl_int put_info(const void *src, size_t n, size_t cap, void *dst, size_t 
 
 static inline cl_int cuda_rc(cudaError_t e) { return e == cudaSuccess ? CL_SUCCESS : CL_OUT_OF_RESOURCES; }
 
+// ---- dirty tracking of the pinned mirrors (transfer elision, mode "track") -------------------------
+// A mirror whose bytes are known to equal a device copy is write-protected.  The first store of the
+// host into it faults; the handler lifts the protection, marks the mirror dirty and lets the store
+// retry.  Reads (the host forwarding the buffer, the entropy threads, DMA in either direction) never
+// fault.  Limitation: a system call that WRITES into a mirror (read(2) straight into a mapped buffer)
+// would fail with EFAULT instead of faulting; the reference host never does that (it stores into
+// these buffers from its intra path only, src/intra_part.h:517-741).
+struct GuardSlot { char *base; size_t bytes; _cl_mem *mem; };
+constexpr int kMaxGuardSlots = 64;
+static GuardSlot g_guard_slots[kMaxGuardSlots];
+static int g_num_guard_slots = 0;
+static struct sigaction g_prev_segv;
+
+static void guard_fault(int sig, siginfo_t *info, void *uctx) {
+    char *addr = (char *)info->si_addr;
+    const int n = __atomic_load_n(&g_num_guard_slots, __ATOMIC_ACQUIRE);
+    for (int i = 0; i < n; ++i) {
+        GuardSlot &g = g_guard_slots[i];
+        if (g.mem && addr >= g.base && addr < g.base + g.bytes && g.mem->guarded) {
+            g.mem->host_dirty = true;
+            g.mem->guarded = false;
+            mprotect(g.base, g.bytes, PROT_READ | PROT_WRITE);
+            return;  // the faulting store is retried
+        }
+    }
+    // not ours: hand over to whoever was there before (default action: re-raise)
+    if (g_prev_segv.sa_flags & SA_SIGINFO) {
+        if (g_prev_segv.sa_sigaction) return g_prev_segv.sa_sigaction(sig, info, uctx);
+    } else if (g_prev_segv.sa_handler != SIG_DFL && g_prev_segv.sa_handler != SIG_IGN) {
+        return g_prev_segv.sa_handler(sig);
+    }
+    signal(SIGSEGV, SIG_DFL);
+    raise(SIGSEGV);
+}
+static void install_guard_handler() {
+    struct sigaction sa;
+    memset(&sa, 0, sizeof(sa));
+    sa.sa_sigaction = guard_fault;
+    sa.sa_flags = SA_SIGINFO | SA_NODEFER;
+    sigemptyset(&sa.sa_mask);
+    sigaction(SIGSEGV, &sa, &g_prev_segv);
+}
+// the mirror's bytes equal a device copy from now on: watch for host stores
+static void guard(_cl_mem *m) {
+    m->host_dirty = false;
+    if (g_elide != 2 || !m->host || m->guarded) return;
+    m->guarded = true;
+    mprotect(m->host, m->host_bytes, PROT_READ);
+}
+static void unguard(_cl_mem *m) {
+    if (!m->guarded) return;
+    m->guarded = false;
+    mprotect(m->host, m->host_bytes, PROT_READ | PROT_WRITE);
+}
+
 // ---- buffer coherence ---------------------------------------------------------------------
 static bool ensure_host_alloc(cl_mem m) {
     if (m->host) return true;
-    if (cudaHostAlloc(&m->host, m->size ? m->size : 1, cudaHostAllocDefault) != cudaSuccess) return false;
+    // our own pages (so that they can be write-protected for dirty tracking), pinned for DMA
+    const size_t page = (size_t)sysconf(_SC_PAGESIZE);
+    m->host_bytes = ((m->size ? m->size : 1) + page - 1) / page * page;
+    void *p = mmap(nullptr, m->host_bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (p == MAP_FAILED) return false;
+    if (cudaHostRegister(p, m->host_bytes, cudaHostRegisterDefault) != cudaSuccess) {
+        munmap(p, m->host_bytes);
+        return false;
+    }
+    m->host = p;
     m->host_valid = false;
+    g_mirrors.push_back(m);
+    if (g_num_guard_slots < kMaxGuardSlots) {
+        g_guard_slots[g_num_guard_slots].base = (char *)p;
+        g_guard_slots[g_num_guard_slots].bytes = m->host_bytes;
+        g_guard_slots[g_num_guard_slots].mem = m;
+        __atomic_store_n(&g_num_guard_slots, g_num_guard_slots + 1, __ATOMIC_RELEASE);
+    }
     return true;
 }
+// ---- transfer elision ------------------------------------------------------------
+// The host moves the same pixels and coefficients over the boundary several times per frame: it
+// reads the reconstruction into a mapped buffer and unmaps it (upload), maps the loop-filtered
+// frame (download) and writes it straight back into two other device objects (uploads), reads the
+// coefficients into a mapped buffer and unmaps it (upload).  Whenever the bytes in a pinned mirror
+// are known to equal a device copy, the upload is replaced by a device-to-device copy:
+//   * a mirror that was completely filled by clEnqueueReadBuffer(X) equals X's device copy for as
+//     long as X is not written ("twin");
+//   * a mirror that was brought up to date by clEnqueueMapBuffer equals its own device copy.
+// Both hold only while the HOST has not stored into the mirror, which is tracked by write-protecting
+// the mirror (VP8B200_ELIDE=track, the default; see "dirty tracking" above).  VP8B200_ELIDE=assume
+// takes it for granted, VP8B200_ELIDE=off uploads everything as the host asks.
+
+static cl_mem mirror_of(const void *ptr, size_t size, size_t *off) {
+    for (cl_mem m : g_mirrors) {
+        const char *b = (const char *)m->host;
+        if ((const char *)ptr >= b && (const char *)ptr + size <= b + m->size) {
+            *off = (size_t)((const char *)ptr - b);
+            return m;
+        }
+    }
+    return nullptr;
+}
+// device address that currently holds the same bytes as mirror range [off, off+size) of m, or null
+static const void *device_twin_of_mirror(cl_mem m, size_t off) {
+    if (!g_elide || m->host_dirty) return nullptr;
+    if (m->twin && m->twin->dev_valid && m->twin->dev_version == m->twin_version) return (const char *)m->twin->dev + off;
+    if (m->dev_valid || m->dev_matches_mirror) return (const char *)m->dev + off;
+    return nullptr;
+}
+
 // device copy up to date (uploads a host-side modification on the stream)
 static void *dev_ptr(cl_mem m, bool will_write) {
     if (!m) return nullptr;
     if (!m->dev_valid) {
-        cudaMemcpyAsync(m->dev, m->host, m->size, cudaMemcpyHostToDevice, g_stream);
-        g_h2d_bytes += m->size;
+        const void *src = (m->twin || m->dev_matches_mirror) ? device_twin_of_mirror(m, 0) : nullptr;
+        if (src == m->dev) {
+            g_elided_bytes += m->size;  // nothing to do: the device copy never stopped being right
+        } else if (src) {
+            cudaMemcpyAsync(m->dev, src, m->size, cudaMemcpyDeviceToDevice, g_stream);
+            g_elided_bytes += m->size;
+        } else {
+            cudaMemcpyAsync(m->dev, m->host, m->size, cudaMemcpyHostToDevice, g_stream);
+            g_h2d_bytes += m->size;
+        }
         m->dev_valid = true;
+        ++m->dev_version;
     }
-    if (will_write) m->host_valid = false;
+    if (will_write) {
+        m->host_valid = false;
+        m->dev_matches_mirror = false;
+        ++m->dev_version;
+    }
     return m->dev;
 }
 // host mirror up to date (downloads and waits)
@@ -228,7 +360,12 @@ static void *host_ptr(cl_mem m, bool will_write, bool discard = false) {
         }
         m->host_valid = true;
     }
-    if (will_write) m->dev_valid = false;
+    if (will_write) {  // (a host-executed kernel is about to store into the mirror)
+        m->dev_valid = false;
+        m->dev_matches_mirror = false;
+        m->twin = nullptr;
+        unguard(m);
+    }
     return m->host;
 }
 
@@ -668,6 +805,13 @@ static cl_mem new_mem(size_t size, bool image, int w, int h, bool want_host, cl_
     m->height = h;
     m->host = nullptr;
     m->mapped_for_write = false;
+    m->dev_version = 0;
+    m->dev_matches_mirror = false;
+    m->twin = nullptr;
+    m->twin_version = 0;
+    m->host_bytes = 0;
+    m->guarded = false;
+    m->host_dirty = false;
     // zero-filled like the reference runtime's calloc: block 24 of never-16x16 macroblocks and the
     // nets of never-searched blocks are read before they are first written (Q4, Q9)
     cudaError_t e = cudaMalloc(&m->dev, size ? size : 1);
@@ -704,7 +848,17 @@ cl_int clReleaseMemObject(cl_mem m) {
     flush_pending();
     stream_sync();
     cudaFree(m->dev);
-    if (m->host) cudaFreeHost(m->host);
+    if (m->host) {
+        for (int i = 0; i < g_num_guard_slots; ++i)
+            if (g_guard_slots[i].mem == m) g_guard_slots[i].mem = nullptr;
+        if (m->guarded) mprotect(m->host, m->host_bytes, PROT_READ | PROT_WRITE);
+        cudaHostUnregister(m->host);
+        munmap(m->host, m->host_bytes);
+    }
+    for (size_t i = 0; i < g_mirrors.size(); ++i)
+        if (g_mirrors[i] == m) g_mirrors.erase(g_mirrors.begin() + i--);
+    for (cl_mem o : g_mirrors)
+        if (o->twin == m) o->twin = nullptr;
     delete m;
     return CL_SUCCESS;
 }
@@ -763,6 +917,20 @@ cl_int clEnqueueReadBuffer(cl_command_queue, cl_mem m, cl_bool blocking, size_t 
     if (!m || off + size > m->size) return CL_INVALID_VALUE;
     ScopedTimer timer(T_READ);
     flush_pending();
+    {   // the destination may be (part of) a pinned mirror: remember / forget what it equals
+        size_t moff = 0;
+        if (cl_mem t = mirror_of(ptr, size, &moff)) {
+            t->dev_matches_mirror = false;
+            if (m->dev_valid && moff == 0 && off == 0 && size == t->size && size == m->size && t != m) {
+                t->twin = m;
+                t->twin_version = m->dev_version;
+                guard(t);  // (the copy below is DMA: page protection does not concern it)
+            } else {
+                t->twin = nullptr;
+                unguard(t);
+            }
+        }
+    }
     if (m->dev_valid) {
         cudaError_t e = cudaMemcpyAsync(ptr, (char *)m->dev + off, size, cudaMemcpyDeviceToHost, g_stream);
         g_d2h_bytes += size;
@@ -782,9 +950,13 @@ cl_int clEnqueueWriteBuffer(cl_command_queue, cl_mem m, cl_bool blocking, size_t
     flush_pending();
     trace_rec(2, m->index, off, size, ptr);
     if (m->host && ptr == (char *)m->host + off) {
-        // the host writes a mapped buffer onto itself (intra_transform(), src/intra_part.h:1122-1124)
+        // the host writes a mapped buffer onto itself (intra_transform(), src/intra_part.h:1122-1124):
+        // it has produced new contents there
         m->host_valid = true;
         m->dev_valid = false;
+        m->dev_matches_mirror = false;
+        m->twin = nullptr;
+        unguard(m);
         return CL_SUCCESS;
     }
     if (!m->dev_valid) {
@@ -797,9 +969,20 @@ cl_int clEnqueueWriteBuffer(cl_command_queue, cl_mem m, cl_bool blocking, size_t
             return CL_SUCCESS;
         }
     }
-    cudaError_t e = cudaMemcpyAsync((char *)m->dev + off, ptr, size, cudaMemcpyHostToDevice, g_stream);
-    g_h2d_bytes += size;
+    cudaError_t e;
+    size_t moff = 0;
+    cl_mem srcm = g_elide ? mirror_of(ptr, size, &moff) : nullptr;
+    const void *dsrc = srcm ? device_twin_of_mirror(srcm, moff) : nullptr;
+    if (dsrc) {  // the bytes are on the device already
+        e = cudaMemcpyAsync((char *)m->dev + off, dsrc, size, cudaMemcpyDeviceToDevice, g_stream);
+        g_elided_bytes += size;
+    } else {
+        e = cudaMemcpyAsync((char *)m->dev + off, ptr, size, cudaMemcpyHostToDevice, g_stream);
+        g_h2d_bytes += size;
+    }
     m->host_valid = false;
+    m->dev_matches_mirror = false;
+    ++m->dev_version;
     if (blocking) stream_sync();
     return cuda_rc(e);
 }
@@ -824,8 +1007,17 @@ cl_int clEnqueueWriteImage(cl_command_queue, cl_mem img, cl_bool blocking, const
     flush_pending();
     const size_t pitch = row_pitch ? row_pitch : region[0];
     char *dst = (char *)dev_ptr(img, true) + origin[1] * img->width + origin[0];
-    cudaError_t e = cudaMemcpy2DAsync(dst, img->width, ptr, pitch, region[0], region[1], cudaMemcpyHostToDevice, g_stream);
-    g_h2d_bytes += region[0] * region[1];
+    cudaError_t e;
+    size_t moff = 0;
+    cl_mem srcm = g_elide ? mirror_of(ptr, pitch * (region[1] - 1) + region[0], &moff) : nullptr;
+    const void *dsrc = srcm ? device_twin_of_mirror(srcm, moff) : nullptr;
+    if (dsrc) {
+        e = cudaMemcpy2DAsync(dst, img->width, dsrc, pitch, region[0], region[1], cudaMemcpyDeviceToDevice, g_stream);
+        g_elided_bytes += region[0] * region[1];
+    } else {
+        e = cudaMemcpy2DAsync(dst, img->width, ptr, pitch, region[0], region[1], cudaMemcpyHostToDevice, g_stream);
+        g_h2d_bytes += region[0] * region[1];
+    }
     if (pitch == region[0]) trace_rec(4, img->index, 0, region[0] * region[1], ptr);
     if (blocking) stream_sync();
     return cuda_rc(e);
@@ -862,7 +1054,15 @@ void *clEnqueueMapBuffer(cl_command_queue, cl_mem m, cl_bool, cl_map_flags flags
     // in-flight asynchronous reads into other mapped buffers must have landed before the host looks
     stream_sync();
     m->mapped_for_write = writes;
-    if (writes) m->dev_valid = false;  // the host owns the contents until the unmap
+    if (writes) {
+        // the host owns the contents until the unmap; until it writes, the device copy still equals
+        // the mirror (unless the mapping discarded the contents)
+        m->dev_matches_mirror = m->dev_valid && !discard;
+        m->dev_valid = false;
+        m->twin = nullptr;
+        if (m->dev_matches_mirror) guard(m);
+        else unguard(m);
+    }
     if (err) *err = CL_SUCCESS;
     return p + off;
 }
