@@ -121,6 +121,18 @@ int vp8b200_mb_predict_transform_fused(void *stream, const uint8_t *cur_y, const
                                        uint8_t *recon_v, const vp8b200_segment_data *SD, float SSIM_target, int width,
                                        int height);
 
+/* GPU half of count_probs + encode_coefficients (src/CPU_kernels.cl:347-778, enqueued src/vp8enc.cpp:65-88):
+ * neighbour contexts (third_context [M][25]), per-partition token statistics coeff_probs /
+ * coeff_probs_denom [P][4][8][3][11] exactly as count_probs leaves them, and for every partition the
+ * stream of coded decisions in coding order (16-bit entries: bit 15 value, bits 0-10 probability slot
+ * or 1056 + fixed probability).  part_info: [0,P) stream bases, [P,2P) counts, [2P] total; if the total
+ * exceeds capacity no stream is written.  mb_tokens/mb_offset: int32 [M] scratch, tail_scratch: uint32 [P*68].
+ * The serial bool coder over the streams runs on the host. */
+int vp8b200_entropy_tokens(void *stream, const int16_t *MB, const int32_t *MB_non_zero_coeffs, const int32_t *MB_parts,
+                           int mb_width, int mb_height, int num_partitions, uint32_t *coeff_probs,
+                           uint32_t *coeff_probs_denom, uint8_t *third_context, uint16_t *tokens, uint32_t capacity,
+                           int32_t *mb_tokens, int32_t *mb_offset, uint32_t *part_info, uint32_t *tail_scratch);
+
 /* replaces prepare_filter_mask, src/CPU_kernels.cl:782-827 (src/loop_filter.h:25-33) */
 int vp8b200_prepare_filter_mask(void *stream, const int16_t *MB, int32_t *MB_non_zero_coeffs,
                                 const int32_t *MB_parts, int32_t *mb_mask, int width, int height);

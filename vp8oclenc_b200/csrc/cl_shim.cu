@@ -138,6 +138,7 @@ static void write_stats() {
     }
 }
 
+static bool g_gpu_tokens = true;       // coefficient decisions prepared on the GPU (see tokens_on_gpu)
 static int g_elide = 2;                // transfer elision: 0 off, 1 assume, 2 track (see "transfer elision" below)
 static std::vector<cl_mem> g_mirrors;  // objects that own a pinned mirror
 static std::vector<Cmd> g_cmds;  // the deferred command list
@@ -168,6 +169,7 @@ static bool cuda_init() {
     if (cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking) != cudaSuccess) return false;
     vp8b200_device_info(g_dev_name, sizeof(g_dev_name), &g_sm_count, nullptr, nullptr);
     if (const char *f = getenv("VP8B200_FUSED")) g_fuse = f[0] != '0';
+    if (const char *f = getenv("VP8B200_GPU_TOKENS")) g_gpu_tokens = f[0] != '0';
     if (const char *f = getenv("VP8B200_ELIDE")) g_elide = !strcmp(f, "assume") ? 1 : (!strcmp(f, "track") ? 2 : 0);
     if (g_elide == 2) install_guard_handler();
     const char *tr = getenv("VP8CL_TRACE");
@@ -395,6 +397,98 @@ template <class T> static inline T *out(cl_kernel k, int i) { return (T *)dev_pt
 template <class T> static inline T *hin(cl_kernel k, int i) { return (T *)host_ptr(arg_mem(k, i), false); }
 template <class T> static inline T *hout(cl_kernel k, int i) { return (T *)host_ptr(arg_mem(k, i), true); }
 
+// ---- coefficient entropy coding with the GPU doing everything but the bool coder --------
+// count_probs      -> vp8b200_entropy_tokens on the stream: statistics, contexts, decision streams
+// num_div_denom    -> host (1056 divisions), then the streams are fetched (sizes are known by then)
+// encode_coefficients -> host threads run the bool coder over the streams
+// Any mismatch (other buffers or geometry between the three calls, streams larger than the scratch,
+// VP8B200_GPU_TOKENS=0) falls back to the host-only path of entropy_host.cpp for that call.
+struct TokenState {
+    int stage = 0;  // 0 idle, 1 scan launched, 2 streams on their way to the host
+    cl_mem MB = nullptr, nz = nullptr, parts = nullptr, ctx = nullptr;
+    int mbh = 0, mbw = 0, P = 0;
+    uint16_t *dev_tokens = nullptr, *host_tokens = nullptr;
+    int32_t *dev_mb_tokens = nullptr, *dev_mb_offset = nullptr;
+    uint32_t *dev_part_info = nullptr, *dev_tail = nullptr, *host_part_info = nullptr;
+    size_t capacity = 0, mbs = 0;
+};
+static TokenState g_tok;
+
+static bool tokens_on_gpu(cl_kernel k) {
+    g_tok.stage = 0;
+    if (!g_gpu_tokens) return false;
+    const int mbh = arg_int(k, 6), mbw = arg_int(k, 7), P = arg_int(k, 8);
+    const size_t M = (size_t)mbh * mbw;
+    if (P < 1 || P > 8 || M == 0) return false;
+    cl_mem MB = arg_mem(k, 0), nz = arg_mem(k, 1), parts = arg_mem(k, 2), probs = arg_mem(k, 3), den = arg_mem(k, 4),
+           ctx = arg_mem(k, 5);
+    if (!MB || !nz || !parts || !probs || !den || !ctx || MB->size < M * 800 || nz->size < M * 4 || parts->size < M * 4 ||
+        probs->size < (size_t)P * 1056 * 4 || den->size < (size_t)P * 1056 * 4 || ctx->size < M * 25)
+        return false;
+    if (M > g_tok.mbs) {  // scratch for this frame size
+        stream_sync();
+        cudaFree(g_tok.dev_tokens); cudaFree(g_tok.dev_mb_tokens); cudaFree(g_tok.dev_mb_offset);
+        if (g_tok.host_tokens) cudaFreeHost(g_tok.host_tokens);
+        g_tok.capacity = M * 400;  // as many decisions as coefficients; larger frames (in bits) use the host path
+        bool ok = cudaMalloc((void **)&g_tok.dev_tokens, g_tok.capacity * 2) == cudaSuccess &&
+                  cudaMalloc((void **)&g_tok.dev_mb_tokens, M * 4) == cudaSuccess &&
+                  cudaMalloc((void **)&g_tok.dev_mb_offset, M * 4) == cudaSuccess &&
+                  cudaHostAlloc((void **)&g_tok.host_tokens, g_tok.capacity * 2, cudaHostAllocDefault) == cudaSuccess;
+        if (ok && !g_tok.dev_part_info)
+            ok = cudaMalloc((void **)&g_tok.dev_part_info, 32 * 4) == cudaSuccess &&
+                 cudaMalloc((void **)&g_tok.dev_tail, 8 * 68 * 4) == cudaSuccess &&
+                 cudaHostAlloc((void **)&g_tok.host_part_info, 32 * 4, cudaHostAllocDefault) == cudaSuccess;
+        if (!ok) {
+            g_gpu_tokens = false;
+            g_tok.mbs = 0;
+            return false;
+        }
+        g_tok.mbs = M;
+    }
+    ++g_kernel_launches;
+    const int rc = vp8b200_entropy_tokens(g_stream, in<int16_t>(k, 0), in<int32_t>(k, 1), in<int32_t>(k, 2), mbw, mbh, P,
+                                          out<uint32_t>(k, 3), out<uint32_t>(k, 4), out<uint8_t>(k, 5), g_tok.dev_tokens,
+                                          (uint32_t)g_tok.capacity, g_tok.dev_mb_tokens, g_tok.dev_mb_offset,
+                                          g_tok.dev_part_info, g_tok.dev_tail);
+    if (rc != 0) {  // nothing usable was produced: redo on the host
+        stream_sync();
+        cudaGetLastError();
+        arg_mem(k, 3)->host_valid = arg_mem(k, 4)->host_valid = arg_mem(k, 5)->host_valid = false;
+        return false;
+    }
+    cudaMemcpyAsync(g_tok.host_part_info, g_tok.dev_part_info, (2 * P + 1) * 4, cudaMemcpyDeviceToHost, g_stream);
+    g_tok.MB = MB; g_tok.nz = nz; g_tok.parts = parts; g_tok.ctx = ctx;
+    g_tok.mbh = mbh; g_tok.mbw = mbw; g_tok.P = P;
+    g_tok.stage = 1;
+    return true;
+}
+// after num_div_denom's download has waited for the stream, the stream sizes are on the host
+static void tokens_fetch() {
+    if (g_tok.stage != 1) return;
+    stream_sync();
+    const uint32_t total = g_tok.host_part_info[2 * g_tok.P];
+    if (total > g_tok.capacity) {
+        g_tok.stage = 0;  // did not fit: encode_coefficients will run on the host from the coefficients
+        return;
+    }
+    if (total) {
+        cudaMemcpyAsync(g_tok.host_tokens, g_tok.dev_tokens, (size_t)total * 2, cudaMemcpyDeviceToHost, g_stream);
+        g_d2h_bytes += (size_t)total * 2;
+    }
+    g_tok.stage = 2;
+}
+static bool tokens_encode(cl_kernel k) {
+    const bool usable = g_tok.stage == 2 && arg_mem(k, 0) == g_tok.MB && arg_mem(k, 1) == g_tok.nz &&
+                        arg_mem(k, 2) == g_tok.parts && arg_mem(k, 5) == g_tok.ctx && arg_int(k, 7) == g_tok.mbh &&
+                        arg_int(k, 8) == g_tok.mbw && arg_int(k, 9) == g_tok.P;
+    g_tok.stage = 0;
+    if (!usable) return false;
+    stream_sync();
+    vp8host::encode_token_streams(g_tok.host_tokens, g_tok.host_part_info, hin<uint32_t>(k, 6), hout<uint8_t>(k, 3),
+                                  hout<int32_t>(k, 4), g_tok.P, arg_int(k, 10));
+    return true;
+}
+
 // executes one kernel now (GPU kernels: launches on the stream; entropy kernels: runs on host threads)
 static cl_int dispatch_now(cl_kernel k, size_t global) {
     void *s = g_stream;
@@ -480,13 +574,18 @@ static cl_int dispatch_now(cl_kernel k, size_t global) {
                                            k->id == K_LF_LUMA ? 16 : 8);
             break;
         case K_COUNT_PROBS:
+            if (tokens_on_gpu(k)) break;
             vp8host::count_probs(hin<int16_t>(k, 0), hin<int32_t>(k, 1), hin<int32_t>(k, 2), hout<uint32_t>(k, 3),
                                  hout<uint32_t>(k, 4), hout<uint8_t>(k, 5), arg_int(k, 6), arg_int(k, 7), arg_int(k, 8));
             break;
-        case K_NUM_DIV_DENOM:
-            vp8host::num_div_denom(hout<uint32_t>(k, 0), hin<uint32_t>(k, 1), arg_int(k, 2));
+        case K_NUM_DIV_DENOM: {
+            uint32_t *probs = hout<uint32_t>(k, 0);  // (downloads the statistics and waits when the GPU made them)
+            vp8host::num_div_denom(probs, hin<uint32_t>(k, 1), arg_int(k, 2));
+            tokens_fetch();
             break;
+        }
         case K_ENCODE_COEFFS:
+            if (tokens_encode(k)) break;
             vp8host::encode_coefficients(hin<int16_t>(k, 0), hin<int32_t>(k, 1), hin<int32_t>(k, 2), hout<uint8_t>(k, 3),
                                          hout<int32_t>(k, 4), hin<uint8_t>(k, 5), hin<uint32_t>(k, 6), arg_int(k, 7),
                                          arg_int(k, 8), arg_int(k, 9), arg_int(k, 10));

@@ -412,6 +412,27 @@ void encode_coefficients(const int16_t *MB, const int32_t *nz, const int32_t *pa
     });
 }
 
+// The partitions from the decision streams the GPU prepared (entropy_kernels.cu): entry = bit 15 value,
+// bits 0-10 probability slot (< 1056) or 1056 + fixed probability.  part_info = [P] stream bases, [P] counts.
+void encode_token_streams(const uint16_t *tokens, const uint32_t *part_info, const uint32_t *coeff_probs, uint8_t *output,
+                          int32_t *partition_sizes, int P, int partition_step) {
+    // one table for both kinds of entry
+    std::vector<uint8_t> table(1056 + 256);
+    for (int i = 0; i < 1056; ++i) table[i] = (uint8_t)coeff_probs[i];
+    for (int i = 0; i < 256; ++i) table[1056 + i] = (uint8_t)i;
+    const uint8_t *tab = table.data();
+    for_each_partition(P, [=](int p) {
+        BoolSink s;
+        s.out = output + (size_t)partition_step * p;
+        s.probs = coeff_probs;
+        const uint16_t *t = tokens + part_info[p];
+        const uint32_t n = part_info[P + p];
+        for (uint32_t i = 0; i < n; ++i) s.put(tab[t[i] & 0x7ff], t[i] >> 15);
+        s.finish();
+        partition_sizes[p] = (int32_t)s.count;
+    });
+}
+
 }  // namespace vp8host
 
 // C entry points (used by the host-logic tests; the shim calls the C++ functions directly)
@@ -419,6 +440,10 @@ extern "C" {
 void vp8b200_host_count_probs(const int16_t *MB, const int32_t *nz, const int32_t *parts, uint32_t *coeff_probs,
                               uint32_t *coeff_probs_denom, uint8_t *third_context, int mb_height, int mb_width, int P) {
     vp8host::count_probs(MB, nz, parts, coeff_probs, coeff_probs_denom, third_context, mb_height, mb_width, P);
+}
+void vp8b200_host_encode_token_streams(const uint16_t *tokens, const uint32_t *part_info, const uint32_t *coeff_probs,
+                                       uint8_t *output, int32_t *partition_sizes, int P, int partition_step) {
+    vp8host::encode_token_streams(tokens, part_info, coeff_probs, output, partition_sizes, P, partition_step);
 }
 void vp8b200_host_num_div_denom(uint32_t *coeff_probs, const uint32_t *coeff_probs_denom, int P) {
     vp8host::num_div_denom(coeff_probs, coeff_probs_denom, P);

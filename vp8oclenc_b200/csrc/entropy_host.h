@@ -22,4 +22,9 @@ void encode_coefficients(const int16_t *MB, const int32_t *MB_non_zero_coeffs, c
                          const uint32_t *coeff_probs, int mb_height, int mb_width, int num_partitions,
                          int partition_step);
 
+// bool-codes the decision streams prepared on the GPU (vp8b200_entropy_tokens); same bytes as
+// encode_coefficients
+void encode_token_streams(const uint16_t *tokens, const uint32_t *part_info, const uint32_t *coeff_probs, uint8_t *output,
+                          int32_t *partition_sizes, int num_partitions, int partition_step);
+
 }  // namespace vp8host
