@@ -158,7 +158,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ref-frames", type=int, default=6, help="timed frames of the CPU reference sample")
-    ap.add_argument("--segments", type=int, default=4, help="independent segments (engines, streams) per GPU in the `value` run")
+    ap.add_argument("--segments", type=int, default=6, help="independent segments (engines, streams) per GPU in the `value` run")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-mps", action="store_true", help="do not start a CUDA MPS daemon for the multi-instance e2e run")
     ap.add_argument("--e2e-procs", type=int, default=0, help="encoder instances per GPU for the e2e run (0 = auto)")
@@ -379,16 +379,19 @@ def b200_arm(args, rank, world, local_rank, tmp, config):
             n = 1 + W + K
 
             def run(P, tag, env_more=None):
-                paths = []
+                # at most 8 distinct segments per rank; further instances re-encode one of them into their own output
+                paths, outs = [], []
                 for p in range(P):
-                    y4m = os.path.join(tmp, "e2e_%s_%d_%d.y4m" % (tag, rank, p))
-                    gen_y4m.write_y4m(y4m, WIDTH, HEIGHT, n, start=(rank * P + p) * n)
+                    y4m = os.path.join(tmp, "e2e_%s_%d_%d.y4m" % (tag, rank, p % 8))
+                    if p < 8:
+                        gen_y4m.write_y4m(y4m, WIDTH, HEIGHT, n, start=(rank * 8 + p) * n)
                     paths.append(y4m)
+                    outs.append(os.path.join(tmp, "e2e_%s_%d_%d" % (tag, rank, p)))
                 if dist:
                     dist.barrier()
-                procs = [segments.EncoderProcess(paths[p], paths[p][:-4] + ".ivf", ENC_ARGS,
+                procs = [segments.EncoderProcess(paths[p], outs[p] + ".ivf", ENC_ARGS,
                                                  os.path.join(tmp, "run_%s_%d_%d" % (tag, rank, p)), device=local_rank,
-                                                 env_extra=dict(env_more or {}, VP8B200_STATS=paths[p][:-4] + ".stats"))
+                                                 env_extra=dict(env_more or {}, VP8B200_STATS=outs[p] + ".stats"))
                          for p in range(P)]
                 stamps = [pr.wait() for pr in procs]
                 for st in stamps:
@@ -407,16 +410,15 @@ def b200_arm(args, rank, world, local_rank, tmp, config):
                     count = int(cc.item())
                 h2d = d2h = launches_ps = None
                 try:
-                    s0 = json.load(open(paths[0][:-4] + ".stats"))
+                    s0 = json.load(open(outs[0] + ".stats"))
                     h2d, d2h, launches_ps = int(s0["h2d_bytes"] / n), int(s0["d2h_bytes"] / n), s0["kernel_launches"] / n
                 except Exception:
                     pass
-                for pth in paths:
-                    for ext in (".y4m", ".ivf"):
-                        try:
-                            os.remove(pth[:-4] + ext)
-                        except OSError:
-                            pass
+                for pth in set(paths) | set(o + ".ivf" for o in outs):
+                    try:
+                        os.remove(pth)
+                    except OSError:
+                        pass
                 return count / (t1 - t0), count, h2d, d2h, launches_ps
 
             # several instances per GPU share it through a private CUDA MPS daemon (one per node, started by
@@ -430,12 +432,12 @@ def b200_arm(args, rank, world, local_rank, tmp, config):
                 daemon.active = os.path.exists(os.path.join(daemon.pipe, "control"))
             cores = os.cpu_count() or 2
             if daemon.active:
-                P = args.e2e_procs or max(1, min(24, (3 * cores) // (2 * world)))
+                P = args.e2e_procs or max(1, min(32, (2 * cores) // world))
             else:
                 P = args.e2e_procs or max(1, min(8, cores // max(2, 2 * world)))
             try:
                 fps1, _, h2d, d2h, lps = run(1, "single")
-                fpsP, cnt, _, _, _ = (fps1, K, 0, 0, 0) if P == 1 else run(P, "multi", daemon.env())
+                fpsP, cnt, _, _, _ = (fps1, K, 0, 0, 0) if P == 1 else run(P, "multi", dict(daemon.env(), VP8B200_SYNC="yield"))
             finally:
                 mps_used = daemon.active
                 if dist:
