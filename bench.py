@@ -159,6 +159,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ref-frames", type=int, default=6, help="timed frames of the CPU reference sample")
     ap.add_argument("--segments", type=int, default=6, help="independent segments (engines, streams) per GPU in the `value` run")
+    ap.add_argument("--size", default="1920x1080", help="frame size WxH (default: the 1080p configuration the metric is quoted on; "
+                                                         "other sizes are informational)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-mps", action="store_true", help="do not start a CUDA MPS daemon for the multi-instance e2e run")
     ap.add_argument("--e2e-procs", type=int, default=0, help="encoder instances per GPU for the e2e run (0 = auto)")
@@ -166,12 +168,15 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
+    global WIDTH, HEIGHT, WRK_W, WRK_H
+    WIDTH, HEIGHT = (int(x) for x in args.size.lower().split("x"))
+    WRK_W, WRK_H = (WIDTH + 15) // 16 * 16, (HEIGHT + 15) // 16 * 16
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     tmp = tempfile.mkdtemp(prefix="vp8bench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
-    config = {"workload": "1920x1080 synthetic YUV420 (tools/gen_y4m.py), padded to 1920x1088, LAST+GOLDEN+ALTREF, "
-                          "q=24, altref-range 5, 8 partitions, loop filter on the GPU",
+    config = {"workload": "%dx%d synthetic YUV420 (tools/gen_y4m.py), padded to %dx%d, LAST+GOLDEN+ALTREF, "
+                          "q=24, altref-range 5, 8 partitions, loop filter on the GPU" % (WIDTH, HEIGHT, WRK_W, WRK_H),
               "frame_size": [WIDTH, HEIGHT], "segments_per_gpu": max(1, args.segments),
               "step": "one frame of each of the segments_per_gpu independent segments (one engine + stream per segment)"}
     try:
@@ -182,7 +187,7 @@ def main():
             if r is None:
                 print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref (compiled reference) is not present"}))
                 return 0
-            line = {"impl": "reference", "metric": "encoded frames/s at 1080p", "value": r["value"], "unit": "frames/s",
+            line = {"impl": "reference", "metric": "encoded frames/s at %s" % ("1080p" if HEIGHT == 1080 else "%dx%d" % (WIDTH, HEIGHT)), "value": r["value"], "unit": "frames/s",
                     "n_gpus": args.gpus, "steps": r["steps"], "warmup": r["warmup"], "ms_per_step": r["ms_per_step"],
                     "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32",
                     "data": "synthetic", "config": config,
@@ -460,7 +465,7 @@ def b200_arm(args, rank, world, local_rank, tmp, config):
             cpu_baseline = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
-        line = {"metric": "encoded frames/s at 1080p", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K,
+        line = {"metric": "encoded frames/s at %s" % ("1080p" if HEIGHT == 1080 else "%dx%d" % (WIDTH, HEIGHT)), "value": value, "unit": "frames/s", "n_gpus": world, "steps": K,
                 "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u8/int32", "data": "synthetic",
                 "config": dict(config, l2="flushed between timed steps (256 MiB fill outside the timed span)",
