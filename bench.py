@@ -442,7 +442,16 @@ def b200_arm(args, rank, world, local_rank, tmp, config):
                 P = args.e2e_procs or max(1, min(8, cores // max(2, 2 * world)))
             try:
                 fps1, _, h2d, d2h, lps = run(1, "single")
-                fpsP, cnt, _, _, _ = (fps1, K, 0, 0, 0) if P == 1 else run(P, "multi", dict(daemon.env(), VP8B200_SYNC="yield"))
+                try:
+                    fpsP, cnt, _, _, _ = (fps1, K, 0, 0, 0) if P == 1 else run(P, "multi", dict(daemon.env(), VP8B200_SYNC="yield"))
+                except RuntimeError as err:
+                    if dist or not daemon.active:
+                        raise
+                    # the instances could not run under the MPS daemon on this box: time-sliced contexts instead
+                    sys.stderr.write("bench: multi-instance run under MPS failed (%s); retrying without MPS\n" % err)
+                    daemon.__exit__(None, None, None)
+                    P = max(1, min(8, cores // 2))
+                    fpsP, cnt, _, _, _ = run(P, "multi_nomps", {})
             finally:
                 mps_used = daemon.active
                 if dist:
