@@ -81,3 +81,23 @@ def test_without_trace_same_bitstream(tmp_path):
     _trace.run_host(_trace.REF_DIR, d, y4m, os.path.join(d, "ref.ivf"), args)
     _trace.run_host(SHIM_DIR, d, y4m, os.path.join(d, "b200.ivf"), args)
     assert open(os.path.join(d, "ref.ivf"), "rb").read() == open(os.path.join(d, "b200.ivf"), "rb").read()
+
+
+@pytest.mark.parametrize("env", [{"VP8B200_TOKEN_CAP": "64"}, {"VP8B200_GPU_TOKENS": "0"}, {"VP8B200_ELIDE": "off"},
+                                 {"VP8B200_FUSED": "0"}, {"VP8B200_SYNC": "sleep20"}],
+                         ids=["token-scratch-grows", "host-entropy", "no-elision", "kernel-per-kernel", "sleep-sync"])
+def test_shim_modes_same_bitstream(env, tmp_path):
+    """every switch of the shim changes HOW the bytes are produced, never the bytes: decision streams that
+    outgrow their scratch, the host-only entropy path, no transfer elision, no fused launches, polling sync.
+    The clip and options force key frames by SSIM fallback, so the host's intra path (which stores into the
+    write-protected mirrors) is exercised as well."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_y4m
+    w, h, frames, args = CASES["cif_ssim"]
+    d = str(tmp_path)
+    y4m = os.path.join(d, "clip.y4m")
+    gen_y4m.write_y4m(y4m, w, h, frames)
+    _trace.run_host(_trace.REF_DIR, d, y4m, os.path.join(d, "ref.ivf"), args)
+    _trace.run_host(SHIM_DIR, d, y4m, os.path.join(d, "b200.ivf"), args, env_extra=env)
+    assert open(os.path.join(d, "ref.ivf"), "rb").read() == open(os.path.join(d, "b200.ivf"), "rb").read()

@@ -401,8 +401,9 @@ template <class T> static inline T *hout(cl_kernel k, int i) { return (T *)host_
 // count_probs      -> vp8b200_entropy_tokens on the stream: statistics, contexts, decision streams
 // num_div_denom    -> host (1056 divisions), then the streams are fetched (sizes are known by then)
 // encode_coefficients -> host threads run the bool coder over the streams
-// Any mismatch (other buffers or geometry between the three calls, streams larger than the scratch,
-// VP8B200_GPU_TOKENS=0) falls back to the host-only path of entropy_host.cpp for that call.
+// Streams larger than the scratch (dense key frames) make the scratch grow and the streams are written again.
+// Only a mismatch between the three calls (other buffers or geometry), an allocation failure or
+// VP8B200_GPU_TOKENS=0 select the host-only path of entropy_host.cpp.
 struct TokenState {
     int stage = 0;  // 0 idle, 1 scan launched, 2 streams on their way to the host
     cl_mem MB = nullptr, nz = nullptr, parts = nullptr, ctx = nullptr;
@@ -413,6 +414,7 @@ struct TokenState {
     size_t capacity = 0, mbs = 0;
 };
 static TokenState g_tok;
+static bool tokens_alloc_streams(size_t entries);
 
 static bool tokens_on_gpu(cl_kernel k) {
     g_tok.stage = 0;
@@ -427,13 +429,12 @@ static bool tokens_on_gpu(cl_kernel k) {
         return false;
     if (M > g_tok.mbs) {  // scratch for this frame size
         stream_sync();
-        cudaFree(g_tok.dev_tokens); cudaFree(g_tok.dev_mb_tokens); cudaFree(g_tok.dev_mb_offset);
-        if (g_tok.host_tokens) cudaFreeHost(g_tok.host_tokens);
-        g_tok.capacity = M * 400;  // as many decisions as coefficients; larger frames (in bits) use the host path
-        bool ok = cudaMalloc((void **)&g_tok.dev_tokens, g_tok.capacity * 2) == cudaSuccess &&
+        cudaFree(g_tok.dev_mb_tokens); cudaFree(g_tok.dev_mb_offset);
+        // as many decisions as coefficients to start with (inter frames need a few per cent of that); grown on demand
+        const char *cap_env = getenv("VP8B200_TOKEN_CAP");  // (tests: start tiny to exercise the growth path)
+        bool ok = tokens_alloc_streams(cap_env ? (size_t)atol(cap_env) : M * 400) &&
                   cudaMalloc((void **)&g_tok.dev_mb_tokens, M * 4) == cudaSuccess &&
-                  cudaMalloc((void **)&g_tok.dev_mb_offset, M * 4) == cudaSuccess &&
-                  cudaHostAlloc((void **)&g_tok.host_tokens, g_tok.capacity * 2, cudaHostAllocDefault) == cudaSuccess;
+                  cudaMalloc((void **)&g_tok.dev_mb_offset, M * 4) == cudaSuccess;
         if (ok && !g_tok.dev_part_info)
             ok = cudaMalloc((void **)&g_tok.dev_part_info, 32 * 4) == cudaSuccess &&
                  cudaMalloc((void **)&g_tok.dev_tail, 8 * 68 * 4) == cudaSuccess &&
@@ -462,14 +463,44 @@ static bool tokens_on_gpu(cl_kernel k) {
     g_tok.stage = 1;
     return true;
 }
+static bool tokens_alloc_streams(size_t entries) {
+    cudaFree(g_tok.dev_tokens);
+    if (g_tok.host_tokens) cudaFreeHost(g_tok.host_tokens);
+    g_tok.dev_tokens = nullptr;
+    g_tok.host_tokens = nullptr;
+    g_tok.capacity = entries;
+    return cudaMalloc((void **)&g_tok.dev_tokens, entries * 2) == cudaSuccess &&
+           cudaHostAlloc((void **)&g_tok.host_tokens, entries * 2, cudaHostAllocDefault) == cudaSuccess;
+}
 // after num_div_denom's download has waited for the stream, the stream sizes are on the host
 static void tokens_fetch() {
     if (g_tok.stage != 1) return;
     stream_sync();
-    const uint32_t total = g_tok.host_part_info[2 * g_tok.P];
+    uint32_t total = g_tok.host_part_info[2 * g_tok.P];
     if (total > g_tok.capacity) {
-        g_tok.stage = 0;  // did not fit: encode_coefficients will run on the host from the coefficients
-        return;
+        // a frame with more decisions than the scratch holds (dense key frames): grow it and write the streams
+        // again; statistics and contexts of the repeat go to scratch tables, the real ones are already in use
+        const size_t M = (size_t)g_tok.mbh * g_tok.mbw, tables = (size_t)g_tok.P * 1056 * 4;
+        void *scratch = nullptr;
+        bool ok = tokens_alloc_streams((size_t)total + total / 4) &&
+                  cudaMalloc(&scratch, 2 * tables + M * 25) == cudaSuccess;
+        if (ok) {
+            ++g_kernel_launches;
+            ok = vp8b200_entropy_tokens(g_stream, (const int16_t *)dev_ptr(g_tok.MB, false), (const int32_t *)dev_ptr(g_tok.nz, false),
+                                        (const int32_t *)dev_ptr(g_tok.parts, false), g_tok.mbw, g_tok.mbh, g_tok.P,
+                                        (uint32_t *)scratch, (uint32_t *)((char *)scratch + tables),
+                                        (uint8_t *)scratch + 2 * tables, g_tok.dev_tokens, (uint32_t)g_tok.capacity,
+                                        g_tok.dev_mb_tokens, g_tok.dev_mb_offset, g_tok.dev_part_info, g_tok.dev_tail) == 0;
+            cudaMemcpyAsync(g_tok.host_part_info, g_tok.dev_part_info, (2 * g_tok.P + 1) * 4, cudaMemcpyDeviceToHost, g_stream);
+            stream_sync();
+            total = g_tok.host_part_info[2 * g_tok.P];
+        }
+        cudaFree(scratch);
+        if (!ok || total > g_tok.capacity) {
+            g_tok.stage = 0;  // out of memory: encode_coefficients runs on the host from the coefficients
+            if (!ok) g_tok.mbs = 0;
+            return;
+        }
     }
     if (total) {
         cudaMemcpyAsync(g_tok.host_tokens, g_tok.dev_tokens, (size_t)total * 2, cudaMemcpyDeviceToHost, g_stream);
