@@ -101,3 +101,50 @@ def test_shim_modes_same_bitstream(env, tmp_path):
     _trace.run_host(_trace.REF_DIR, d, y4m, os.path.join(d, "ref.ivf"), args)
     _trace.run_host(SHIM_DIR, d, y4m, os.path.join(d, "b200.ivf"), args, env_extra=env)
     assert open(os.path.join(d, "ref.ivf"), "rb").read() == open(os.path.join(d, "b200.ivf"), "rb").read()
+
+
+def _write_scene_cut_clip(path, w, h, frames, cut):
+    """a clip whose chroma jumps at frame `cut` (the reference's colour-difference scene detector fires,
+    src/vp8enc.cpp:265-311) and whose luma is a different texture from there on"""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_y4m
+    clip = gen_y4m.Clip(w, h)
+    with open(path, "wb") as f:
+        f.write(b"YUV4MPEG2 W%d H%d F30:1 Ip A1:1 C420\n" % (w, h))
+        for i in range(frames):
+            y, u, v = clip.frame(i if i < cut else i + 400)
+            if i >= cut:
+                y = np.ascontiguousarray(y[::-1, ::-1])
+                u = (255 - u.astype(np.int32)).clip(0, 255).astype(np.uint8)
+                v = ((v.astype(np.int32) + 90) % 256).astype(np.uint8)
+            f.write(b"FRAME\n")
+            f.write(np.ascontiguousarray(y).tobytes() + np.ascontiguousarray(u).tobytes() + np.ascontiguousarray(v).tobytes())
+
+
+@pytest.mark.parametrize("name,args,cut", [
+    ("scene-cut", ["-qmin", 20, "-qmax", 40, "-g", 50, "-altref-range", 4, "-partitions", 4, "-threads", 4], 7),
+    ("golden-altref-rotation", ["-qmin", 28, "-qmax", 28, "-g", 40, "-altref-range", 2, "-partitions", 2, "-threads", 4], None),
+    ("gop-2", ["-qmin", 30, "-qmax", 30, "-g", 2, "-partitions", 2, "-threads", 2], None),
+])
+def test_host_control_flow_variants(name, args, cut, tmp_path):
+    """paths of the unmodified host that the synthetic clips above do not reach: a key frame forced by the
+    colour-difference scene detector in the middle of a GOP, many golden/altref refreshes, and -g 2 (every
+    other frame a key frame; -g 1 crashes the reference host on its own runtime too, so it is not a case)"""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_y4m
+    w, h, frames = 352, 288, 26 if cut is None else 14
+    d = str(tmp_path)
+    y4m = os.path.join(d, "clip.y4m")
+    if cut is None:
+        gen_y4m.write_y4m(y4m, w, h, frames)
+    else:
+        _write_scene_cut_clip(y4m, w, h, frames, cut)
+    out_ref = _trace.run_host(_trace.REF_DIR, d, y4m, os.path.join(d, "ref.ivf"), args)
+    _trace.run_host(SHIM_DIR, d, y4m, os.path.join(d, "b200.ivf"), args)
+    a = open(os.path.join(d, "ref.ivf"), "rb").read()
+    assert len(a) > 32 + 12 * frames
+    assert a == open(os.path.join(d, "b200.ivf"), "rb").read()
+    if cut is not None:
+        assert "1 scene changes detected by color change" in out_ref, out_ref[-400:]
