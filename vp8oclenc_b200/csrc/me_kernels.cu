@@ -302,24 +302,26 @@ k_luma_search_2step(const uint8_t *__restrict__ cur, Search2Refs refs, int width
     const int n0 = blockIdx.x * S2_BLOCKS;
 
     __shared__ int4 s_geo[S2_BLOCKS];              // bx, by, v0x, v0y of every block
-    if (tid < S2_BLOCKS) {
-        const int n = min(n0 + tid, nblocks - 1);
+    // Every staging thread derives the geometry of its block itself (one cached load and a division): no
+    // separate "eight threads look up the vectors" phase with a barrier behind it.
+    auto block_geometry = [&](int b) {
+        const int n = min(n0 + b, nblocks - 1);
         const short2 v = __ldg(net + n);
         // short lanes in the reference; v0 is a multiple of 4
-        s_geo[tid] = make_int4((n % bw) * 8, (n / bw) * 8, (short)(v.x * 4), (short)(v.y * 4));
-        s_key[tid] = 0xffffffffu;
-    }
-    __syncthreads();
+        return make_int4((n % bw) * 8, (n / bw) * 8, (short)(v.x * 4), (short)(v.y * 4));
+    };
     auto geometry = [&](int b, int &bx, int &by, int &v0x, int &v0y) {
         const int4 g = s_geo[b];
         bx = g.x; by = g.y; v0x = g.z; v0y = g.w;
     };
+    if (tid < S2_BLOCKS) s_key[tid] = 0xffffffffu;
 
     // one window line per thread: five aligned words cover its 14 pixels wherever they start; lines that
     // touch the left/right frame edge (or an unaligned plane) take the clamped byte path
     for (int i = tid; i < S2_BLOCKS * 14; i += S2_THREADS) {
         const int b = i / 14, r = i % 14;
-        const int4 g = s_geo[b];
+        const int4 g = block_geometry(b);
+        if (r == 0) s_geo[b] = g;
         const int x0 = g.x + (g.z >> 2) - 3, y = clampi(g.y + (g.w >> 2) - 3 + r, 0, height - 1);
         const uint8_t *line = ref + (size_t)y * width;
         const int xa = x0 & ~3;
@@ -336,26 +338,42 @@ k_luma_search_2step(const uint8_t *__restrict__ cur, Search2Refs refs, int width
             for (int c = 0; c < 14; ++c) dst[c] = __ldg(line + clampi(x0 + c, 0, width - 1));
         }
     }
-    if (tid < S2_BLOCKS * 16) {
-        const int b = tid >> 4, r = (tid >> 1) & 7, h = tid & 1;
-        const int4 g = s_geo[b];
-        s_cur[b][r][h] = __ldg(reinterpret_cast<const uint32_t *>(cur + (size_t)(g.y + r) * width + g.x) + h);
-        s_zero[b][r][h] = __ldg(reinterpret_cast<const uint32_t *>(ref + (size_t)(g.y + r) * width + g.x) + h);
+    // (S2_THREADS - S2_BLOCKS * 16 = 64 < 112: most threads do one of the two jobs; going backwards spreads them)
+    if (tid >= S2_THREADS - S2_BLOCKS * 16) {
+        const int t = S2_THREADS - 1 - tid;
+        const int b = t >> 4, r = (t >> 1) & 7, h = t & 1;
+        const int n = min(n0 + b, nblocks - 1);
+        const int gx = (n % bw) * 8, gy = (n / bw) * 8;
+        s_cur[b][r][h] = __ldg(reinterpret_cast<const uint32_t *>(cur + (size_t)(gy + r) * width + gx) + h);
+        s_zero[b][r][h] = __ldg(reinterpret_cast<const uint32_t *>(ref + (size_t)(gy + r) * width + gx) + h);
     }
     __syncthreads();
 
-    // horizontal pass: 5 x-variants x 14 rows x 8 columns per block, four columns (one word) per item
+    // horizontal pass: 5 x-variants x 14 rows x 8 columns per block, four columns per item.  The window line
+    // is three aligned words; an output's six taps are two dp4a on funnel-shifted words (the full-pel variant
+    // is a byte copy: its tap 128 does not fit a signed byte).
     for (int i = tid; i < S2_BLOCKS * 140; i += S2_THREADS) {
         const int b = i / 140, q = i % 140;
         const int var = q / 28, r = (q % 28) >> 1, h = q & 1;
-        const int ph = s2_phase(var), first = s2_origin(var) + 1 + 4 * h;  // window column of tap 0 of output 0
+        const int first = s2_origin(var) + 1;  // window column of tap 0 of output 0, relative to word h
+        const uint32_t wa = s_win[b][r][h], wb = s_win[b][r][h + 1], wc = s_win[b][r][h + 2];
+        uint8_t *dst = &s_h[b][var][4 * h][r];
+        if (var == 2) {  // phase 0: the pixel itself (tap 2 of outputs 0..3 = bytes 3..6 of the three words)
+            const uint32_t px = __funnelshift_r(wa, wb, 24);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            int s = 64;
+            for (int c = 0; c < 4; ++c) dst[16 * c] = (uint8_t)(px >> (8 * c));
+        } else {
+            const uint32_t lo = var == 3 ? taps_lo(2) : (var == 1 ? taps_lo(6) : taps_lo(4));
+            const uint32_t hi = var == 3 ? taps_hi(2) : (var == 1 ? taps_hi(6) : taps_hi(4));
 #pragma unroll
-            for (int t = 0; t < 6; ++t) s += (int)c_sixtap[ph][t] * (int)reinterpret_cast<const uint8_t *>(&s_win[b][r][0])[first + c + t];
-            // (s/128 then saturate) == saturate(s>>7): the two only differ for -128<s<0, both give 0
-            s_h[b][var][4 * h + c][r] = (uint8_t)sat8(s >> 7);
+            for (int c = 0; c < 4; ++c) {
+                const int sh = 8 * (first + c);  // 0..32
+                const uint32_t w_lo = sh == 32 ? wb : __funnelshift_r(wa, wb, sh);
+                const uint32_t w_hi = sh == 32 ? wc : __funnelshift_r(wb, wc, sh);
+                const int s = dp4a_u8s8(w_hi, hi, dp4a_u8s8(w_lo, lo, 64));
+                // (s/128 then saturate) == saturate(s>>7): the two only differ for -128<s<0, both give 0
+                dst[16 * c] = (uint8_t)sat8(s >> 7);
+            }
         }
     }
     __syncthreads();
