@@ -158,7 +158,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ref-frames", type=int, default=6, help="timed frames of the CPU reference sample")
-    ap.add_argument("--segments", type=int, default=6, help="independent segments (engines, streams) per GPU in the `value` run")
+    ap.add_argument("--segments", type=int, default=8, help="independent segments (engines, streams) per GPU in the `value` run")
     ap.add_argument("--size", default="1920x1080", help="frame size WxH (default: the 1080p configuration the metric is quoted on; "
                                                          "other sizes are informational)")
     ap.add_argument("--no-e2e", action="store_true")
