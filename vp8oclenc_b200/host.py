@@ -139,6 +139,16 @@ def loop_filter_planes(y, u, v, MB_segment_ids, mb_mask, SD, width, height):
                                             width, height), "loop_filter_planes")
 
 
+def entropy_tokens(MB, MB_non_zero_coeffs, MB_parts, mb_width, mb_height, num_partitions, coeff_probs, coeff_probs_denom,
+                   third_context, tokens, mb_tokens, mb_offset, part_info, tail_scratch):
+    """GPU half of count_probs + encode_coefficients (src/CPU_kernels.cl:347-778): statistics, contexts and the
+    decision stream of every partition; `tokens` is an int16/uint16 tensor whose length is the capacity"""
+    _check(lib().vp8b200_entropy_tokens(_stream(), _p(MB), _p(MB_non_zero_coeffs), _p(MB_parts), mb_width, mb_height,
+                                        num_partitions, _p(coeff_probs), _p(coeff_probs_denom), _p(third_context),
+                                        _p(tokens), ctypes.c_uint32(tokens.numel()), _p(mb_tokens), _p(mb_offset),
+                                        _p(part_info), _p(tail_scratch)), "entropy_tokens")
+
+
 # ---------------------------------------------------------------------------------------------
 class Engine:
     """Frame-level engine (vp8b200_engine_* of include/vp8b200.h): the sequence of
