@@ -128,6 +128,10 @@ def run_encoder_timed(host_bin, lib_dir, workdir, y4m, ivf, frames_total, env_ex
     return stamps, "".join(out)
 
 
+def _tempfile_dir():
+    return tempfile.gettempdir()
+
+
 def reference_arm(args, tmp):
     """the reference's own CPU implementation: its host + its .cl kernels compiled for the CPU
     (oracle/_ref), all host cores (OpenMP), on a bounded sample of the same workload"""
@@ -381,7 +385,11 @@ def b200_arm(args, rank, world, local_rank, tmp, config):
     if not args.no_e2e:
         from vp8oclenc_b200 import segments
         if os.path.exists(segments.HOST_BIN):
-            n = 1 + W + K
+            # every instance encodes 1 key + W warm-up + Ke timed frames; Ke >= 80 so that the timed window is long
+            # against the scheduling noise of P processes on the host cores
+            Ke = max(K, 80)
+            n = 1 + W + Ke
+            gate_root = "/dev/shm" if os.path.isdir("/dev/shm") else _tempfile_dir()
 
             def run(P, tag, env_more=None):
                 # at most 8 distinct segments per rank; further instances re-encode one of them into their own output
@@ -392,11 +400,18 @@ def b200_arm(args, rank, world, local_rank, tmp, config):
                         gen_y4m.write_y4m(y4m, WIDTH, HEIGHT, n, start=(rank * 8 + p) * n)
                     paths.append(y4m)
                     outs.append(os.path.join(tmp, "e2e_%s_%d_%d" % (tag, rank, p)))
+                # start gate (cl_shim.cu start_gate): all P x world instances create their CUDA context (15-20 s for
+                # 32 of them, serialised by the driver), then begin to encode together
+                gate = os.path.join(gate_root, "vp8b200_gate_%s_%s" % (os.environ.get("MASTER_PORT", os.getpid()), tag))
+                if rank == 0:
+                    shutil.rmtree(gate, ignore_errors=True)
+                    os.makedirs(gate)
                 if dist:
                     dist.barrier()
                 procs = [segments.EncoderProcess(paths[p], outs[p] + ".ivf", ENC_ARGS,
                                                  os.path.join(tmp, "run_%s_%d_%d" % (tag, rank, p)), device=local_rank,
-                                                 env_extra=dict(env_more or {}, VP8B200_STATS=outs[p] + ".stats"))
+                                                 env_extra=dict(env_more or {}, VP8B200_STATS=outs[p] + ".stats",
+                                                                VP8B200_START_GATE="%s:%d" % (gate, P * world)))
                          for p in range(P)]
                 stamps = [pr.wait() for pr in procs]
                 for st in stamps:
@@ -419,6 +434,10 @@ def b200_arm(args, rank, world, local_rank, tmp, config):
                     h2d, d2h, launches_ps = int(s0["h2d_bytes"] / n), int(s0["d2h_bytes"] / n), s0["kernel_launches"] / n
                 except Exception:
                     pass
+                if dist:
+                    dist.barrier()
+                if rank == 0:
+                    shutil.rmtree(gate, ignore_errors=True)
                 for pth in set(paths) | set(o + ".ivf" for o in outs):
                     try:
                         os.remove(pth)
@@ -443,7 +462,7 @@ def b200_arm(args, rank, world, local_rank, tmp, config):
             try:
                 fps1, _, h2d, d2h, lps = run(1, "single")
                 try:
-                    fpsP, cnt, _, _, _ = (fps1, K, 0, 0, 0) if P == 1 else run(P, "multi", dict(daemon.env(), VP8B200_SYNC="yield"))
+                    fpsP, cnt, _, _, _ = (fps1, Ke, 0, 0, 0) if P == 1 else run(P, "multi", dict(daemon.env(), VP8B200_SYNC="yield"))
                 except RuntimeError as err:
                     if dist or not daemon.active:
                         raise
@@ -462,7 +481,9 @@ def b200_arm(args, rank, world, local_rank, tmp, config):
             e2e = {"value": best, "unit": "frames/s", "ms_per_step": 1000.0 / best,
                    "processes_per_gpu": P if fpsP >= fps1 else 1, "single_process_fps": fps1 * (1 if not dist else 1),
                    "multi_process_fps": fpsP, "mps": bool(mps_used and P > 1), "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                   "shim_kernel_launches_per_step": lps,
+                   "shim_kernel_launches_per_step": lps, "timed_frames_per_instance": Ke,
+                   "window": "from the moment the last instance has finished its key + warm-up frames to the moment the last "
+                             "instance is done; instances start encoding together (start gate after CUDA context creation)",
                    "what": "unmodified reference host (vp8enc.cpp + entropy_host.cpp) + libOpenCL.so.1 shim; Y4M file in, "
                            "IVF file out; all host<->device copies, host intra/entropy work and file I/O included; "
                            "instances encode independent keyframe-delimited segments (no collective)"}

@@ -25,6 +25,7 @@
 //    match exactly runs kernel by kernel.  VP8B200_FUSED=0 turns the replacement off.
 #include <CL/cl.h>
 #include <cuda_runtime.h>
+#include <dirent.h>
 #include <signal.h>
 #include <sys/mman.h>
 #include <sys/resource.h>
@@ -34,6 +35,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 #include <vector>
 
 #include "entropy_host.h"
@@ -178,6 +180,39 @@ static bool cuda_init() {
     g_ns_start = now_ns();
     g_cuda_ok = true;
     return true;
+}
+
+// Start gate for multi-instance throughput measurements (VP8B200_START_GATE=<dir>:<count>): at its first
+// enqueue call -- context, buffers and kernels exist, no frame has been touched -- an instance drops a file
+// into <dir> and waits until <count> instances have done so (or 180 s have passed).  Creating 32 CUDA contexts
+// takes the driver 15-20 s, one after the other; without the gate the first instances are done before the last
+// ones start and a short run never sees all of them encoding at the same time.  Not set: no effect.
+static void start_gate() {
+    static bool done = false;
+    if (done) return;
+    done = true;
+    const char *g = getenv("VP8B200_START_GATE");
+    const char *colon = g ? strrchr(g, ':') : nullptr;
+    if (!colon || colon == g) return;
+    const std::string dir(g, colon - g);
+    const int want = atoi(colon + 1);
+    char name[64];
+    snprintf(name, sizeof(name), "/ready.%d", (int)getpid());
+    if (FILE *f = fopen((dir + name).c_str(), "w")) fclose(f);
+    const unsigned long long t0 = now_ns();
+    while (now_ns() - t0 < 180ull * 1000000000ull) {
+        int n = 0;
+        if (DIR *d = opendir(dir.c_str())) {
+            while (dirent *e = readdir(d)) n += !strncmp(e->d_name, "ready.", 6);
+            closedir(d);
+        } else {
+            return;
+        }
+        if (n >= want) break;
+        timespec ts = {0, 2000000L};
+        nanosleep(&ts, nullptr);
+    }
+    g_ns_start = now_ns();
 }
 
 // Waits for everything issued on the stream.  VP8B200_SYNC=sleep polls an event with short sleeps in
@@ -1038,6 +1073,7 @@ cl_int clEnqueueNDRangeKernel(cl_command_queue, cl_kernel k, cl_uint dim, const 
     if (dim != 1 || !gsz) return CL_INVALID_WORK_DIMENSION;
     for (int i = 0; i < kKernels[k->id].nargs; ++i)
         if (!k->set[i]) return CL_INVALID_KERNEL_ARGS;
+    start_gate();
     ScopedTimer timer(k->id >= K_COUNT_PROBS ? T_HOST_KERNEL : T_LAUNCH);
     return dispatch(k, gsz[0]);
 }
@@ -1045,6 +1081,7 @@ cl_int clEnqueueNDRangeKernel(cl_command_queue, cl_kernel k, cl_uint dim, const 
 cl_int clEnqueueReadBuffer(cl_command_queue, cl_mem m, cl_bool blocking, size_t off, size_t size, void *ptr, cl_uint,
                            const cl_event *, cl_event *) {
     if (!m || off + size > m->size) return CL_INVALID_VALUE;
+    start_gate();
     ScopedTimer timer(T_READ);
     flush_pending();
     {   // the destination may be (part of) a pinned mirror: remember / forget what it equals
@@ -1076,6 +1113,7 @@ cl_int clEnqueueReadBuffer(cl_command_queue, cl_mem m, cl_bool blocking, size_t 
 cl_int clEnqueueWriteBuffer(cl_command_queue, cl_mem m, cl_bool blocking, size_t off, size_t size, const void *ptr,
                             cl_uint, const cl_event *, cl_event *) {
     if (!m || off + size > m->size) return CL_INVALID_VALUE;
+    start_gate();
     ScopedTimer timer(T_WRITE);
     flush_pending();
     trace_rec(2, m->index, off, size, ptr);
@@ -1133,6 +1171,7 @@ cl_int clEnqueueCopyBuffer(cl_command_queue, cl_mem s, cl_mem d, size_t so, size
 cl_int clEnqueueWriteImage(cl_command_queue, cl_mem img, cl_bool blocking, const size_t *origin, const size_t *region,
                            size_t row_pitch, size_t, const void *ptr, cl_uint, const cl_event *, cl_event *) {
     if (!img || !img->is_image) return CL_INVALID_MEM_OBJECT;
+    start_gate();
     ScopedTimer timer(T_WRITE);
     flush_pending();
     const size_t pitch = row_pitch ? row_pitch : region[0];
@@ -1172,6 +1211,7 @@ void *clEnqueueMapBuffer(cl_command_queue, cl_mem m, cl_bool, cl_map_flags flags
         if (err) *err = CL_INVALID_VALUE;
         return nullptr;
     }
+    start_gate();
     ScopedTimer timer(T_MAP);
     flush_pending();
     const bool discard = (flags & CL_MAP_WRITE_INVALIDATE_REGION) && off == 0 && size == m->size;
