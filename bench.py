@@ -400,8 +400,9 @@ def b200_arm(args, rank, world, local_rank, tmp, config):
                         gen_y4m.write_y4m(y4m, WIDTH, HEIGHT, n, start=(rank * 8 + p) * n)
                     paths.append(y4m)
                     outs.append(os.path.join(tmp, "e2e_%s_%d_%d" % (tag, rank, p)))
-                # start gate (cl_shim.cu start_gate): all P x world instances create their CUDA context (15-20 s for
-                # 32 of them, serialised by the driver), then begin to encode together
+                # start gate (cl_shim.cu start_gate): all P x world instances come up (15-30 s for 32 of them: context
+                # creation, module loading and page pinning are serialised by the driver), encode their key frame
+                # and two inter frames, then go on together; frames 3..W are the common warm-up
                 gate = os.path.join(gate_root, "vp8b200_gate_%s_%s" % (os.environ.get("MASTER_PORT", os.getpid()), tag))
                 if rank == 0:
                     shutil.rmtree(gate, ignore_errors=True)
@@ -411,7 +412,7 @@ def b200_arm(args, rank, world, local_rank, tmp, config):
                 procs = [segments.EncoderProcess(paths[p], outs[p] + ".ivf", ENC_ARGS,
                                                  os.path.join(tmp, "run_%s_%d_%d" % (tag, rank, p)), device=local_rank,
                                                  env_extra=dict(env_more or {}, VP8B200_STATS=outs[p] + ".stats",
-                                                                VP8B200_START_GATE="%s:%d" % (gate, P * world)))
+                                                                VP8B200_START_GATE="%s:%d:3" % (gate, P * world)))
                          for p in range(P)]
                 stamps = [pr.wait() for pr in procs]
                 for st in stamps:
@@ -483,7 +484,7 @@ def b200_arm(args, rank, world, local_rank, tmp, config):
                    "multi_process_fps": fpsP, "mps": bool(mps_used and P > 1), "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                    "shim_kernel_launches_per_step": lps, "timed_frames_per_instance": Ke,
                    "window": "from the moment the last instance has finished its key + warm-up frames to the moment the last "
-                             "instance is done; instances start encoding together (start gate after CUDA context creation)",
+                             "instance is done; instances wait for each other at the start of their third inter frame (start gate, inside the warm-up)",
                    "what": "unmodified reference host (vp8enc.cpp + entropy_host.cpp) + libOpenCL.so.1 shim; Y4M file in, "
                            "IVF file out; all host<->device copies, host intra/entropy work and file I/O included; "
                            "instances encode independent keyframe-delimited segments (no collective)"}

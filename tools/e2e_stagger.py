@@ -33,7 +33,7 @@ if __name__ == "__main__":
         gate = os.path.join(tmp, "gate%d" % rep)
         os.makedirs(gate)
         if extra.pop("GATE", "1") != "0":
-            extra["VP8B200_START_GATE"] = "%s:%d" % (gate, P)
+            extra["VP8B200_START_GATE"] = "%s:%d:3" % (gate, P)
         with segments.MpsDaemon(os.path.join(tmp, "mps%d" % rep)) as d:
             T0 = time.perf_counter()
             procs = [segments.EncoderProcess(paths[p % 8], os.path.join(tmp, "o%d.ivf" % p), ENC_ARGS,

@@ -182,20 +182,35 @@ static bool cuda_init() {
     return true;
 }
 
-// Start gate for multi-instance throughput measurements (VP8B200_START_GATE=<dir>:<count>): at its first
-// enqueue call -- context, buffers and kernels exist, no frame has been touched -- an instance drops a file
-// into <dir> and waits until <count> instances have done so (or 180 s have passed).  Creating 32 CUDA contexts
-// takes the driver 15-20 s, one after the other; without the gate the first instances are done before the last
-// ones start and a short run never sees all of them encoding at the same time.  Not set: no effect.
-static void start_gate() {
-    static bool done = false;
-    if (done) return;
-    done = true;
-    const char *g = getenv("VP8B200_START_GATE");
-    const char *colon = g ? strrchr(g, ':') : nullptr;
-    if (!colon || colon == g) return;
-    const std::string dir(g, colon - g);
-    const int want = atoi(colon + 1);
+// Start gate for multi-instance throughput measurements (VP8B200_START_GATE=<dir>:<count>[:<frame>]): when the
+// host starts its <frame>-th inter frame (its <frame>-th reset_vectors launch; default 0 = at its first enqueue
+// call) an instance drops a file into <dir> and waits until <count> instances have done so (or 180 s have
+// passed).  Bringing up 32 instances takes the driver 15-30 s, one after the other (context creation, then module
+// loading and page pinning during the first frames); without the gate the first instances are done before the
+// last ones start and a short run never sees all of them encoding at the same time.  Not set: no effect.
+static void start_gate(bool inter_frame_start) {
+    static int state = -1, frame = 0, seen = 0;  // state: -1 not parsed, 0 armed, 1 passed / off
+    static std::string dir;
+    static int want = 0;
+    if (state == 1) return;
+    if (state < 0) {
+        state = 1;
+        const char *g = getenv("VP8B200_START_GATE");
+        if (!g || !*g) return;
+        std::string spec(g);
+        size_t c1 = spec.find(':');
+        if (c1 == std::string::npos || c1 == 0) return;
+        size_t c2 = spec.find(':', c1 + 1);
+        dir = spec.substr(0, c1);
+        want = atoi(spec.substr(c1 + 1, c2 == std::string::npos ? std::string::npos : c2 - c1 - 1).c_str());
+        frame = c2 == std::string::npos ? 0 : atoi(spec.substr(c2 + 1).c_str());
+        state = 0;
+    }
+    if (frame > 0) {
+        if (!inter_frame_start || ++seen < frame) return;
+    }
+    state = 1;
+    cudaStreamSynchronize(g_stream);
     char name[64];
     snprintf(name, sizeof(name), "/ready.%d", (int)getpid());
     if (FILE *f = fopen((dir + name).c_str(), "w")) fclose(f);
@@ -212,7 +227,6 @@ static void start_gate() {
         timespec ts = {0, 2000000L};
         nanosleep(&ts, nullptr);
     }
-    g_ns_start = now_ns();
 }
 
 // Waits for everything issued on the stream.  VP8B200_SYNC=sleep polls an event with short sleeps in
@@ -1073,7 +1087,7 @@ cl_int clEnqueueNDRangeKernel(cl_command_queue, cl_kernel k, cl_uint dim, const 
     if (dim != 1 || !gsz) return CL_INVALID_WORK_DIMENSION;
     for (int i = 0; i < kKernels[k->id].nargs; ++i)
         if (!k->set[i]) return CL_INVALID_KERNEL_ARGS;
-    start_gate();
+    start_gate(k->id == K_RESET_VECTORS);
     ScopedTimer timer(k->id >= K_COUNT_PROBS ? T_HOST_KERNEL : T_LAUNCH);
     return dispatch(k, gsz[0]);
 }
@@ -1081,7 +1095,7 @@ cl_int clEnqueueNDRangeKernel(cl_command_queue, cl_kernel k, cl_uint dim, const 
 cl_int clEnqueueReadBuffer(cl_command_queue, cl_mem m, cl_bool blocking, size_t off, size_t size, void *ptr, cl_uint,
                            const cl_event *, cl_event *) {
     if (!m || off + size > m->size) return CL_INVALID_VALUE;
-    start_gate();
+    start_gate(false);
     ScopedTimer timer(T_READ);
     flush_pending();
     {   // the destination may be (part of) a pinned mirror: remember / forget what it equals
@@ -1113,7 +1127,7 @@ cl_int clEnqueueReadBuffer(cl_command_queue, cl_mem m, cl_bool blocking, size_t 
 cl_int clEnqueueWriteBuffer(cl_command_queue, cl_mem m, cl_bool blocking, size_t off, size_t size, const void *ptr,
                             cl_uint, const cl_event *, cl_event *) {
     if (!m || off + size > m->size) return CL_INVALID_VALUE;
-    start_gate();
+    start_gate(false);
     ScopedTimer timer(T_WRITE);
     flush_pending();
     trace_rec(2, m->index, off, size, ptr);
@@ -1171,7 +1185,7 @@ cl_int clEnqueueCopyBuffer(cl_command_queue, cl_mem s, cl_mem d, size_t so, size
 cl_int clEnqueueWriteImage(cl_command_queue, cl_mem img, cl_bool blocking, const size_t *origin, const size_t *region,
                            size_t row_pitch, size_t, const void *ptr, cl_uint, const cl_event *, cl_event *) {
     if (!img || !img->is_image) return CL_INVALID_MEM_OBJECT;
-    start_gate();
+    start_gate(false);
     ScopedTimer timer(T_WRITE);
     flush_pending();
     const size_t pitch = row_pitch ? row_pitch : region[0];
@@ -1211,7 +1225,7 @@ void *clEnqueueMapBuffer(cl_command_queue, cl_mem m, cl_bool, cl_map_flags flags
         if (err) *err = CL_INVALID_VALUE;
         return nullptr;
     }
-    start_gate();
+    start_gate(false);
     ScopedTimer timer(T_MAP);
     flush_pending();
     const bool discard = (flags & CL_MAP_WRITE_INVALIDATE_REGION) && off == 0 && size == m->size;

@@ -27,6 +27,20 @@ __device__ __forceinline__ void wht_bf(int a0, int a1, int a2, int a3, int &o0, 
     const int a = a0 + a3, b = a1 + a2, c = a1 - a2, d = a0 - a3;
     o0 = a + b; o1 = c + d; o2 = a - b; o3 = d - c;
 }
+// element r of wht_bf(a0, a1, a2, a3)
+__device__ __forceinline__ int wht_pick(int a0, int a1, int a2, int a3, int r) {
+    const int a = a0 + a3, b = a1 + a2, c = a1 - a2, d = a0 - a3;
+    const int p = (r & 1) ? d : a, q = (r & 1) ? c : b;
+    return (r & 2) ? p - q : p + q;
+}
+// Truncating x / q through m = magic(q): |x| * m >> 32 with the sign put back.  m * q = 2^32 + e with 0 <= e < q,
+// so the quotient is exact while |x| * e < 2^32; quantisers are <= 440 and the dividends below 2^18.
+// q == 1 (m would be 2^32) is encoded as m == 0.
+__device__ __forceinline__ uint32_t magic(int q) { return q == 1 ? 0u : 0xffffffffu / (uint32_t)q + 1u; }
+__device__ __forceinline__ int div_magic(int x, uint32_t m) {
+    const int r = (int)__umulhi((uint32_t)abs(x), m);
+    return m == 0u ? x : (x < 0 ? -r : r);
+}
 __device__ __forceinline__ void idct1d(int i0, int i1, int i2, int i3, int &o0, int &o1, int &o2, int &o3) {
     const int a1 = i0 + i2, b1 = i0 - i2;
     const int c1 = ((i1 * 35468) >> 16) - (i3 + ((i3 * 20091) >> 16));
@@ -90,8 +104,7 @@ k_mb_fused(const uint8_t *__restrict__ cur_y, const uint8_t *__restrict__ cur_u,
            float *__restrict__ MB_SSIM, uint8_t *__restrict__ rec_y, uint8_t *__restrict__ rec_u,
            uint8_t *__restrict__ rec_v, const vp8b200_segment_data *__restrict__ SD, float SSIM_target, int width,
            int height, int mb_count) {
-    __shared__ uint8_t s_cur[FUSED_WARPS][384], s_rec[FUSED_WARPS][384];  // Y 16x16 | U 8x8 | V 8x8, row-major each
-    __shared__ int s_dc[FUSED_WARPS][16];
+    __shared__ __align__(16) uint8_t s_cur[FUSED_WARPS][384], s_rec[FUSED_WARPS][384];  // Y 16x16 | U 8x8 | V 8x8, row-major each
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mb = blockIdx.x * FUSED_WARPS + warp;
     if (mb >= mb_count) return;  // whole warp
@@ -141,6 +154,7 @@ k_mb_fused(const uint8_t *__restrict__ cur_y, const uint8_t *__restrict__ cur_u,
         const Quants Q = derive_quants(SD, seg);
         const int dc_q = plane == 0 ? (parts == ARE16x16 ? 1 : Q.y_dc) : Q.uv_dc;
         const int ac_q = plane == 0 ? Q.y_ac : Q.uv_ac;
+        const uint32_t mdc = magic(dc_q), mac = magic(ac_q), my2_dc = magic(Q.y2_dc), my2_ac = magic(Q.y2_ac);
         int coef[16];  // quantised, raster order
         if (has_block) {
             int o[16];
@@ -157,51 +171,35 @@ k_mb_fused(const uint8_t *__restrict__ cur_y, const uint8_t *__restrict__ cur_u,
             for (int r = 0; r < 4; ++r) {
                 const int a1 = o[4 * r] + o[4 * r + 3], d1 = o[4 * r] - o[4 * r + 3];
                 const int b1 = o[4 * r + 1] + o[4 * r + 2], c1 = o[4 * r + 1] - o[4 * r + 2];
-                coef[4 * r + 0] = ((a1 + b1 + 7) >> 4) / (r == 0 ? dc_q : ac_q);
-                coef[4 * r + 2] = ((a1 - b1 + 7) >> 4) / ac_q;
-                coef[4 * r + 1] = (((c1 * 2217 + d1 * 5352 + 12000) >> 16) + (d1 != 0)) / ac_q;
-                coef[4 * r + 3] = ((d1 * 2217 - c1 * 5352 + 51000) >> 16) / ac_q;
+                coef[4 * r + 0] = div_magic((a1 + b1 + 7) >> 4, r == 0 ? mdc : mac);
+                coef[4 * r + 2] = div_magic((a1 - b1 + 7) >> 4, mac);
+                coef[4 * r + 1] = div_magic(((c1 * 2217 + d1 * 5352 + 12000) >> 16) + (d1 != 0), mac);
+                coef[4 * r + 3] = div_magic((d1 * 2217 - c1 * 5352 + 51000) >> 16, mac);
             }
             coef[0] = (int)(short)coef[0];  // the record stores int16
         }
-        // Y2: WHT of the 16 luma DCs, reconstructed DCs go back into the luma blocks (Q9)
+        // Y2: WHT of the 16 luma DCs, reconstructed DCs go back into the luma blocks (Q9).  Lane i < 16 holds the
+        // DC of luma block i and computes element i of every butterfly pass from its row / column, fetched with
+        // shuffles (parts is warp-uniform, all lanes take part; lanes >= 16 compute values nobody uses).
         if (parts == ARE16x16) {
-            if (lane < 16) s_dc[warp][lane] = coef[0];
-            __syncwarp();
-            if (lane == 24) {
-                int L[16], t[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) L[i] = s_dc[warp][i];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) wht_bf(L[c], L[4 + c], L[8 + c], L[12 + c], t[c], t[4 + c], t[8 + c], t[12 + c]);
-#pragma unroll
-                for (int r = 0; r < 4; ++r)
-                    wht_bf(t[4 * r], t[4 * r + 1], t[4 * r + 2], t[4 * r + 3], L[4 * r], L[4 * r + 1], L[4 * r + 2], L[4 * r + 3]);
-                __align__(16) short y2[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int qq = i == 0 ? Q.y2_dc : Q.y2_ac;
-                    int vv = L[i];
-                    vv += (vv > 0);
-                    vv >>= 1;
-                    vv /= qq;
-                    y2[inv_zz(i)] = (short)vv;
-                    L[i] = vv * qq;
-                }
-                int4 *d4 = reinterpret_cast<int4 *>(MB + (size_t)mb * 400 + 24 * 16);
-                d4[0] = reinterpret_cast<const int4 *>(y2)[0];
-                d4[1] = reinterpret_cast<const int4 *>(y2)[1];
-#pragma unroll
-                for (int r = 0; r < 4; ++r)
-                    wht_bf(L[4 * r], L[4 * r + 1], L[4 * r + 2], L[4 * r + 3], t[4 * r], t[4 * r + 1], t[4 * r + 2], t[4 * r + 3]);
-#pragma unroll
-                for (int c = 0; c < 4; ++c) wht_bf(t[c], t[4 + c], t[8 + c], t[12 + c], L[c], L[4 + c], L[8 + c], L[12 + c]);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) s_dc[warp][i] = (int)(short)((L[i] + 3) >> 3);
-            }
-            __syncwarp();
-            if (lane < 16) coef[0] = s_dc[warp][lane];
-            __syncwarp();
+            const int col = lane & 3, row4 = lane & 12, r_out = (lane >> 2) & 3;
+            int v = lane < 16 ? coef[0] : 0;
+            v = wht_pick(__shfl_sync(0xffffffffu, v, col), __shfl_sync(0xffffffffu, v, col + 4),
+                         __shfl_sync(0xffffffffu, v, col + 8), __shfl_sync(0xffffffffu, v, col + 12), r_out);
+            v = wht_pick(__shfl_sync(0xffffffffu, v, row4), __shfl_sync(0xffffffffu, v, row4 + 1),
+                         __shfl_sync(0xffffffffu, v, row4 + 2), __shfl_sync(0xffffffffu, v, row4 + 3), col);
+            const bool dc = (lane & 15) == 0;
+            const int qq = dc ? Q.y2_dc : Q.y2_ac;
+            v += (v > 0);
+            v >>= 1;
+            v = div_magic(v, dc ? my2_dc : my2_ac);
+            if (lane < 16) MB[(size_t)mb * 400 + 24 * 16 + ((0xFEA9DB83C7426510ULL >> (4 * lane)) & 15)] = (short)v;
+            v *= qq;
+            v = wht_pick(__shfl_sync(0xffffffffu, v, row4), __shfl_sync(0xffffffffu, v, row4 + 1),
+                         __shfl_sync(0xffffffffu, v, row4 + 2), __shfl_sync(0xffffffffu, v, row4 + 3), col);
+            v = wht_pick(__shfl_sync(0xffffffffu, v, col), __shfl_sync(0xffffffffu, v, col + 4),
+                         __shfl_sync(0xffffffffu, v, col + 8), __shfl_sync(0xffffffffu, v, col + 12), r_out);
+            if (lane < 16) coef[0] = (int)(short)((v + 3) >> 3);
         }
         if (has_block) {
             // the coefficient block in zig-zag position order, two 16-byte stores
@@ -263,29 +261,66 @@ k_mb_fused(const uint8_t *__restrict__ cur_y, const uint8_t *__restrict__ cur_u,
             M2[p] = __fdiv_rn((float)sumr[p], area);
         }
         // 36 ordered chains: quantity qn (0 var(cur), 1 var(rec), 2 cov) x float4 lane kk, per plane.
-        // lanes 0-11: luma (64 elements each); lanes 12-23: U then V (16 elements each)
+        // lanes 0-11: luma (64 elements each); lanes 12-23: U then V (16 elements each).
+        // Chain kk takes every fourth byte of the row-major tile (i = 4m + kk), so a 16-byte load brings four of
+        // its elements.  pixel - mean is formed exactly in one FADD: as_float(0x47000000 | pixel << 8) is
+        // 32768 + pixel, and 32768 + mean is representable (the mean is a multiple of 1/256 below 256), so the
+        // difference equals the reference's fsub(float(pixel), mean), which is exact as well.  The chain itself is
+        // one FFMA per element: fma(d, d, acc) where the reference has mad, fma(d1*d2, 1, acc) == acc + d1*d2 where
+        // it multiplies and adds.
         float acc0 = 0.0f, acc1 = 0.0f;
         if (lane < 24) {
-            const int idx = lane < 12 ? lane : lane - 12;
+            const bool luma = lane < 12;
+            const int idx = luma ? lane : lane - 12;
             const int qn = idx >> 2, kk = idx & 3;
-            const int np = lane < 12 ? 1 : 2;
-            for (int pi = 0; pi < np; ++pi) {
-                const int p = lane < 12 ? 0 : 1 + pi;
-                const int nn = p == 0 ? 16 : 8;
-                const uint8_t *a = &s_cur[warp][p == 0 ? 0 : (p == 1 ? 256 : 320)];
-                const uint8_t *b = &s_rec[warp][p == 0 ? 0 : (p == 1 ? 256 : 320)];
-                const float m1 = M1[p], m2 = M2[p];
-                float acc = 0.0f;
-                for (int y = 0; y < nn; ++y)
-                    for (int g = 0; g < nn / 4; ++g) {
-                        const int i = y * nn + 4 * g + kk;
-                        const float d1 = __fsub_rn((float)a[i], m1), d2 = __fsub_rn((float)b[i], m2);
-                        const bool first = (y == 0 && g == 0);
-                        if (qn == 0) acc = first ? __fmul_rn(d1, d1) : __fmaf_rn(d1, d1, acc);
-                        else if (qn == 1) acc = first ? __fmul_rn(d2, d2) : __fmaf_rn(d2, d2, acc);
-                        else acc = first ? __fmul_rn(d1, d2) : __fadd_rn(acc, __fmul_rn(d1, d2));
-                    }
-                if (pi == 0) acc0 = acc; else acc1 = acc;
+            const bool nonfused = qn == 2;
+            const uint32_t sel = 0x7604u | ((uint32_t)kk << 4);   // byte kk of the word -> bits 8..15 of 0x47000000
+            const uint8_t *tx = (qn == 1 ? s_rec[warp] : s_cur[warp]) + (luma ? 0 : 256);
+            const uint8_t *ty = (qn == 0 ? s_cur[warp] : s_rec[warp]) + (luma ? 0 : 256);
+            const int p0 = luma ? 0 : 1, p1 = luma ? 0 : 2;       // plane of element groups 0-3 and 4-7
+            float kx = __fadd_rn(32768.0f, qn == 1 ? M2[p0] : M1[p0]), ky = __fadd_rn(32768.0f, qn == 0 ? M1[p0] : M2[p0]);
+            float acc = 0.0f;
+            auto group = [&](int g, bool first) {
+                const uint4 wx = *reinterpret_cast<const uint4 *>(tx + 16 * g);
+                const uint4 wy = *reinterpret_cast<const uint4 *>(ty + 16 * g);
+                const uint32_t ax[4] = {wx.x, wx.y, wx.z, wx.w}, ay[4] = {wy.x, wy.y, wy.z, wy.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float x = __fsub_rn(__uint_as_float(__byte_perm(ax[e], 0x47000000u, sel)), kx);
+                    const float y = __fsub_rn(__uint_as_float(__byte_perm(ay[e], 0x47000000u, sel)), ky);
+                    const float pr = __fmul_rn(x, y);
+                    if (first && e == 0) acc = pr;
+                    else acc = __fmaf_rn(nonfused ? pr : x, nonfused ? 1.0f : y, acc);
+                }
+            };
+#pragma unroll
+            for (int g = 0; g < 4; ++g) group(g, g == 0);
+            if (!luma) {  // chroma lanes: U is done, start V
+                acc0 = acc;
+                kx = __fadd_rn(32768.0f, qn == 1 ? M2[p1] : M1[p1]);
+                ky = __fadd_rn(32768.0f, qn == 0 ? M1[p1] : M2[p1]);
+            }
+            {   // group 4: the first element restarts the chain on the chroma lanes only
+                const uint4 wx = *reinterpret_cast<const uint4 *>(tx + 64);
+                const uint4 wy = *reinterpret_cast<const uint4 *>(ty + 64);
+                const uint32_t ax[4] = {wx.x, wx.y, wx.z, wx.w}, ay[4] = {wy.x, wy.y, wy.z, wy.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float x = __fsub_rn(__uint_as_float(__byte_perm(ax[e], 0x47000000u, sel)), kx);
+                    const float y = __fsub_rn(__uint_as_float(__byte_perm(ay[e], 0x47000000u, sel)), ky);
+                    const float pr = __fmul_rn(x, y);
+                    const float nx = __fmaf_rn(nonfused ? pr : x, nonfused ? 1.0f : y, acc);
+                    acc = (e == 0 && !luma) ? pr : nx;
+                }
+            }
+#pragma unroll
+            for (int g = 5; g < 8; ++g) group(g, false);
+            if (luma) {
+#pragma unroll
+                for (int g = 8; g < 16; ++g) group(g, false);
+                acc0 = acc;
+            } else {
+                acc1 = acc;
             }
         }
         // (s0+s1)+s2)+s3 inside every group of four lanes
