@@ -22,6 +22,7 @@ if __name__ == "__main__":
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 46
     reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
     extra = dict(kv.split("=", 1) for kv in sys.argv[4:])
+    sync = extra.pop("SYNC", "yield")
     W = 5
     tmp = tempfile.mkdtemp(prefix="stagger_", dir="/dev/shm")
     paths = []
@@ -32,14 +33,19 @@ if __name__ == "__main__":
     for rep in range(reps):
         gate = os.path.join(tmp, "gate%d" % rep)
         os.makedirs(gate)
-        if extra.pop("GATE", "1") != "0":
+        if extra.get("GATE", "1") != "0":
             extra["VP8B200_START_GATE"] = "%s:%d:3" % (gate, P)
         with segments.MpsDaemon(os.path.join(tmp, "mps%d" % rep)) as d:
             T0 = time.perf_counter()
             procs = [segments.EncoderProcess(paths[p % 8], os.path.join(tmp, "o%d.ivf" % p), ENC_ARGS,
                                              os.path.join(tmp, "run%d" % p),
-                                             env_extra=dict(d.env(), VP8B200_SYNC="yield", **extra)) for p in range(P)]
+                                             env_extra=dict(d.env(), VP8B200_SYNC=sync, VP8B200_STATS=os.path.join(tmp, "st%d.json" % p),
+                                                            **{k: v for k, v in extra.items() if k != "GATE"})) for p in range(P)]
             stamps = [pr.wait() for pr in procs]
+        import json
+        st = [json.load(open(os.path.join(tmp, "st%d.json" % p))) for p in range(P)]
+        keys = [k for k in st[0] if k.startswith(("ms_", "cpu_"))]
+        print("      per frame per instance: " + "  ".join("%s %.2f" % (k, sum(x[k] for x in st) / P / n) for k in keys), flush=True)
         first = sorted(s[0] - T0 for s in stamps)
         warm = sorted(s[W] - T0 for s in stamps)
         last = sorted(s[-1] - T0 for s in stamps)

@@ -349,31 +349,25 @@ k_luma_search_2step(const uint8_t *__restrict__ cur, Search2Refs refs, int width
     }
     __syncthreads();
 
-    // horizontal pass: 5 x-variants x 14 rows x 8 columns per block, four columns per item.  The window line
-    // is three aligned words; an output's six taps are two dp4a on funnel-shifted words (the full-pel variant
-    // is a byte copy: its tap 128 does not fit a signed byte).
-    for (int i = tid; i < S2_BLOCKS * 140; i += S2_THREADS) {
-        const int b = i / 140, q = i % 140;
-        const int var = q / 28, r = (q % 28) >> 1, h = q & 1;
-        const int first = s2_origin(var) + 1;  // window column of tap 0 of output 0, relative to word h
+    // horizontal pass: 5 x-variants x 14 rows x 8 columns per block.  An item is (block, row, half line): its
+    // three window words give all five variants of four columns.  An output's six taps are two dp4a on
+    // funnel-shifted words; the two variants with origin -1 start at window byte 0, the two with origin 0 at
+    // byte 1, so six funnel shifts serve all sixteen filtered outputs.  The full-pel variant is a byte copy (its
+    // tap 128 does not fit a signed byte).  (s/128 then saturate) == saturate(s>>7): the two only differ for
+    // -128<s<0, both give 0.
+    for (int i = tid; i < S2_BLOCKS * 28; i += S2_THREADS) {
+        const int b = i / 28, q = i % 28, r = q >> 1, h = q & 1;
         const uint32_t wa = s_win[b][r][h], wb = s_win[b][r][h + 1], wc = s_win[b][r][h + 2];
-        uint8_t *dst = &s_h[b][var][4 * h][r];
-        if (var == 2) {  // phase 0: the pixel itself (tap 2 of outputs 0..3 = bytes 3..6 of the three words)
-            const uint32_t px = __funnelshift_r(wa, wb, 24);
+        const uint32_t lo[5] = {wa, __funnelshift_r(wa, wb, 8), __funnelshift_r(wa, wb, 16), __funnelshift_r(wa, wb, 24), wb};
+        const uint32_t hi[5] = {wb, __funnelshift_r(wb, wc, 8), __funnelshift_r(wb, wc, 16), __funnelshift_r(wb, wc, 24), wc};
+        uint8_t *dst = &s_h[b][0][4 * h][r];  // + 128 per variant, + 16 per column
 #pragma unroll
-            for (int c = 0; c < 4; ++c) dst[16 * c] = (uint8_t)(px >> (8 * c));
-        } else {
-            const uint32_t lo = var == 3 ? taps_lo(2) : (var == 1 ? taps_lo(6) : taps_lo(4));
-            const uint32_t hi = var == 3 ? taps_hi(2) : (var == 1 ? taps_hi(6) : taps_hi(4));
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int sh = 8 * (first + c);  // 0..32
-                const uint32_t w_lo = sh == 32 ? wb : __funnelshift_r(wa, wb, sh);
-                const uint32_t w_hi = sh == 32 ? wc : __funnelshift_r(wb, wc, sh);
-                const int s = dp4a_u8s8(w_hi, hi, dp4a_u8s8(w_lo, lo, 64));
-                // (s/128 then saturate) == saturate(s>>7): the two only differ for -128<s<0, both give 0
-                dst[16 * c] = (uint8_t)sat8(s >> 7);
-            }
+        for (int c = 0; c < 4; ++c) {
+            dst[0 * 128 + 16 * c] = (uint8_t)sat8(dp4a_u8s8(hi[c], taps_hi(4), dp4a_u8s8(lo[c], taps_lo(4), 64)) >> 7);
+            dst[1 * 128 + 16 * c] = (uint8_t)sat8(dp4a_u8s8(hi[c], taps_hi(6), dp4a_u8s8(lo[c], taps_lo(6), 64)) >> 7);
+            dst[2 * 128 + 16 * c] = (uint8_t)(lo[3] >> (8 * c));  // tap 2 of outputs 0..3 = window bytes 3..6
+            dst[3 * 128 + 16 * c] = (uint8_t)sat8(dp4a_u8s8(hi[c + 1], taps_hi(2), dp4a_u8s8(lo[c + 1], taps_lo(2), 64)) >> 7);
+            dst[4 * 128 + 16 * c] = (uint8_t)sat8(dp4a_u8s8(hi[c + 1], taps_hi(4), dp4a_u8s8(lo[c + 1], taps_lo(4), 64)) >> 7);
         }
     }
     __syncthreads();
