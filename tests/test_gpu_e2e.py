@@ -84,8 +84,11 @@ def test_without_trace_same_bitstream(tmp_path):
 
 
 @pytest.mark.parametrize("env", [{"VP8B200_TOKEN_CAP": "64"}, {"VP8B200_GPU_TOKENS": "0"}, {"VP8B200_ELIDE": "off"},
+                                 {"VP8B200_ELIDE": "track"}, {"VP8B200_ELIDE": "assume"},
+                                 {"VP8B200_ELIDE": "lazy", "VP8B200_GPU_TOKENS": "0"},
                                  {"VP8B200_FUSED": "0"}, {"VP8B200_SYNC": "sleep20"}],
-                         ids=["token-scratch-grows", "host-entropy", "no-elision", "kernel-per-kernel", "sleep-sync"])
+                         ids=["token-scratch-grows", "host-entropy", "no-elision", "eager-downloads", "elision-assumed",
+                              "lazy-host-entropy", "kernel-per-kernel", "sleep-sync"])
 def test_shim_modes_same_bitstream(env, tmp_path):
     """every switch of the shim changes HOW the bytes are produced, never the bytes: decision streams that
     outgrow their scratch, the host-only entropy path, no transfer elision, no fused launches, polling sync.
@@ -101,6 +104,27 @@ def test_shim_modes_same_bitstream(env, tmp_path):
     _trace.run_host(_trace.REF_DIR, d, y4m, os.path.join(d, "ref.ivf"), args)
     _trace.run_host(SHIM_DIR, d, y4m, os.path.join(d, "b200.ivf"), args, env_extra=env)
     assert open(os.path.join(d, "ref.ivf"), "rb").read() == open(os.path.join(d, "b200.ivf"), "rb").read()
+
+
+def test_lazy_downloads_skip_what_the_host_never_reads(tmp_path):
+    """default mode: the coefficient / reconstruction / loop-filtered-frame downloads of inter frames are parked on
+    the device and never cross the bus (the host only forwards those pointers); same bitstream as with eager
+    downloads, far fewer device-to-host bytes"""
+    import json
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_y4m
+    w, h, frames, args = CASES["cif"]
+    d = str(tmp_path)
+    y4m = os.path.join(d, "clip.y4m")
+    gen_y4m.write_y4m(y4m, w, h, frames)
+    stats = {}
+    for mode in ("track", "lazy"):
+        _trace.run_host(SHIM_DIR, d, y4m, os.path.join(d, mode + ".ivf"), args,
+                        env_extra={"VP8B200_ELIDE": mode, "VP8B200_STATS": os.path.join(d, mode + ".json")})
+        stats[mode] = json.load(open(os.path.join(d, mode + ".json")))
+    assert open(os.path.join(d, "track.ivf"), "rb").read() == open(os.path.join(d, "lazy.ivf"), "rb").read()
+    assert stats["lazy"]["d2h_bytes"] < 0.4 * stats["track"]["d2h_bytes"], stats
 
 
 def _write_scene_cut_clip(path, w, h, frames, cut):

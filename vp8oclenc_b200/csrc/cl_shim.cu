@@ -65,6 +65,11 @@ struct _cl_mem {
     size_t host_bytes;           // size of the mirror's mapping (whole pages)
     volatile bool guarded;       // mirror is write-protected: a host store faults and sets host_dirty
     volatile bool host_dirty;    // the host has stored into the mirror since the guard was set
+    // lazy downloads (VP8B200_ELIDE=lazy): the bytes the mirror is supposed to hold are parked in a device-side
+    // shadow; the mirror itself is inaccessible and is only filled when the host touches it
+    void *shadow;                // device snapshot, mirror-sized, allocated on first use
+    bool shadow_valid;           // the shadow holds exactly what the (clean) mirror holds / would hold
+    volatile bool lazy;          // the mirror has not been filled: PROT_NONE, fetch from the shadow on access
 };
 
 enum KernelId {
@@ -141,7 +146,7 @@ static void write_stats() {
 }
 
 static bool g_gpu_tokens = true;       // coefficient decisions prepared on the GPU (see tokens_on_gpu)
-static int g_elide = 2;                // transfer elision: 0 off, 1 assume, 2 track (see "transfer elision" below)
+static int g_elide = 3;                // transfer elision: 0 off, 1 assume, 2 track, 3 track + lazy downloads (see "transfer elision" below)
 static std::vector<cl_mem> g_mirrors;  // objects that own a pinned mirror
 static std::vector<Cmd> g_cmds;  // the deferred command list
 static bool g_fuse = true;       // VP8B200_FUSED=0: execute the list kernel by kernel
@@ -172,8 +177,10 @@ static bool cuda_init() {
     vp8b200_device_info(g_dev_name, sizeof(g_dev_name), &g_sm_count, nullptr, nullptr);
     if (const char *f = getenv("VP8B200_FUSED")) g_fuse = f[0] != '0';
     if (const char *f = getenv("VP8B200_GPU_TOKENS")) g_gpu_tokens = f[0] != '0';
-    if (const char *f = getenv("VP8B200_ELIDE")) g_elide = !strcmp(f, "assume") ? 1 : (!strcmp(f, "track") ? 2 : 0);
-    if (g_elide == 2) install_guard_handler();
+    if (const char *f = getenv("VP8B200_ELIDE"))
+        g_elide = !strcmp(f, "assume") ? 1 : (!strcmp(f, "track") ? 2 : (!strcmp(f, "lazy") ? 3 : 0));
+    if (getenv("VP8CL_TRACE") && g_elide == 3) g_elide = 2;  // the trace records what every read delivered
+    if (g_elide >= 2) install_guard_handler();
     const char *tr = getenv("VP8CL_TRACE");
     if (tr && *tr) g_trace = fopen(tr, "wb");
     atexit(write_stats);
@@ -279,13 +286,22 @@ static GuardSlot g_guard_slots[kMaxGuardSlots];
 static int g_num_guard_slots = 0;
 static struct sigaction g_prev_segv;
 
+static void materialise_in_handler(_cl_mem *m);
 static void guard_fault(int sig, siginfo_t *info, void *uctx) {
     char *addr = (char *)info->si_addr;
     const int n = __atomic_load_n(&g_num_guard_slots, __ATOMIC_ACQUIRE);
     for (int i = 0; i < n; ++i) {
         GuardSlot &g = g_guard_slots[i];
+        if (g.mem && addr >= g.base && addr < g.base + g.bytes && g.mem->lazy) {
+            // first access of the host to a mirror whose download was deferred: fetch it now.  The fault is
+            // synchronous (host code touching mapped memory, never inside a CUDA call), so the runtime may be
+            // used here.  The mirror comes back clean and write-protected; a store faults once more.
+            materialise_in_handler(g.mem);
+            return;  // the faulting access is retried
+        }
         if (g.mem && addr >= g.base && addr < g.base + g.bytes && g.mem->guarded) {
             g.mem->host_dirty = true;
+            g.mem->shadow_valid = false;
             g.mem->guarded = false;
             mprotect(g.base, g.bytes, PROT_READ | PROT_WRITE);
             return;  // the faulting store is retried
@@ -311,13 +327,66 @@ static void install_guard_handler() {
 // the mirror's bytes equal a device copy from now on: watch for host stores
 static void guard(_cl_mem *m) {
     m->host_dirty = false;
-    if (g_elide != 2 || !m->host || m->guarded) return;
+    if (g_elide < 2 || !m->host || m->guarded || m->lazy) return;  // (a parked mirror is inaccessible: tracked anyway)
     m->guarded = true;
     mprotect(m->host, m->host_bytes, PROT_READ);
 }
+// tracking ends: nothing is known about the mirror's bytes any more (a parked mirror stays parked and tracked)
 static void unguard(_cl_mem *m) {
+    if (!m->lazy) m->shadow_valid = false;
     if (!m->guarded) return;
     m->guarded = false;
+    mprotect(m->host, m->host_bytes, PROT_READ | PROT_WRITE);
+}
+
+// ---- lazy downloads (transfer elision, mode "lazy") ------------------------------------------------
+// The host reads the coefficients and the reconstruction into mapped buffers every frame and maps the
+// loop-filtered frame (src/vp8enc.cpp:359-361, 422-433), 12.7 MB per 1080p frame, but only its intra path ever
+// looks at those bytes: for inter frames it forwards the pointers to other device objects.  In this mode a
+// download that fills a whole mirror is parked in a device-side shadow copy (a device-to-device copy on the
+// stream) and the mirror is made inaccessible; forwarding uses the shadow (see device_twin_of_mirror), and the
+// first load or store of the host faults and fetches the bytes then (guard_fault).
+static void fill_from_shadow(_cl_mem *m) {
+    mprotect(m->host, m->host_bytes, PROT_READ | PROT_WRITE);
+    cudaMemcpyAsync(m->host, m->shadow, m->size, cudaMemcpyDeviceToHost, g_stream);
+    g_d2h_bytes += m->size;
+    cudaStreamSynchronize(g_stream);
+    m->lazy = false;
+}
+static void materialise_in_handler(_cl_mem *m) {
+    fill_from_shadow(m);
+    m->guarded = true;  // clean: equals the shadow until the host stores into it
+    m->host_dirty = false;
+    mprotect(m->host, m->host_bytes, PROT_READ);
+}
+// the shim itself is about to access the mirror's bytes (or to change part of them)
+static void materialise(_cl_mem *m) {
+    if (!m->lazy) return;
+    fill_from_shadow(m);
+    m->guarded = false;
+    guard(m);
+}
+// parks `size` bytes of device memory `src` as the contents of m's mirror; false: no shadow, download as usual
+static bool park_download(_cl_mem *m, const void *src) {
+    if (g_elide != 3 || !m->host) return false;
+    if (!m->shadow && cudaMalloc(&m->shadow, m->size ? m->size : 1) != cudaSuccess) {
+        m->shadow = nullptr;
+        return false;
+    }
+    cudaMemcpyAsync(m->shadow, src, m->size, cudaMemcpyDeviceToDevice, g_stream);
+    g_elided_bytes += m->size;
+    m->shadow_valid = true;
+    m->host_dirty = false;
+    m->guarded = false;
+    m->lazy = true;
+    mprotect(m->host, m->host_bytes, PROT_NONE);
+    return true;
+}
+static void drop_shadow(_cl_mem *m) { m->shadow_valid = false; }
+// the mirror is about to be overwritten completely: whatever is parked for it is void
+static void cancel_lazy(_cl_mem *m) {
+    if (!m->lazy) return;
+    m->lazy = false;
     mprotect(m->host, m->host_bytes, PROT_READ | PROT_WRITE);
 }
 
@@ -370,6 +439,7 @@ static cl_mem mirror_of(const void *ptr, size_t size, size_t *off) {
 // device address that currently holds the same bytes as mirror range [off, off+size) of m, or null
 static const void *device_twin_of_mirror(cl_mem m, size_t off) {
     if (!g_elide || m->host_dirty) return nullptr;
+    if (m->shadow_valid) return (const char *)m->shadow + off;
     if (m->twin && m->twin->dev_valid && m->twin->dev_version == m->twin_version) return (const char *)m->twin->dev + off;
     if (m->dev_valid || m->dev_matches_mirror) return (const char *)m->dev + off;
     return nullptr;
@@ -379,13 +449,14 @@ static const void *device_twin_of_mirror(cl_mem m, size_t off) {
 static void *dev_ptr(cl_mem m, bool will_write) {
     if (!m) return nullptr;
     if (!m->dev_valid) {
-        const void *src = (m->twin || m->dev_matches_mirror) ? device_twin_of_mirror(m, 0) : nullptr;
+        const void *src = (m->twin || m->dev_matches_mirror || m->shadow_valid) ? device_twin_of_mirror(m, 0) : nullptr;
         if (src == m->dev) {
             g_elided_bytes += m->size;  // nothing to do: the device copy never stopped being right
         } else if (src) {
             cudaMemcpyAsync(m->dev, src, m->size, cudaMemcpyDeviceToDevice, g_stream);
             g_elided_bytes += m->size;
         } else {
+            materialise(m);
             cudaMemcpyAsync(m->dev, m->host, m->size, cudaMemcpyHostToDevice, g_stream);
             g_h2d_bytes += m->size;
         }
@@ -400,21 +471,30 @@ static void *dev_ptr(cl_mem m, bool will_write) {
     return m->dev;
 }
 // host mirror up to date (downloads and waits)
-static void *host_ptr(cl_mem m, bool will_write, bool discard = false) {
+// lazy_ok: the caller only hands the pointer to the host (clEnqueueMapBuffer); the shim does not look at the bytes
+static void *host_ptr(cl_mem m, bool will_write, bool discard = false, bool lazy_ok = false) {
     if (!m) return nullptr;
     if (!ensure_host_alloc(m)) return nullptr;
     if (!m->host_valid) {
-        if (!discard) {
+        if (discard) {
+            cancel_lazy(m);
+            drop_shadow(m);
+        } else if (!(lazy_ok && park_download(m, m->dev))) {
+            cancel_lazy(m);
+            drop_shadow(m);
             cudaMemcpyAsync(m->host, m->dev, m->size, cudaMemcpyDeviceToHost, g_stream);
             g_d2h_bytes += m->size;
             stream_sync();
         }
         m->host_valid = true;
+    } else if (!lazy_ok) {
+        materialise(m);
     }
     if (will_write) {  // (a host-executed kernel is about to store into the mirror)
         m->dev_valid = false;
         m->dev_matches_mirror = false;
         m->twin = nullptr;
+        drop_shadow(m);
         unguard(m);
     }
     return m->host;
@@ -991,6 +1071,9 @@ static cl_mem new_mem(size_t size, bool image, int w, int h, bool want_host, cl_
     m->host_bytes = 0;
     m->guarded = false;
     m->host_dirty = false;
+    m->shadow = nullptr;
+    m->shadow_valid = false;
+    m->lazy = false;
     // zero-filled like the reference runtime's calloc: block 24 of never-16x16 macroblocks and the
     // nets of never-searched blocks are read before they are first written (Q4, Q9)
     cudaError_t e = cudaMalloc(&m->dev, size ? size : 1);
@@ -1027,10 +1110,11 @@ cl_int clReleaseMemObject(cl_mem m) {
     flush_pending();
     stream_sync();
     cudaFree(m->dev);
+    if (m->shadow) cudaFree(m->shadow);
     if (m->host) {
         for (int i = 0; i < g_num_guard_slots; ++i)
             if (g_guard_slots[i].mem == m) g_guard_slots[i].mem = nullptr;
-        if (m->guarded) mprotect(m->host, m->host_bytes, PROT_READ | PROT_WRITE);
+        if (m->guarded || m->lazy) mprotect(m->host, m->host_bytes, PROT_READ | PROT_WRITE);
         cudaHostUnregister(m->host);
         munmap(m->host, m->host_bytes);
     }
@@ -1098,26 +1182,39 @@ cl_int clEnqueueReadBuffer(cl_command_queue, cl_mem m, cl_bool blocking, size_t 
     start_gate(false);
     ScopedTimer timer(T_READ);
     flush_pending();
+    bool parked = false;
     {   // the destination may be (part of) a pinned mirror: remember / forget what it equals
         size_t moff = 0;
         if (cl_mem t = mirror_of(ptr, size, &moff)) {
+            const bool whole = moff == 0 && size == t->size;
             t->dev_matches_mirror = false;
-            if (m->dev_valid && moff == 0 && off == 0 && size == t->size && size == m->size && t != m) {
-                t->twin = m;
-                t->twin_version = m->dev_version;
-                guard(t);  // (the copy below is DMA: page protection does not concern it)
+            if (whole) cancel_lazy(t);
+            else materialise(t);
+            drop_shadow(t);
+            if (m->dev_valid && whole && off == 0 && size == m->size && t != m) {
+                if (park_download(t, m->dev)) {  // no copy now: the host may never look (see "lazy downloads")
+                    t->twin = nullptr;
+                    parked = true;
+                } else {
+                    t->twin = m;
+                    t->twin_version = m->dev_version;
+                    guard(t);  // (the copy below is DMA: page protection does not concern it)
+                }
             } else {
                 t->twin = nullptr;
                 unguard(t);
             }
         }
     }
-    if (m->dev_valid) {
+    if (parked) {
+        // nothing to wait for
+    } else if (m->dev_valid) {
         cudaError_t e = cudaMemcpyAsync(ptr, (char *)m->dev + off, size, cudaMemcpyDeviceToHost, g_stream);
         g_d2h_bytes += size;
         if (e != cudaSuccess) return cuda_rc(e);
         if (blocking || g_trace) stream_sync();
     } else {
+        materialise(m);
         memcpy(ptr, (char *)m->host + off, size);
     }
     trace_rec(3, m->index, off, size, ptr);
@@ -1134,6 +1231,7 @@ cl_int clEnqueueWriteBuffer(cl_command_queue, cl_mem m, cl_bool blocking, size_t
     if (m->host && ptr == (char *)m->host + off) {
         // the host writes a mapped buffer onto itself (intra_transform(), src/intra_part.h:1122-1124):
         // it has produced new contents there
+        materialise(m);  // (never parked in practice: the host has just stored into it)
         m->host_valid = true;
         m->dev_valid = false;
         m->dev_matches_mirror = false;
@@ -1147,6 +1245,8 @@ cl_int clEnqueueWriteBuffer(cl_command_queue, cl_mem m, cl_bool blocking, size_t
         } else {
             // the current contents live in the host mirror (a buffer the host-executed entropy kernels
             // work on, e.g. coeff_probs): keep it there
+            materialise(m);
+            unguard(m);
             memcpy((char *)m->host + off, ptr, size);
             return CL_SUCCESS;
         }
@@ -1230,7 +1330,7 @@ void *clEnqueueMapBuffer(cl_command_queue, cl_mem m, cl_bool, cl_map_flags flags
     flush_pending();
     const bool discard = (flags & CL_MAP_WRITE_INVALIDATE_REGION) && off == 0 && size == m->size;
     const bool writes = (flags & (CL_MAP_WRITE | CL_MAP_WRITE_INVALIDATE_REGION)) != 0;
-    char *p = (char *)host_ptr(m, false, discard);
+    char *p = (char *)host_ptr(m, false, discard, true);
     if (!p) {
         if (err) *err = CL_MAP_FAILURE;
         return nullptr;
@@ -1244,7 +1344,7 @@ void *clEnqueueMapBuffer(cl_command_queue, cl_mem m, cl_bool, cl_map_flags flags
         m->dev_matches_mirror = m->dev_valid && !discard;
         m->dev_valid = false;
         m->twin = nullptr;
-        if (m->dev_matches_mirror) guard(m);
+        if (m->dev_matches_mirror || m->shadow_valid) guard(m);  // (shadow_valid implies a clean mirror)
         else unguard(m);
     }
     if (err) *err = CL_SUCCESS;
