@@ -60,22 +60,44 @@ __device__ __forceinline__ int sat8(int v) { return min(max(v, 0), 255); }
 // follows, which is exact: d1*5352 = (r0-r3)*42816, d1*2217 = (r0-r3)*17736; rows 0 and 2 of the
 // intermediate are 8*p with p = (r0+r3) +- (r1-r2), and for them (8m+7)>>4 == m>>1 for every
 // integer m, (8c*2217 + 8d*5352 + k)>>16 == (c*17736 + d*42816 + k)>>16, (8d != 0) == (d != 0).
-// BIAS = 0: plain residual.  BIAS = 256: every r[i] carries +256 (16-bit lane arithmetic of
-// luma_search_1step); the bias cancels in all differences, adds 512 to p (1024 to the row sums, an
-// even number, so it comes out of (A+B)>>1 exactly as 1024) and is taken out of the two pass-1
-// products' constants.
-template <int BIAS>
-__device__ __forceinline__ int weight4x4_t(const int (&r)[16]) {
+__device__ __forceinline__ int weight4x4_rows(const int (&o)[16]);
+__device__ __forceinline__ int weight4x4(const int (&r)[16]) {
     int o[16];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int s = r[k] + r[12 + k], t = r[k] - r[12 + k], u = r[4 + k] - r[8 + k];
         const int x = r[8 + k];
-        o[k] = s + u;      // = reference value / 8 (+ 2*BIAS)
-        o[8 + k] = s - u;  // = reference value / 8 (+ 2*BIAS)
-        o[4 + k] = (x * 2217 + t * 42816 + (14500 - BIAS * 2217)) >> 12;
-        o[12 + k] = (t * 17736 - x * 5352 + (7500 + BIAS * 5352)) >> 12;
+        o[k] = s + u;      // = reference value / 8
+        o[8 + k] = s - u;  // = reference value / 8
+        o[4 + k] = (x * 2217 + t * 42816 + 14500) >> 12;
+        o[12 + k] = (t * 17736 - x * 5352 + 7500) >> 12;
     }
+    return weight4x4_rows(o);
+}
+
+// The same cost from per-column features, for searches whose candidates are full-pel shifts of one window
+// (luma_search_1step).  Pass 1 of weight4x4 is linear in the residual before its shift, so it splits into a part
+// of the current block and a part of the predictor column, and a predictor column (4 vertically adjacent window
+// pixels) is shared by every candidate that covers it:
+//   o[k]      = (s+u)(cur) - (s+u)(pred)                 s = p0+p3, t = p0-p3, u = p1-p2, x = p2
+//   o[8+k]    = (s-u)(cur) - (s-u)(pred)
+//   o[4+k]    = ((x*2217 + t*42816 + 14500)(cur) - (x*2217 + t*42816)(pred)) >> 12
+//   o[12+k]   = ((t*17736 - x*5352 + 7500)(cur) - (t*17736 - x*5352)(pred)) >> 12
+// (exact integer identities; the magnitudes stay below 2^25).
+struct ColFeat {
+    int e0, e8, a4, a12;
+};
+__device__ __forceinline__ ColFeat col_features(int p0, int p1, int p2, int p3, int k4, int k12) {
+    const int s = p0 + p3, t = p0 - p3, u = p1 - p2;
+    ColFeat f;
+    f.e0 = s + u;
+    f.e8 = s - u;
+    f.a4 = p2 * 2217 + t * 42816 + k4;
+    f.a12 = t * 17736 - p2 * 5352 + k12;
+    return f;
+}
+// pass 2 of weight4x4 on the intermediate o (rows 0 and 2 are the reference's values / 8)
+__device__ __forceinline__ int weight4x4_rows(const int (&o)[16]) {
     int sum = 0;
 #pragma unroll
     for (int row = 0; row < 4; ++row) {
@@ -87,8 +109,8 @@ __device__ __forceinline__ int weight4x4_t(const int (&r)[16]) {
             f2 = (a - b + 7) >> 4;
             f1 = ((c * 2217 + d * 5352 + 12000) >> 16) + (d != 0);
             f3 = (d * 2217 - c * 5352 + 51000) >> 16;
-        } else {  // a, b, c, d are the reference's values / 8 (a, b carry + 4*BIAS each)
-            f0 = ((a + b) >> 1) - 4 * BIAS;
+        } else {
+            f0 = (a + b) >> 1;
             f2 = (a - b) >> 1;
             f1 = ((c * 17736 + d * 42816 + 12000) >> 16) + (d != 0);
             f3 = (d * 17736 - c * 42816 + 51000) >> 16;
@@ -97,7 +119,6 @@ __device__ __forceinline__ int weight4x4_t(const int (&r)[16]) {
     }
     return sum;
 }
-__device__ __forceinline__ int weight4x4(const int (&r)[16]) { return weight4x4_t<0>(r); }
 
 // quantisers of one segment, derived exactly as the device code of the reference does it
 // in three places (Q11; src/GPU_kernels.cl:1394-1408, 1515-1524, 1568-1582)

@@ -95,7 +95,7 @@ __device__ __forceinline__ void predict4x4(const uint8_t *__restrict__ ref, int 
 }
 
 #ifndef VP8_FUSED_MINCTAS
-#define VP8_FUSED_MINCTAS 8
+#define VP8_FUSED_MINCTAS 5
 #endif
 __global__ void __launch_bounds__(FUSED_WARPS * 32, VP8_FUSED_MINCTAS)
 k_mb_fused(const uint8_t *__restrict__ cur_y, const uint8_t *__restrict__ cur_u, const uint8_t *__restrict__ cur_v,

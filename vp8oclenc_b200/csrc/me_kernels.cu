@@ -45,15 +45,15 @@ __global__ void k_downsample_x2(const uint8_t *__restrict__ src, uint8_t *__rest
 //
 // S1_BLOCKS 8x8 blocks per CTA, 20 threads per block: a thread owns one row of candidates (dy) of
 // one 4x4 sub-block (j) and walks the five dx.  The eight window bytes per line that those five
-// candidates cover are two aligned words held in registers; a candidate's four pixels are a funnel
-// shift away.  Residuals are formed two at a time in 16-bit lanes with a +256 bias per lane (no
-// borrow between lanes), and the bias is folded into the constants of the cost transform
-// (weight4x4_t<256>), so unpacking costs one AND / one shift per pixel.
+// candidates cover are two aligned words held in registers.  No residual is ever formed: the first
+// pass of the cost transform is linear before its shift, so it is computed per COLUMN of the current
+// sub-block (4 columns, once) and of the window (8 columns, each once) and a candidate only subtracts
+// the two (col_features / weight4x4_rows in common.cuh); candidate dx uses window columns dx..dx+3.
 #ifndef VP8_S1_BLOCKS
 #define VP8_S1_BLOCKS 8
 #endif
 #ifndef VP8_S1_MINCTAS
-#define VP8_S1_MINCTAS 8
+#define VP8_S1_MINCTAS 7
 #endif
 constexpr int S1_BLOCKS = VP8_S1_BLOCKS;
 static_assert(S1_BLOCKS % 8 == 0, "threads must fill whole warps (full-mask shuffles)");
@@ -150,33 +150,45 @@ k_luma_search_1step(const uint8_t *__restrict__ cur, Search1Refs refs, int net_w
         const int4 g = s_geo[b];
         const int cx = g.x, cy = g.y, vx = g.z, vy = g.w;
         const bool live = n0 + b < nblocks;
-        uint32_t clo[4], chi[4], w0[4], w1[4];
+        // column features of the current sub-block (once) and of the eight window columns the five candidates
+        // cover (each once, when the first candidate needs it): see col_features in common.cuh
+        uint32_t w0[4], w1[4], cw[4];
 #pragma unroll
         for (int y = 0; y < 4; ++y) {
-            const uint32_t cw = s_cur[b][sy + y][sxw];
-            clo[y] = __byte_perm(cw, 0, 0x4140) + 0x01000100u;  // (c0, c1) + bias
-            chi[y] = __byte_perm(cw, 0, 0x4342) + 0x01000100u;  // (c2, c3) + bias
+            cw[y] = s_cur[b][sy + y][sxw];
             w0[y] = s_win[b][dy + sy + y][sxw];
             w1[y] = s_win[b][dy + sy + y][sxw + 1];
         }
+        ColFeat cf[4], pf[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            cf[k] = col_features((int)__byte_perm(cw[0], 0, 0x4440 + k), (int)__byte_perm(cw[1], 0, 0x4440 + k),
+                                 (int)__byte_perm(cw[2], 0, 0x4440 + k), (int)__byte_perm(cw[3], 0, 0x4440 + k), 14500, 7500);
+        auto window_column = [&](int X) {  // X is a compile-time constant after unrolling
+            const int sel = 0x4440 + (X & 3);
+            return X < 4 ? col_features((int)__byte_perm(w0[0], 0, sel), (int)__byte_perm(w0[1], 0, sel),
+                                        (int)__byte_perm(w0[2], 0, sel), (int)__byte_perm(w0[3], 0, sel), 0, 0)
+                         : col_features((int)__byte_perm(w1[0], 0, sel), (int)__byte_perm(w1[1], 0, sel),
+                                        (int)__byte_perm(w1[2], 0, sel), (int)__byte_perm(w1[3], 0, sel), 0, 0);
+        };
+#pragma unroll
+        for (int X = 0; X < 3; ++X) pf[X] = window_column(X);
         const int py = (short)(cy + vy + dy - 2);
         const bool yok = py >= 0 && py <= height - 8;
         const int ypen = abs(abs(py - cy) - vy);
         unsigned best = 0xffffffffu;
 #pragma unroll
         for (int dx = 0; dx < 5; ++dx) {
-            int r[16];
+            pf[dx + 3] = window_column(dx + 3);
+            int o[16];
 #pragma unroll
-            for (int y = 0; y < 4; ++y) {
-                const uint32_t pw = dx == 0 ? w0[y] : (dx == 4 ? w1[y] : __funnelshift_r(w0[y], w1[y], 8 * dx));
-                const uint32_t dlo = clo[y] - __byte_perm(pw, 0, 0x4140);
-                const uint32_t dhi = chi[y] - __byte_perm(pw, 0, 0x4342);
-                r[4 * y + 0] = (int)(dlo & 0xffffu);
-                r[4 * y + 1] = (int)(dlo >> 16);
-                r[4 * y + 2] = (int)(dhi & 0xffffu);
-                r[4 * y + 3] = (int)(dhi >> 16);
+            for (int k = 0; k < 4; ++k) {
+                o[k] = cf[k].e0 - pf[dx + k].e0;
+                o[8 + k] = cf[k].e8 - pf[dx + k].e8;
+                o[4 + k] = (cf[k].a4 - pf[dx + k].a4) >> 12;
+                o[12 + k] = (cf[k].a12 - pf[dx + k].a12) >> 12;
             }
-            int cost = weight4x4_t<256>(r);  // see common.cuh for the bias algebra
+            int cost = weight4x4_rows(o);
             cost += __shfl_xor_sync(0xffffffffu, cost, 1);
             cost += __shfl_xor_sync(0xffffffffu, cost, 2);
             const int px = (short)(cx + vx + dx - 2);
