@@ -145,7 +145,9 @@ def reference_arm(args, tmp):
     n = 1 + warm + steps
     y4m = os.path.join(tmp, "ref_clip.y4m")
     gen_y4m.write_y4m(y4m, WIDTH, HEIGHT, n)
-    stamps, _ = run_encoder_timed(host_bin, ref_dir, os.path.join(tmp, "ref_run"), y4m, os.path.join(tmp, "ref.ivf"), n)
+    # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1 to its workers)
+    stamps, _ = run_encoder_timed(host_bin, ref_dir, os.path.join(tmp, "ref_run"), y4m, os.path.join(tmp, "ref.ivf"), n,
+                                  env_extra={"OMP_NUM_THREADS": str(os.cpu_count() or 1)})
     dt = stamps[-1] - stamps[warm]  # frame 0 is the key frame, then `warm` untimed inter frames
     fps = steps / dt
     return {"value": fps, "unit": "frames/s", "cores": os.cpu_count(), "kind": "reference",

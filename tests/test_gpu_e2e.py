@@ -106,6 +106,24 @@ def test_shim_modes_same_bitstream(env, tmp_path):
     assert open(os.path.join(d, "ref.ivf"), "rb").read() == open(os.path.join(d, "b200.ivf"), "rb").read()
 
 
+def test_1080p_bench_configuration_byte_identical(tmp_path):
+    """BASELINE configs[1] at full size (1920x1080 padded to 1088 lines, LAST+GOLDEN+ALTREF, 8 partitions, the
+    options bench.py uses): a key frame and seven inter frames through the shim give the reference's bytes.
+    The golden/altref rotation at altref-range 5 puts all three references in play."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_y4m
+    args = ["-qmin", 24, "-qmax", 24, "-g", 150, "-altref-range", 5, "-partitions", 8, "-threads", 12]
+    d = str(tmp_path)
+    y4m = os.path.join(d, "clip.y4m")
+    gen_y4m.write_y4m(y4m, 1920, 1080, 8)
+    _trace.run_host(_trace.REF_DIR, d, y4m, os.path.join(d, "ref.ivf"), args)
+    _trace.run_host(SHIM_DIR, d, y4m, os.path.join(d, "b200.ivf"), args)
+    a = open(os.path.join(d, "ref.ivf"), "rb").read()
+    assert len(a) > 32 + 12 * 8
+    assert a == open(os.path.join(d, "b200.ivf"), "rb").read()
+
+
 def test_lazy_downloads_skip_what_the_host_never_reads(tmp_path):
     """default mode: the coefficient / reconstruction / loop-filtered-frame downloads of inter frames are parked on
     the device and never cross the bus (the host only forwards those pointers); same bitstream as with eager

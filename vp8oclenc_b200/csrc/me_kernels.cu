@@ -231,25 +231,26 @@ k_luma_search_1step(const uint8_t *__restrict__ cur, Search1Refs refs, int net_w
 // the zero vector, six-tap interpolation of the "search flavour" (every horizontally filtered
 // line is saturated before the vertical pass, Q5).
 //
-// S2_BLOCKS 8x8 blocks per CTA.  Per block 20 "six-tap" threads (x-phase xi, 4x4 sub-block j) that
-// each walk the five y-phases of their column of candidates, and 4 threads for the zero-vector
-// candidate.  The horizontally filtered lines are kept transposed (a word = four consecutive lines
-// of one column), so the vertical six taps are two dp4a; the twelve lines a thread needs are loaded
-// once for its five candidates (12 registers), the current sub-block once; the y-phase loop is
+// S2_BLOCKS 8x8 blocks per CTA, 20 threads per block: a thread owns (x-phase xi, 4x4 sub-block j) and walks the
+// five y-phases of its column of candidates.  The horizontally filtered lines are kept transposed (a word =
+// four consecutive lines of one column), so the vertical six taps are two dp4a; the twelve lines a thread needs
+// are loaded once for its five candidates (12 registers), the current sub-block once; the y-phase loop is
 // unrolled, so taps and alignment shifts are immediates and the full-pel phase has no filter at all.
+// The zero-vector candidate is evaluated by one warp during the second, partly filled round of the horizontal
+// pass: no thread is set aside for it, the CTA is five full warps and five CTAs fit an SM.
 #ifndef VP8_S2_BLOCKS
 #define VP8_S2_BLOCKS 8
 #endif
 #ifndef VP8_S2_MINCTAS
-#define VP8_S2_MINCTAS 4
+#define VP8_S2_MINCTAS 5
 #endif
 #ifndef VP8_S2_UNROLL
 #define VP8_S2_UNROLL 1
 #endif
 constexpr int S2_BLOCKS = VP8_S2_BLOCKS;
 static_assert(S2_BLOCKS % 8 == 0, "the six-tap threads must fill whole warps (full-mask shuffles)");
-constexpr int S2_SIX = S2_BLOCKS * 20;           // six-tap threads
-constexpr int S2_THREADS = S2_BLOCKS * 24;       // + zero-vector threads
+constexpr int S2_THREADS = S2_BLOCKS * 20;
+static_assert(S2_BLOCKS * 28 - S2_THREADS <= S2_THREADS - 32, "round 2 of the horizontal pass must leave a warp free");
 
 // x/y phase variants of the five offsets -2..+2 quarter pels around a full-pel position:
 // integer origin offset (-1,-1,0,0,0) and eighth-pel filter phase (4,6,0,2,4)
@@ -350,7 +351,7 @@ k_luma_search_2step(const uint8_t *__restrict__ cur, Search2Refs refs, int width
             for (int c = 0; c < 14; ++c) dst[c] = __ldg(line + clampi(x0 + c, 0, width - 1));
         }
     }
-    // (S2_THREADS - S2_BLOCKS * 16 = 64 < 112: most threads do one of the two jobs; going backwards spreads them)
+    // (S2_THREADS - S2_BLOCKS * 16 = 32 < 112: going backwards spreads the two jobs over the threads)
     if (tid >= S2_THREADS - S2_BLOCKS * 16) {
         const int t = S2_THREADS - 1 - tid;
         const int b = t >> 4, r = (t >> 1) & 7, h = t & 1;
@@ -382,13 +383,28 @@ k_luma_search_2step(const uint8_t *__restrict__ cur, Search2Refs refs, int width
             dst[4 * 128 + 16 * c] = (uint8_t)sat8(dp4a_u8s8(hi[c + 1], taps_hi(4), dp4a_u8s8(lo[c + 1], taps_lo(4), 64)) >> 7);
         }
     }
+    // candidate #25, the zero vector (full-pel, no penalty), on the last warp, which has no item in round 2:
+    // four threads per block, one 4x4 sub-block each
+    if (tid >= S2_THREADS - 32) {
+        const int t = tid - (S2_THREADS - 32), b = t >> 2, j = t & 3;
+        const int sx = j >> 1, sy = (j & 1) * 4;
+        int r[16];
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+            const uint32_t cw = s_cur[b][sy + y][sx], zw = s_zero[b][sy + y][sx];
+#pragma unroll
+            for (int x = 0; x < 4; ++x) r[4 * y + x] = (int)__byte_perm(cw, 0, 0x4440 + x) - (int)__byte_perm(zw, 0, 0x4440 + x);
+        }
+        int cost = weight4x4(r);
+        cost += __shfl_xor_sync(0xffffffffu, cost, 1);
+        cost += __shfl_xor_sync(0xffffffffu, cost, 2);
+        if (j == 0 && n0 + b < nblocks && cost < 0x7fff) atomicMin(&s_key[b], ((unsigned)cost << 5) | 25u);
+    }
     __syncthreads();
 
     {
-        const bool six = tid < S2_SIX;
-        const int b = six ? tid / 20 : (tid - S2_SIX) >> 2;
-        const int u = six ? tid % 20 : 0;
-        const int xi = u >> 2, j = tid & 3;             // 20 and S2_SIX are multiples of 4
+        const int b = tid / 20, u = tid % 20;
+        const int xi = u >> 2, j = tid & 3;             // 20 is a multiple of 4
         const int sx = j >> 1, sy = (j & 1) * 4;        // sub-block (x word, y row offset); order as dx4/dy4
         const bool live = n0 + b < nblocks;
         int bx, by, v0x, v0y;
@@ -398,54 +414,40 @@ k_luma_search_2step(const uint8_t *__restrict__ cur, Search2Refs refs, int width
         for (int y = 0; y < 4; ++y) cu[y] = s_cur[b][sy + y][sx];
         unsigned best = 0xffffffffu;
         int r[16];
-        if (six) {
-            uint32_t tl[4][3];  // lines sy .. sy+11 of the four columns of this x-phase (lines >= 14 are never used)
+        uint32_t tl[4][3];  // lines sy .. sy+11 of the four columns of this x-phase (lines >= 14 are never used)
 #pragma unroll
-            for (int x = 0; x < 4; ++x) {
-                const uint32_t *cw = reinterpret_cast<const uint32_t *>(&s_h[b][xi][4 * sx + x][sy]);
-                tl[x][0] = cw[0]; tl[x][1] = cw[1]; tl[x][2] = cw[2];
-            }
-            const int qx = (short)(bx * 4 + v0x + xi - 2);
-            const bool xok = qx >= 0 && qx <= width * 4 - 32;
-            // y-phases 4,6,0,2,4 with first line 0,0,1,1,1 (s2_origin + 1).  The loop is kept rolled (the
-            // branches are warp-uniform): unrolled, the five bodies get interleaved and spill.
+        for (int x = 0; x < 4; ++x) {
+            const uint32_t *cw = reinterpret_cast<const uint32_t *>(&s_h[b][xi][4 * sx + x][sy]);
+            tl[x][0] = cw[0]; tl[x][1] = cw[1]; tl[x][2] = cw[2];
+        }
+        const int qx = (short)(bx * 4 + v0x + xi - 2);
+        const bool xok = qx >= 0 && qx <= width * 4 - 32;
+        // y-phases 4,6,0,2,4 with first line 0,0,1,1,1 (s2_origin + 1)
 #if VP8_S2_UNROLL
 #pragma unroll
 #else
 #pragma unroll 1
 #endif
-            for (int yi = 0; yi < 5; ++yi) {
-                if (yi < 2) {
-                    s2_residual(tl, 0, yi == 0 ? taps_lo(4) : taps_lo(6), yi == 0 ? taps_hi(4) : taps_hi(6), cu, r);
-                } else if (yi == 2) {
+        for (int yi = 0; yi < 5; ++yi) {
+            if (yi < 2) {
+                s2_residual(tl, 0, yi == 0 ? taps_lo(4) : taps_lo(6), yi == 0 ? taps_hi(4) : taps_hi(6), cu, r);
+            } else if (yi == 2) {
 #pragma unroll
-                    for (int y = 0; y < 4; ++y)
+                for (int y = 0; y < 4; ++y)
 #pragma unroll
-                        for (int x = 0; x < 4; ++x)  // full-pel phase: line 1+2+y itself
-                            r[4 * y + x] = (int)__byte_perm(cu[y], 0, 0x4440 + x) -
-                                           (int)__byte_perm(tl[x][(3 + y) >> 2], 0, 0x4440 + ((3 + y) & 3));
-                } else {
-                    s2_residual(tl, 1, yi == 3 ? taps_lo(2) : taps_lo(4), yi == 3 ? taps_hi(2) : taps_hi(4), cu, r);
-                }
-                int cost = weight4x4(r);
-                cost += __shfl_xor_sync(0xffffffffu, cost, 1);
-                cost += __shfl_xor_sync(0xffffffffu, cost, 2);
-                cost += (abs(xi - 2) + abs(yi - 2)) * 32;
-                const int qy = (short)(by * 4 + v0y + yi - 2);
-                const bool valid = xok && qy >= 0 && qy <= height * 4 - 32;
-                if (valid && cost < 0x7fff) best = min(best, ((unsigned)cost << 5) | (unsigned)(yi * 5 + xi));
-            }
-        } else {  // candidate #25: the zero vector, full-pel, no penalty
-#pragma unroll
-            for (int y = 0; y < 4; ++y) {
-                const uint32_t zw = s_zero[b][sy + y][sx];
-#pragma unroll
-                for (int x = 0; x < 4; ++x) r[4 * y + x] = (int)__byte_perm(cu[y], 0, 0x4440 + x) - (int)((zw >> (8 * x)) & 255);
+                    for (int x = 0; x < 4; ++x)  // full-pel phase: line 1+2+y itself
+                        r[4 * y + x] = (int)__byte_perm(cu[y], 0, 0x4440 + x) -
+                                       (int)__byte_perm(tl[x][(3 + y) >> 2], 0, 0x4440 + ((3 + y) & 3));
+            } else {
+                s2_residual(tl, 1, yi == 3 ? taps_lo(2) : taps_lo(4), yi == 3 ? taps_hi(2) : taps_hi(4), cu, r);
             }
             int cost = weight4x4(r);
             cost += __shfl_xor_sync(0xffffffffu, cost, 1);
             cost += __shfl_xor_sync(0xffffffffu, cost, 2);
-            if (cost < 0x7fff) best = ((unsigned)cost << 5) | 25u;
+            cost += (abs(xi - 2) + abs(yi - 2)) * 32;
+            const int qy = (short)(by * 4 + v0y + yi - 2);
+            const bool valid = xok && qy >= 0 && qy <= height * 4 - 32;
+            if (valid && cost < 0x7fff) best = min(best, ((unsigned)cost << 5) | (unsigned)(yi * 5 + xi));
         }
         if (j == 0 && live && best != 0xffffffffu) atomicMin(&s_key[b], best);
     }
