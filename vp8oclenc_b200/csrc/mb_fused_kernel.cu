@@ -50,36 +50,56 @@ __device__ __forceinline__ void idct1d(int i0, int i1, int i2, int i3, int &o0, 
 
 // six-tap prediction of one 4x4 block, "predictor flavour" (construct, src/GPU_kernels.cl:574-774):
 // lines Y-2..Y+3 saturate, lines Y+4..Y+6 wrap (Q5)
+__device__ __forceinline__ int dp4a_px_taps(uint32_t px, uint32_t taps, int acc) {  // unsigned pixels x signed taps
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(px), "r"(taps), "r"(acc));
+    return d;
+}
 __device__ __forceinline__ void predict4x4(const uint8_t *__restrict__ ref, int w, int h, int ox, int oy, int fx, int fy,
                                            int (&pred)[16]) {
     int line[9][4];
-    const int t0 = c_sixtap[fx][0], t1 = c_sixtap[fx][1], t2 = c_sixtap[fx][2], t3 = c_sixtap[fx][3],
-              t4 = c_sixtap[fx][4], t5 = c_sixtap[fx][5];
+    // Horizontal pass: the six taps of an output are two dp4a over funnel-shifted words of the window line.
+    // The taps are packed as signed bytes; phase 0's single tap 128 wraps to -128, so its sum is taken negative.
+    const uint32_t tlo = (uint32_t)(c_sixtap[fx][0] & 255) | ((uint32_t)(c_sixtap[fx][1] & 255) << 8) |
+                         ((uint32_t)(c_sixtap[fx][2] & 255) << 16) | ((uint32_t)(c_sixtap[fx][3] & 255) << 24);
+    const uint32_t thi = (uint32_t)(c_sixtap[fx][4] & 255) | ((uint32_t)(c_sixtap[fx][5] & 255) << 8);
+    const int sgn = fx == 0 ? -1 : 1;
     // the 9x9 window needs no clamping and the three aligned words per line stay inside the row
     const bool inside = ox >= 2 && ox + 10 <= w && oy >= 2 && oy + 6 < h;
     const int off = (ox - 2) & 3;
+    uint32_t wa[9], wb[9], wc[9];  // window bytes 0-3, 4-7, 8.. of every line
+    if (inside) {
+        const uint32_t *row = reinterpret_cast<const uint32_t *>(ref + (size_t)(oy - 2) * w + ((ox - 2) & ~3));
 #pragma unroll
-    for (int l = 0; l < 9; ++l) {
-        int p[9];
-        if (inside) {
-            // 9 unaligned bytes out of three aligned words
-            const uint32_t *row = reinterpret_cast<const uint32_t *>(ref + (size_t)(oy - 2 + l) * w + ((ox - 2) & ~3));
-            const uint32_t w0 = __ldg(row), w1 = __ldg(row + 1), w2 = __ldg(row + 2);
-            const uint32_t a = __funnelshift_r(w0, w1, 8 * off), b = __funnelshift_r(w1, w2, 8 * off);
-            const uint32_t c = w2 >> (8 * off);
-            p[0] = a & 255; p[1] = (a >> 8) & 255; p[2] = (a >> 16) & 255; p[3] = a >> 24;
-            p[4] = b & 255; p[5] = (b >> 8) & 255; p[6] = (b >> 16) & 255; p[7] = b >> 24;
-            p[8] = c & 255;
-        } else {
+        for (int l = 0; l < 9; ++l) {  // 9 unaligned bytes out of three aligned words
+            const uint32_t *rl = reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(row) + (size_t)l * w);
+            const uint32_t w0 = __ldg(rl), w1 = __ldg(rl + 1), w2 = __ldg(rl + 2);
+            wa[l] = __funnelshift_r(w0, w1, 8 * off);
+            wb[l] = __funnelshift_r(w1, w2, 8 * off);
+            wc[l] = w2 >> (8 * off);
+        }
+    } else {
+#pragma unroll
+        for (int l = 0; l < 9; ++l) {
             const uint8_t *row = ref + (size_t)clampi(oy - 2 + l, 0, h - 1) * w;
+            uint32_t p[9];
 #pragma unroll
             for (int c = 0; c < 9; ++c) p[c] = __ldg(row + clampi(ox - 2 + c, 0, w - 1));
+            wa[l] = p[0] | (p[1] << 8) | (p[2] << 16) | (p[3] << 24);
+            wb[l] = p[4] | (p[5] << 8) | (p[6] << 16) | (p[7] << 24);
+            wc[l] = p[8];
         }
+    }
+#pragma unroll
+    for (int l = 0; l < 9; ++l) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            int s = 64 + t0 * p[c] + t1 * p[c + 1] + t2 * p[c + 2] + t3 * p[c + 3] + t4 * p[c + 4] + t5 * p[c + 5];
-            s /= 128;  // truncating
-            line[l][c] = (l < 6) ? sat8(s) : (s & 255);
+            const uint32_t lo = c ? __funnelshift_r(wa[l], wb[l], 8 * c) : wa[l];
+            const uint32_t hi = c ? __funnelshift_r(wb[l], wc[l], 8 * c) : wb[l];
+            const int s = 64 + sgn * dp4a_px_taps(hi, thi, dp4a_px_taps(lo, tlo, 0));
+            // s / 128 truncates: under the saturation that is s >> 7 (both give 0 for negative s), under the
+            // wrap of lines 6..8 it is not
+            line[l][c] = (l < 6) ? sat8(s >> 7) : (((s + ((s >> 31) & 127)) >> 7) & 255);
         }
     }
     const int u0 = c_sixtap[fy][0], u1 = c_sixtap[fy][1], u2 = c_sixtap[fy][2], u3 = c_sixtap[fy][3],
