@@ -13,6 +13,7 @@
 #include <emmintrin.h>
 
 #include <condition_variable>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <mutex>
@@ -319,10 +320,24 @@ class Pool {
     unsigned long generation_ = 0;
 };
 
+// VP8B200_ENTROPY_THREADS=<k> caps the threads a frame's partitions are spread over (default: one per partition).
+// With more encoder instances than cores on the machine fewer, longer jobs cost fewer wake-ups.
 template <class F>
 void for_each_partition(int n, F f) {
     static Pool *pool = new Pool;  // never destroyed: its threads outlive static destruction
-    pool->run(n, std::function<void(int)>(f));
+    static const int cap = [] {
+        const char *e = getenv("VP8B200_ENTROPY_THREADS");
+        const int k = e ? atoi(e) : 0;
+        return k > 0 ? k : 1 << 30;
+    }();
+    const int T = n < cap ? n : cap;
+    if (T == n) {
+        pool->run(n, std::function<void(int)>(f));
+    } else {
+        pool->run(T, std::function<void(int)>([&](int t) {
+            for (int p = t; p < n; p += T) f(p);
+        }));
+    }
 }
 
 }  // namespace

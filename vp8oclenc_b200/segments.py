@@ -21,7 +21,7 @@ import time
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 SHIM_DIR = os.path.join(PKG, "lib")
-HOST_BIN = os.path.join(PKG, "bin", "vp8enc")
+HOST_BIN = os.environ.get("VP8B200_HOST_BIN") or os.path.join(PKG, "bin", "vp8enc")
 
 GPU_STUB = "// vp8oclenc_b200 placeholder: kernels are built into libOpenCL.so.1; program = GPU (luma_search_1step)\n"
 CPU_STUB = "// vp8oclenc_b200 placeholder: kernels are built into libOpenCL.so.1; program = CPU (encode_coefficients)\n"
