@@ -389,18 +389,22 @@ def b200_arm(args, rank, world, local_rank, tmp, config):
         if os.path.exists(segments.HOST_BIN):
             # every instance encodes 1 key + W warm-up + Ke timed frames; Ke >= 80 so that the timed window is long
             # against the scheduling noise of P processes on the host cores
-            Ke = max(K, 80)
+            Ke = max(K, 120)
             n = 1 + W + Ke
+            distinct = 8 if world == 1 else (4 if world == 2 else 2)  # clips per rank (they live in /dev/shm)
+            clips = []
             gate_root = "/dev/shm" if os.path.isdir("/dev/shm") else _tempfile_dir()
 
             def run(P, tag, env_more=None):
-                # at most 8 distinct segments per rank; further instances re-encode one of them into their own output
+                # a few distinct segments per rank, written once; further instances re-encode one of them into their
+                # own output
                 paths, outs = [], []
                 for p in range(P):
-                    y4m = os.path.join(tmp, "e2e_%s_%d_%d.y4m" % (tag, rank, p % 8))
-                    if p < 8:
-                        gen_y4m.write_y4m(y4m, WIDTH, HEIGHT, n, start=(rank * 8 + p) * n)
-                    paths.append(y4m)
+                    if p % distinct >= len(clips):
+                        y4m = os.path.join(tmp, "e2e_%d_%d.y4m" % (rank, p % distinct))
+                        gen_y4m.write_y4m(y4m, WIDTH, HEIGHT, n, start=(rank * distinct + p) * n)
+                        clips.append(y4m)
+                    paths.append(clips[p % distinct])
                     outs.append(os.path.join(tmp, "e2e_%s_%d_%d" % (tag, rank, p)))
                 # start gate (cl_shim.cu start_gate): all P x world instances come up (15-30 s for 32 of them: context
                 # creation, module loading and page pinning are serialised by the driver), encode their key frame
@@ -416,10 +420,25 @@ def b200_arm(args, rank, world, local_rank, tmp, config):
                                                  env_extra=dict(env_more or {}, VP8B200_STATS=outs[p] + ".stats",
                                                                 VP8B200_START_GATE="%s:%d:3" % (gate, P * world)))
                          for p in range(P)]
-                stamps = [pr.wait() for pr in procs]
-                for st in stamps:
-                    if len(st) != n:
-                        raise RuntimeError("an encoder instance finished %d of %d frames" % (len(st), n))
+                # a failure on one rank must not leave the others waiting in a collective: agree on it first
+                failure = None
+                try:
+                    stamps = [pr.wait(timeout=900) for pr in procs]
+                    for st in stamps:
+                        if len(st) != n:
+                            raise RuntimeError("an encoder instance finished %d of %d frames" % (len(st), n))
+                except Exception as err:  # noqa: BLE001
+                    failure = "rank %d: %s" % (rank, err)
+                    for pr in procs:
+                        if pr.proc.poll() is None:
+                            pr.proc.kill()
+                if dist:
+                    ok = torch.tensor([0.0 if failure else 1.0], device="cuda", dtype=torch.float64)
+                    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+                    if ok.item() < 1.0 and not failure:
+                        failure = "an encoder instance of another rank failed"
+                if failure:
+                    raise RuntimeError(failure)
                 t0 = max(st[W] for st in stamps)
                 t1 = max(st[-1] for st in stamps)
                 if dist:  # one window for all ranks (perf_counter is a per-host monotonic clock; one node)
@@ -441,7 +460,7 @@ def b200_arm(args, rank, world, local_rank, tmp, config):
                     dist.barrier()
                 if rank == 0:
                     shutil.rmtree(gate, ignore_errors=True)
-                for pth in set(paths) | set(o + ".ivf" for o in outs):
+                for pth in set(o + ".ivf" for o in outs):
                     try:
                         os.remove(pth)
                     except OSError:
@@ -462,6 +481,9 @@ def b200_arm(args, rank, world, local_rank, tmp, config):
                 P = args.e2e_procs or max(1, min(32, (2 * cores) // world))
             else:
                 P = args.e2e_procs or max(1, min(8, cores // max(2, 2 * world)))
+            e2e_error = None
+            fps1 = fpsP = 0.0
+            h2d = d2h = lps = None
             try:
                 fps1, _, h2d, d2h, lps = run(1, "single")
                 try:
@@ -474,6 +496,10 @@ def b200_arm(args, rank, world, local_rank, tmp, config):
                     daemon.__exit__(None, None, None)
                     P = max(1, min(8, cores // 2))
                     fpsP, cnt, _, _, _ = run(P, "multi_nomps", {})
+            except RuntimeError as err:
+                # (run() has made sure every rank raises together)  The line is still printed, without an e2e value.
+                e2e_error = str(err)
+                sys.stderr.write("bench: end-to-end run failed: %s\n" % err)
             finally:
                 mps_used = daemon.active
                 if dist:
@@ -481,15 +507,20 @@ def b200_arm(args, rank, world, local_rank, tmp, config):
                 if local_rank == 0:
                     daemon.__exit__(None, None, None)
             best = max(fps1, fpsP)
-            e2e = {"value": best, "unit": "frames/s", "ms_per_step": 1000.0 / best,
-                   "processes_per_gpu": P if fpsP >= fps1 else 1, "single_process_fps": fps1 * (1 if not dist else 1),
-                   "multi_process_fps": fpsP, "mps": bool(mps_used and P > 1), "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                   "shim_kernel_launches_per_step": lps, "timed_frames_per_instance": Ke,
-                   "window": "from the moment the last instance has finished its key + warm-up frames to the moment the last "
-                             "instance is done; instances wait for each other at the start of their third inter frame (start gate, inside the warm-up)",
-                   "what": "unmodified reference host (vp8enc.cpp + entropy_host.cpp) + libOpenCL.so.1 shim; Y4M file in, "
-                           "IVF file out; all host<->device copies, host intra/entropy work and file I/O included; "
-                           "instances encode independent keyframe-delimited segments (no collective)"}
+            if e2e_error or best <= 0:
+                e2e = {"value": None, "unit": "frames/s", "error": e2e_error or "no frames", "h2d_bytes_per_step": None,
+                       "d2h_bytes_per_step": None}
+            else:
+                e2e = {"value": best, "unit": "frames/s", "ms_per_step": 1000.0 / best,
+                       "processes_per_gpu": P if fpsP >= fps1 else 1, "single_process_fps": fps1,
+                       "multi_process_fps": fpsP, "mps": bool(mps_used and P > 1), "h2d_bytes_per_step": h2d,
+                       "d2h_bytes_per_step": d2h, "shim_kernel_launches_per_step": lps, "timed_frames_per_instance": Ke,
+                       "window": "from the moment the last instance has finished its key + warm-up frames to the moment the "
+                                 "last instance is done; instances wait for each other at the start of their third inter "
+                                 "frame (start gate, inside the warm-up)",
+                       "what": "unmodified reference host (vp8enc.cpp + entropy_host.cpp) + libOpenCL.so.1 shim; Y4M file in, "
+                               "IVF file out; all host<->device copies, host intra/entropy work and file I/O included; "
+                               "instances encode independent keyframe-delimited segments (no collective)"}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

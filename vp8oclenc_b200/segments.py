@@ -161,8 +161,14 @@ class EncoderProcess:
             if "br=" in line:  # printed once per finished frame (src/vp8enc.cpp:482-483)
                 self.stamps.append(time.perf_counter())
 
-    def wait(self):
-        self.proc.wait()
+    def wait(self, timeout=None):
+        try:
+            self.proc.wait(timeout)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            self.proc.wait()
+            self.thread.join()
+            raise RuntimeError("encoder did not finish within %.0f s" % timeout)
         self.thread.join()
         self.t_end = time.perf_counter()
         if self.proc.returncode != 777 % 256:  # main() returns 777
