@@ -133,6 +133,14 @@ int vp8b200_entropy_tokens(void *stream, const int16_t *MB, const int32_t *MB_no
                            uint32_t *coeff_probs_denom, uint8_t *third_context, uint16_t *tokens, uint32_t capacity,
                            int32_t *mb_tokens, int32_t *mb_offset, uint32_t *part_info, uint32_t *tail_scratch);
 
+/* encode_coefficients (src/CPU_kernels.cl:541-778, enqueued src/vp8enc.cpp:88) over the decision streams of
+ * vp8b200_entropy_tokens: RFC 6386's boolean coder, one warp per partition, partition p written at
+ * output + p * partition_step, its byte count to partition_sizes[p].  coeff_probs: the table the host wrote back
+ * ([4][8][3][11] uint32, first partition's slot).  Same bytes as the host bool coder; costs no host time. */
+int vp8b200_entropy_boolcode(void *stream, const uint16_t *tokens, const uint32_t *part_info,
+                             const uint32_t *coeff_probs, uint8_t *output, int32_t *partition_sizes,
+                             int num_partitions, int partition_step);
+
 /* replaces prepare_filter_mask, src/CPU_kernels.cl:782-827 (src/loop_filter.h:25-33) */
 int vp8b200_prepare_filter_mask(void *stream, const int16_t *MB, int32_t *MB_non_zero_coeffs,
                                 const int32_t *MB_parts, int32_t *mb_mask, int width, int height);

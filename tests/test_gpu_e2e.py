@@ -86,9 +86,10 @@ def test_without_trace_same_bitstream(tmp_path):
 @pytest.mark.parametrize("env", [{"VP8B200_TOKEN_CAP": "64"}, {"VP8B200_GPU_TOKENS": "0"}, {"VP8B200_ELIDE": "off"},
                                  {"VP8B200_ELIDE": "track"}, {"VP8B200_ELIDE": "assume"},
                                  {"VP8B200_ELIDE": "lazy", "VP8B200_GPU_TOKENS": "0"},
-                                 {"VP8B200_FUSED": "0"}, {"VP8B200_SYNC": "sleep20"}],
+                                 {"VP8B200_FUSED": "0"}, {"VP8B200_SYNC": "sleep20"}, {"VP8B200_ENTROPY_THREADS": "3"},
+                                 {"VP8B200_GPU_BOOLCODER": "1"}],
                          ids=["token-scratch-grows", "host-entropy", "no-elision", "eager-downloads", "elision-assumed",
-                              "lazy-host-entropy", "kernel-per-kernel", "sleep-sync"])
+                              "lazy-host-entropy", "kernel-per-kernel", "sleep-sync", "three-entropy-threads", "gpu-bool-coder"])
 def test_shim_modes_same_bitstream(env, tmp_path):
     """every switch of the shim changes HOW the bytes are produced, never the bytes: decision streams that
     outgrow their scratch, the host-only entropy path, no transfer elision, no fused launches, polling sync.
@@ -122,6 +123,34 @@ def test_1080p_bench_configuration_byte_identical(tmp_path):
     a = open(os.path.join(d, "ref.ivf"), "rb").read()
     assert len(a) > 32 + 12 * 8
     assert a == open(os.path.join(d, "b200.ivf"), "rb").read()
+
+
+def test_start_gate_two_instances(tmp_path):
+    """VP8B200_START_GATE: two concurrent instances wait for each other at their second inter frame and then
+    produce the bytes of an ungated run; a gate nobody else arrives at only delays (here: is not armed, the clip
+    ends before its frame)"""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_y4m
+    from vp8oclenc_b200 import segments
+    w, h, frames, args = CASES["qcif"]
+    d = str(tmp_path)
+    y4m = os.path.join(d, "clip.y4m")
+    gen_y4m.write_y4m(y4m, w, h, frames)
+    _trace.run_host(SHIM_DIR, d, y4m, os.path.join(d, "plain.ivf"), args)
+    gate = os.path.join(d, "gate")
+    os.makedirs(gate)
+    procs = [segments.EncoderProcess(y4m, os.path.join(d, "g%d.ivf" % i), args, os.path.join(d, "run%d" % i),
+                                     env_extra={"VP8B200_START_GATE": "%s:2:2" % gate}) for i in range(2)]
+    for pr in procs:
+        pr.wait(timeout=300)
+    assert len(os.listdir(gate)) == 2
+    plain = open(os.path.join(d, "plain.ivf"), "rb").read()
+    for i in range(2):
+        assert open(os.path.join(d, "g%d.ivf" % i), "rb").read() == plain
+    # armed for a frame the clip never reaches: no effect
+    _trace.run_host(SHIM_DIR, d, y4m, os.path.join(d, "late.ivf"), args, env_extra={"VP8B200_START_GATE": "%s:5:1000" % gate})
+    assert open(os.path.join(d, "late.ivf"), "rb").read() == plain
 
 
 def test_lazy_downloads_skip_what_the_host_never_reads(tmp_path):

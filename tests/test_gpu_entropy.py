@@ -94,6 +94,19 @@ def test_token_streams_match_host_path(nparts, seed, mbw, mbh, density, big):
     assert np.array_equal(size_g, size_h), (size_g, size_h)
     assert np.array_equal(out_g, out_h), "partition bytes differ"
 
+    # the bool coder on the GPU as well (one warp per partition): same bytes, same sizes
+    d_table = dev(probs_g.view(np.int32))
+    d_out = torch.zeros(step * nparts + 64, dtype=torch.uint8, device="cuda")
+    d_size = torch.zeros(8, dtype=torch.int32, device="cuda")
+    rc = L.vp8b200_entropy_boolcode(st, D(d_tok), D(d_info), D(d_table), D(d_out), D(d_size), nparts, step)
+    assert rc == 0
+    torch.cuda.synchronize()
+    size_d = d_size.cpu().numpy()
+    assert np.array_equal(size_d, size_h), (size_d, size_h)
+    out_d = d_out.cpu().numpy()
+    for p in range(nparts):  # (bytes past a partition's size are scratch on both sides)
+        assert np.array_equal(out_d[p * step:p * step + size_h[p]], out_h[p * step:p * step + size_h[p]]), "partition %d" % p
+
 
 def test_token_stream_overflow_is_reported():
     """streams that do not fit the scratch are not written; the total says so (the shim then codes on the host)"""

@@ -344,9 +344,150 @@ __global__ void k_entropy_finish(unsigned *part_info, unsigned *num, unsigned *d
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// RFC 6386 section 7.3 boolean entropy encoder over the decision streams: one warp per partition.  The coder is
+// a serial recurrence (range, bottom, bit count), so one lane runs it; the warp resolves the probabilities of
+// the next 256 decisions into shared memory meanwhile (coalesced stream reads, table lookups), which leaves the
+// serial lane a shared-memory load per decision.  Same arithmetic as entropy_host.cpp's BoolSink (renormalisation
+// in at most two strides, carries walked back through the bytes already written), hence the same bytes.
+// Opt-in (VP8B200_GPU_BOOLCODER=1) and, as measured, not yet worth it: a lone lane retires an instruction every
+// ~8 cycles, about 110 ns per decision, 7 ms per 1080p frame against 0.3 ms on eight host threads (one instance
+// 101 instead of 257 frames/s, 32 instances 1494 instead of 2260).  It costs the host nothing, so it is the
+// building block for the parallel formulation (range as a 128-state machine scanned over chunks).
+constexpr int BC_CHUNK = 256;
+
+struct BoolCoder {
+    uint8_t *out;
+    uint32_t range = 255, bottom = 0, count = 0;
+    int bit_count = 24;
+    __device__ __forceinline__ static void carry(uint8_t *q) {
+        while (*--q == 255) *q = 0;
+        ++*q;
+    }
+    // the renormalisation of entropy_host.cpp's BoolSink::put from the point where range and bottom have taken
+    // the decision in: at most two strides, a byte leaves between them, carries walk back through the output
+    __device__ __forceinline__ void renormalise_general(int s) {
+        if (s >= bit_count) {
+            const int c = bit_count;
+            for (uint32_t t = bottom >> (32 - c); t; t &= t - 1) carry(out);
+            bottom <<= c;
+            *out++ = (uint8_t)(bottom >> 24);
+            ++count;
+            bottom &= (1u << 24) - 1;
+            bit_count = 8;
+            s -= c;
+        }
+        const unsigned long long wide = (unsigned long long)bottom << s;
+        for (uint32_t t = (uint32_t)(wide >> 32); t; t &= t - 1) carry(out);
+        bottom = (uint32_t)wide;
+        bit_count -= s;
+    }
+    __device__ __forceinline__ void put(uint32_t prob, uint32_t bit) {
+        const uint32_t split = 1 + (((range - 1) * prob) >> 8);
+        const uint32_t r = bit ? range - split : split;
+        bottom += bit ? split : 0u;
+        const int s = __clz(r) - 24;
+        range = r << s;
+        // Common case: no byte leaves (s < bit_count) and none of the s bits shifted out of bottom is set (no carry):
+        // plain shift.  __funnelshift_l(bottom, 0, s) is bottom >> (32 - s), 0 for s == 0.
+        if (s >= bit_count || __funnelshift_l(bottom, 0u, s) != 0u) {
+            renormalise_general(s);
+        } else {
+            bottom <<= s;
+            bit_count -= s;
+        }
+    }
+    __device__ __forceinline__ void finish() {
+        int c = bit_count;
+        uint32_t v = bottom;
+        if (v & (1u << (32 - c))) carry(out);
+        v <<= c & 7;
+        c >>= 3;
+        while (--c >= 0) v <<= 8;
+        for (c = 0; c < 4; ++c) {
+            *out++ = (uint8_t)(v >> 24);
+            ++count;
+            v <<= 8;
+        }
+    }
+};
+
+__global__ void __launch_bounds__(32) k_entropy_boolcode(const uint16_t *__restrict__ tokens, const uint32_t *__restrict__ part_info,
+                                                         const uint32_t *__restrict__ coeff_probs, uint8_t *output,
+                                                         int32_t *partition_sizes, int P, int partition_step) {
+    __shared__ uint8_t s_tab[1056 + 256];          // one table for both kinds of entry (slot / fixed probability)
+    __shared__ __align__(16) uint16_t s_dec[2][BC_CHUNK];  // probability | bit << 8 of a chunk of decisions, double buffered
+    const int p = blockIdx.x, lane = threadIdx.x;
+    for (int i = lane; i < 1056 + 256; i += 32) s_tab[i] = i < 1056 ? (uint8_t)coeff_probs[i] : (uint8_t)(i - 1056);
+    const uint16_t *t = tokens + part_info[p];
+    const uint32_t n = part_info[P + p];
+    __syncwarp();
+    auto resolve = [&](uint32_t base, int buf) {
+#pragma unroll
+        for (int k = 0; k < BC_CHUNK / 32; ++k) {
+            const uint32_t i = base + k * 32 + lane;
+            if (i < n) {
+                const uint32_t e = t[i];
+                s_dec[buf][k * 32 + lane] = (uint16_t)(s_tab[e & 0x7ff] | ((e >> 15) << 8));
+            }
+        }
+    };
+    BoolCoder bc;
+    bc.out = output + (size_t)partition_step * p;
+    if (n) resolve(0, 0);
+    __syncwarp();
+    int buf = 0;
+    for (uint32_t base = 0; base < n; base += BC_CHUNK, buf ^= 1) {
+        if (lane == 0) {
+            const uint32_t m = min((uint32_t)BC_CHUNK, n - base);
+            uint32_t j = 0;
+            for (; j + 8 <= m; j += 8) {  // eight decisions per 16-byte shared load
+                const uint4 q = *reinterpret_cast<const uint4 *>(&s_dec[buf][j]);
+                const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    bc.put(w[e] & 255u, (w[e] >> 8) & 1u);
+                    bc.put((w[e] >> 16) & 255u, w[e] >> 24);
+                }
+            }
+            for (; j < m; ++j) {
+                const uint32_t d = s_dec[buf][j];
+                bc.put(d & 255u, d >> 8);
+            }
+        } else if (base + BC_CHUNK < n) {
+            resolve(base + BC_CHUNK, buf ^ 1);  // the other 31 lanes prepare the next chunk (lane 0's share: below)
+        }
+        __syncwarp();
+        if (base + BC_CHUNK < n) {  // entries of lane 0 of the next chunk
+#pragma unroll
+            for (int k = 0; k < BC_CHUNK / 32; ++k) {
+                const uint32_t i = base + BC_CHUNK + k * 32;
+                if (lane == 0 && i < n) {
+                    const uint32_t e = t[i];
+                    s_dec[buf ^ 1][k * 32] = (uint16_t)(s_tab[e & 0x7ff] | ((e >> 15) << 8));
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        bc.finish();
+        partition_sizes[p] = (int32_t)bc.count;
+    }
+}
+
 }  // namespace vp8
 
 using namespace vp8;
+
+extern "C" int vp8b200_entropy_boolcode(void *stream, const uint16_t *tokens, const uint32_t *part_info,
+                                        const uint32_t *coeff_probs, uint8_t *output, int32_t *partition_sizes,
+                                        int num_partitions, int partition_step) {
+    if (num_partitions < 1 || num_partitions > 8) return -(int)cudaErrorInvalidValue;
+    k_entropy_boolcode<<<num_partitions, 32, 0, (cudaStream_t)stream>>>(tokens, part_info, coeff_probs, output, partition_sizes,
+                                                                         num_partitions, partition_step);
+    VP8_LAUNCH_CHECK();
+}
 
 extern "C" int vp8b200_entropy_tokens(void *stream, const int16_t *MB, const int32_t *MB_non_zero_coeffs,
                                       const int32_t *MB_parts, int mb_width, int mb_height, int num_partitions,

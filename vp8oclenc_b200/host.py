@@ -149,6 +149,13 @@ def entropy_tokens(MB, MB_non_zero_coeffs, MB_parts, mb_width, mb_height, num_pa
                                         _p(part_info), _p(tail_scratch)), "entropy_tokens")
 
 
+def entropy_boolcode(tokens, part_info, coeff_probs, output, partition_sizes, num_partitions, partition_step):
+    """encode_coefficients (src/CPU_kernels.cl:541-778) over the decision streams of entropy_tokens: RFC 6386's
+    boolean coder on the GPU, one warp per partition; partition p lands at output[p * partition_step:]"""
+    _check(lib().vp8b200_entropy_boolcode(_stream(), _p(tokens), _p(part_info), _p(coeff_probs), _p(output),
+                                          _p(partition_sizes), num_partitions, partition_step), "entropy_boolcode")
+
+
 # ---------------------------------------------------------------------------------------------
 class Engine:
     """Frame-level engine (vp8b200_engine_* of include/vp8b200.h): the sequence of
