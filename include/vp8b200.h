@@ -22,6 +22,7 @@
 #ifndef VP8B200_H
 #define VP8B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -134,12 +135,17 @@ int vp8b200_entropy_tokens(void *stream, const int16_t *MB, const int32_t *MB_no
                            int32_t *mb_tokens, int32_t *mb_offset, uint32_t *part_info, uint32_t *tail_scratch);
 
 /* encode_coefficients (src/CPU_kernels.cl:541-778, enqueued src/vp8enc.cpp:88) over the decision streams of
- * vp8b200_entropy_tokens: RFC 6386's boolean coder, one warp per partition, partition p written at
- * output + p * partition_step, its byte count to partition_sizes[p].  coeff_probs: the table the host wrote back
- * ([4][8][3][11] uint32, first partition's slot).  Same bytes as the host bool coder; costs no host time. */
+ * vp8b200_entropy_tokens: RFC 6386's boolean coder in parallel (the range as a 128-state machine scanned over
+ * chunks of decisions, the partition as one big sum, see entropy_kernels.cu).  Partition p is written at
+ * output + p * partition_step, its byte count to partition_sizes[p] (0 if it does not fit its slot).
+ * coeff_probs: the table the host wrote back ([4][8][3][11] uint32, first partition's slot).  max_decisions: an upper
+ * bound of the decisions of any one partition (the total will do); scratch: device memory of
+ * vp8b200_entropy_boolcode_scratch_bytes(max_decisions, num_partitions, partition_step) bytes.
+ * Same bytes as the host bool coder; costs no host time. */
+size_t vp8b200_entropy_boolcode_scratch_bytes(uint32_t max_decisions, int num_partitions, int partition_step);
 int vp8b200_entropy_boolcode(void *stream, const uint16_t *tokens, const uint32_t *part_info,
                              const uint32_t *coeff_probs, uint8_t *output, int32_t *partition_sizes,
-                             int num_partitions, int partition_step);
+                             int num_partitions, int partition_step, uint32_t max_decisions, void *scratch);
 
 /* replaces prepare_filter_mask, src/CPU_kernels.cl:782-827 (src/loop_filter.h:25-33) */
 int vp8b200_prepare_filter_mask(void *stream, const int16_t *MB, int32_t *MB_non_zero_coeffs,

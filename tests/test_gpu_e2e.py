@@ -86,10 +86,10 @@ def test_without_trace_same_bitstream(tmp_path):
 @pytest.mark.parametrize("env", [{"VP8B200_TOKEN_CAP": "64"}, {"VP8B200_GPU_TOKENS": "0"}, {"VP8B200_ELIDE": "off"},
                                  {"VP8B200_ELIDE": "track"}, {"VP8B200_ELIDE": "assume"},
                                  {"VP8B200_ELIDE": "lazy", "VP8B200_GPU_TOKENS": "0"},
-                                 {"VP8B200_FUSED": "0"}, {"VP8B200_SYNC": "sleep20"}, {"VP8B200_ENTROPY_THREADS": "3"},
-                                 {"VP8B200_GPU_BOOLCODER": "1"}],
+                                 {"VP8B200_FUSED": "0"}, {"VP8B200_SYNC": "sleep20"}, {"VP8B200_ENTROPY_THREADS": "3", "VP8B200_GPU_BOOLCODER": "0"},
+                                 {"VP8B200_GPU_BOOLCODER": "0"}],
                          ids=["token-scratch-grows", "host-entropy", "no-elision", "eager-downloads", "elision-assumed",
-                              "lazy-host-entropy", "kernel-per-kernel", "sleep-sync", "three-entropy-threads", "gpu-bool-coder"])
+                              "lazy-host-entropy", "kernel-per-kernel", "sleep-sync", "three-entropy-threads", "host-bool-coder"])
 def test_shim_modes_same_bitstream(env, tmp_path):
     """every switch of the shim changes HOW the bytes are produced, never the bytes: decision streams that
     outgrow their scratch, the host-only entropy path, no transfer elision, no fused launches, polling sync.

@@ -94,11 +94,15 @@ def test_token_streams_match_host_path(nparts, seed, mbw, mbh, density, big):
     assert np.array_equal(size_g, size_h), (size_g, size_h)
     assert np.array_equal(out_g, out_h), "partition bytes differ"
 
-    # the bool coder on the GPU as well (one warp per partition): same bytes, same sizes
+    # the bool coder on the GPU as well (parallel formulation): same bytes, same sizes
     d_table = dev(probs_g.view(np.int32))
     d_out = torch.zeros(step * nparts + 64, dtype=torch.uint8, device="cuda")
     d_size = torch.zeros(8, dtype=torch.int32, device="cuda")
-    rc = L.vp8b200_entropy_boolcode(st, D(d_tok), D(d_info), D(d_table), D(d_out), D(d_size), nparts, step)
+    L.vp8b200_entropy_boolcode_scratch_bytes.restype = ctypes.c_size_t
+    need = L.vp8b200_entropy_boolcode_scratch_bytes(ctypes.c_uint32(total), nparts, step)
+    d_scratch = torch.empty(need, dtype=torch.uint8, device="cuda")
+    rc = L.vp8b200_entropy_boolcode(st, D(d_tok), D(d_info), D(d_table), D(d_out), D(d_size), nparts, step,
+                                    ctypes.c_uint32(total), D(d_scratch))
     assert rc == 0
     torch.cuda.synchronize()
     size_d = d_size.cpu().numpy()

@@ -146,7 +146,7 @@ static void write_stats() {
 }
 
 static bool g_gpu_tokens = true;       // coefficient decisions prepared on the GPU (see tokens_on_gpu)
-static bool g_gpu_boolcoder = false;   // ... and bool-coded there as well (VP8B200_GPU_BOOLCODER=1, see tokens_encode)
+static bool g_gpu_boolcoder = true;    // ... and bool-coded there as well (VP8B200_GPU_BOOLCODER=0: host threads; see tokens_encode)
 static int g_elide = 3;                // transfer elision: 0 off, 1 assume, 2 track, 3 track + lazy downloads (see "transfer elision" below)
 static std::vector<cl_mem> g_mirrors;  // objects that own a pinned mirror
 static std::vector<Cmd> g_cmds;  // the deferred command list
@@ -178,7 +178,7 @@ static bool cuda_init() {
     vp8b200_device_info(g_dev_name, sizeof(g_dev_name), &g_sm_count, nullptr, nullptr);
     if (const char *f = getenv("VP8B200_FUSED")) g_fuse = f[0] != '0';
     if (const char *f = getenv("VP8B200_GPU_TOKENS")) g_gpu_tokens = f[0] != '0';
-    if (const char *f = getenv("VP8B200_GPU_BOOLCODER")) g_gpu_boolcoder = f[0] == '1';
+    if (const char *f = getenv("VP8B200_GPU_BOOLCODER")) g_gpu_boolcoder = f[0] != '0';
     if (const char *f = getenv("VP8B200_ELIDE"))
         g_elide = !strcmp(f, "assume") ? 1 : (!strcmp(f, "track") ? 2 : (!strcmp(f, "lazy") ? 3 : 0));
     if (getenv("VP8CL_TRACE") && g_elide == 3) g_elide = 2;  // the trace records what every read delivered
@@ -543,6 +543,8 @@ struct TokenState {
     int32_t *dev_mb_tokens = nullptr, *dev_mb_offset = nullptr;
     uint32_t *dev_part_info = nullptr, *dev_tail = nullptr, *host_part_info = nullptr;
     size_t capacity = 0, mbs = 0;
+    void *bool_scratch = nullptr;  // vp8b200_entropy_boolcode's working memory
+    size_t bool_scratch_bytes = 0;
 };
 static TokenState g_tok;
 static bool tokens_alloc_streams(size_t entries);
@@ -646,15 +648,37 @@ static bool tokens_encode(cl_kernel k) {
     g_tok.stage = 0;
     if (!usable) return false;
     if (g_gpu_boolcoder) {
-        // The bool coder runs on the stream as well (one warp per partition): the streams never leave the device,
-        // the host thread goes on to code the frame header and meets the partitions in gather_frame()'s reads.
-        // No host time at all, but 7 ms per 1080p frame today (entropy_kernels.cu): opt-in, slower than the host
-        // threads on every box measured so far.
-        cl_mem parts_out = arg_mem(k, 3), sizes = arg_mem(k, 4);
-        parts_out->dev_valid = sizes->dev_valid = true;  // (both are only ever read as far as this kernel writes them)
-        ++g_kernel_launches;
-        return vp8b200_entropy_boolcode(g_stream, g_tok.dev_tokens, g_tok.dev_part_info, in<uint32_t>(k, 6),
-                                        out<uint8_t>(k, 3), out<int32_t>(k, 4), g_tok.P, arg_int(k, 10)) == 0;
+        // The bool coder runs on the stream as well (parallel formulation, entropy_kernels.cu): the streams never
+        // leave the device, the host thread goes on to code the frame header and meets the partitions in
+        // gather_frame()'s reads.
+        const uint32_t total = g_tok.host_part_info[2 * g_tok.P];
+        const int step = arg_int(k, 10);
+        const size_t need = vp8b200_entropy_boolcode_scratch_bytes(total, g_tok.P, step);
+        if (need > g_tok.bool_scratch_bytes) {
+            stream_sync();
+            cudaFree(g_tok.bool_scratch);
+            g_tok.bool_scratch = nullptr;
+            g_tok.bool_scratch_bytes = 0;
+            if (cudaMalloc(&g_tok.bool_scratch, need + need / 4) != cudaSuccess) {
+                cudaGetLastError();
+                g_gpu_boolcoder = false;  // out of memory: the host threads code this and all later frames
+            } else {
+                g_tok.bool_scratch_bytes = need + need / 4;
+            }
+        }
+        if (g_gpu_boolcoder) {
+            cl_mem parts_out = arg_mem(k, 3), sizes = arg_mem(k, 4);
+            parts_out->dev_valid = sizes->dev_valid = true;  // (both are only ever read as far as the kernels write them)
+            g_kernel_launches += 4;
+            return vp8b200_entropy_boolcode(g_stream, g_tok.dev_tokens, g_tok.dev_part_info, in<uint32_t>(k, 6),
+                                            out<uint8_t>(k, 3), out<int32_t>(k, 4), g_tok.P, step, total,
+                                            g_tok.bool_scratch) == 0;
+        }
+        // (fall through to the host threads: the streams have to come over after all)
+        if (total) {
+            cudaMemcpyAsync(g_tok.host_tokens, g_tok.dev_tokens, (size_t)total * 2, cudaMemcpyDeviceToHost, g_stream);
+            g_d2h_bytes += (size_t)total * 2;
+        }
     }
     stream_sync();
     vp8host::encode_token_streams(g_tok.host_tokens, g_tok.host_part_info, hin<uint32_t>(k, 6), hout<uint8_t>(k, 3),

@@ -345,149 +345,261 @@ __global__ void k_entropy_finish(unsigned *part_info, unsigned *num, unsigned *d
 }
 
 // ------------------------------------------------------------------------------------------
-// RFC 6386 section 7.3 boolean entropy encoder over the decision streams: one warp per partition.  The coder is
-// a serial recurrence (range, bottom, bit count), so one lane runs it; the warp resolves the probabilities of
-// the next 256 decisions into shared memory meanwhile (coalesced stream reads, table lookups), which leaves the
-// serial lane a shared-memory load per decision.  Same arithmetic as entropy_host.cpp's BoolSink (renormalisation
-// in at most two strides, carries walked back through the bytes already written), hence the same bytes.
-// Opt-in (VP8B200_GPU_BOOLCODER=1) and, as measured, not yet worth it: a lone lane retires an instruction every
-// ~8 cycles, about 110 ns per decision, 7 ms per 1080p frame against 0.3 ms on eight host threads (one instance
-// 101 instead of 257 frames/s, 32 instances 1494 instead of 2260).  It costs the host nothing, so it is the
-// building block for the parallel formulation (range as a 128-state machine scanned over chunks).
+// RFC 6386 section 7.3 boolean entropy encoder over the decision streams, in parallel.
+//
+// The coder looks serial (range, bottom, bit count), but its output is a plain number.  With R_i the range before
+// decision i, split_i = 1 + ((R_i - 1) * prob_i >> 8), s_i the normalisation shift of decision i and
+// T_i = s_0 + .. + s_(i-1), the bytes of a partition are the big-endian digits of
+//     L = sum over the decisions with value 1 of  split_i << (T' - T_i),     T' = 24 + 8 m,
+// m = bytes that leave during coding (the k with 24 + 8 k <= T_n), m + 4 bytes in all (the flush writes four).
+// Carry propagation into bytes already written is just the carries of this sum.  (Checked against the serial
+// coder of entropy_host.cpp, which is checked against the reference's kernel.)  So:
+//   A  the range is a state machine with 128 states: a warp walks a chunk of BC_CHUNK decisions from all 128
+//      possible ranges at once (4 per lane) and leaves the chunk's map: range in -> range out, sum of shifts;
+//   B  one warp per partition chains the maps (a shuffle per chunk): range and T at the start of every chunk, T_n;
+//   C  one thread per chunk walks it again from its now known start and adds split_i << (T' - T_i) into the
+//      partition's 32-bit words (64-bit accumulators: a few threads touch a word);
+//   D  per partition the words are reduced to 32 bits each, the remaining 0/1 carries resolved by a
+//      generate/propagate scan, and the bytes written most significant first.
 constexpr int BC_CHUNK = 256;
 
-struct BoolCoder {
-    uint8_t *out;
-    uint32_t range = 255, bottom = 0, count = 0;
-    int bit_count = 24;
-    __device__ __forceinline__ static void carry(uint8_t *q) {
-        while (*--q == 255) *q = 0;
-        ++*q;
-    }
-    // the renormalisation of entropy_host.cpp's BoolSink::put from the point where range and bottom have taken
-    // the decision in: at most two strides, a byte leaves between them, carries walk back through the output
-    __device__ __forceinline__ void renormalise_general(int s) {
-        if (s >= bit_count) {
-            const int c = bit_count;
-            for (uint32_t t = bottom >> (32 - c); t; t &= t - 1) carry(out);
-            bottom <<= c;
-            *out++ = (uint8_t)(bottom >> 24);
-            ++count;
-            bottom &= (1u << 24) - 1;
-            bit_count = 8;
-            s -= c;
-        }
-        const unsigned long long wide = (unsigned long long)bottom << s;
-        for (uint32_t t = (uint32_t)(wide >> 32); t; t &= t - 1) carry(out);
-        bottom = (uint32_t)wide;
-        bit_count -= s;
-    }
-    __device__ __forceinline__ void put(uint32_t prob, uint32_t bit) {
-        const uint32_t split = 1 + (((range - 1) * prob) >> 8);
-        const uint32_t r = bit ? range - split : split;
-        bottom += bit ? split : 0u;
-        const int s = __clz(r) - 24;
-        range = r << s;
-        // Common case: no byte leaves (s < bit_count) and none of the s bits shifted out of bottom is set (no carry):
-        // plain shift.  __funnelshift_l(bottom, 0, s) is bottom >> (32 - s), 0 for s == 0.
-        if (s >= bit_count || __funnelshift_l(bottom, 0u, s) != 0u) {
-            renormalise_general(s);
-        } else {
-            bottom <<= s;
-            bit_count -= s;
-        }
-    }
-    __device__ __forceinline__ void finish() {
-        int c = bit_count;
-        uint32_t v = bottom;
-        if (v & (1u << (32 - c))) carry(out);
-        v <<= c & 7;
-        c >>= 3;
-        while (--c >= 0) v <<= 8;
-        for (c = 0; c < 4; ++c) {
-            *out++ = (uint8_t)(v >> 24);
-            ++count;
-            v <<= 8;
-        }
-    }
+struct BoolcodeScratch {  // carved out of one allocation, see vp8b200_entropy_boolcode_scratch_bytes
+    uint8_t *map_range;            // [chunks][128]
+    uint16_t *map_shift;           // [chunks][128]
+    uint8_t *start_range;          // [chunks]
+    uint32_t *start_shift;         // [chunks]
+    uint32_t *params;              // [P][4]: T', bytes, words, -
+    unsigned long long *words;     // [P][words_per_partition]
+    uint32_t words_per_partition;
 };
 
-__global__ void __launch_bounds__(32) k_entropy_boolcode(const uint16_t *__restrict__ tokens, const uint32_t *__restrict__ part_info,
-                                                         const uint32_t *__restrict__ coeff_probs, uint8_t *output,
-                                                         int32_t *partition_sizes, int P, int partition_step) {
-    __shared__ uint8_t s_tab[1056 + 256];          // one table for both kinds of entry (slot / fixed probability)
-    __shared__ __align__(16) uint16_t s_dec[2][BC_CHUNK];  // probability | bit << 8 of a chunk of decisions, double buffered
-    const int p = blockIdx.x, lane = threadIdx.x;
-    for (int i = lane; i < 1056 + 256; i += 32) s_tab[i] = i < 1056 ? (uint8_t)coeff_probs[i] : (uint8_t)(i - 1056);
-    const uint16_t *t = tokens + part_info[p];
+__device__ __forceinline__ uint32_t bc_chunk_base(const uint32_t *part_info, int P, int p) {
+    uint32_t base = 0;
+    for (int q = 0; q < p; ++q) base += (part_info[P + q] + BC_CHUNK - 1) / BC_CHUNK;
+    return base;
+}
+// one decision from range R: returns the new range, adds the shift to T, hands back split
+__device__ __forceinline__ uint32_t bc_step(uint32_t R, uint32_t prob, bool bit, uint32_t &T, uint32_t &split) {
+    split = 1 + (((R - 1) * prob) >> 8);
+    const uint32_t r = bit ? R - split : split;
+    const int s = __clz(r) - 24;
+    T += s;
+    return r << s;
+}
+
+// A: blockIdx.y = partition, one warp per chunk
+constexpr int BC_A_WARPS = 4;
+__global__ void __launch_bounds__(BC_A_WARPS * 32) k_boolcode_maps(const uint16_t *__restrict__ tokens,
+                                                                   const uint32_t *__restrict__ part_info,
+                                                                   const uint32_t *__restrict__ coeff_probs, int P,
+                                                                   BoolcodeScratch sc) {
+    __shared__ uint8_t s_tab[1056 + 256];  // one table for both kinds of entry (slot / fixed probability)
+    for (int i = threadIdx.x; i < 1056 + 256; i += blockDim.x) s_tab[i] = i < 1056 ? (uint8_t)coeff_probs[i] : (uint8_t)(i - 1056);
+    __syncthreads();
+    const int p = blockIdx.y, lane = threadIdx.x & 31;
+    const uint32_t k = blockIdx.x * BC_A_WARPS + (threadIdx.x >> 5);
     const uint32_t n = part_info[P + p];
-    __syncwarp();
-    auto resolve = [&](uint32_t base, int buf) {
+    if (k * BC_CHUNK >= n) return;  // whole warp
+    const uint16_t *t = tokens + part_info[p] + (size_t)k * BC_CHUNK;
+    const uint32_t cnt = min((uint32_t)BC_CHUNK, n - k * BC_CHUNK);
+    uint32_t R[4], T[4] = {0, 0, 0, 0};
 #pragma unroll
-        for (int k = 0; k < BC_CHUNK / 32; ++k) {
-            const uint32_t i = base + k * 32 + lane;
-            if (i < n) {
-                const uint32_t e = t[i];
-                s_dec[buf][k * 32 + lane] = (uint16_t)(s_tab[e & 0x7ff] | ((e >> 15) << 8));
+    for (int q = 0; q < 4; ++q) R[q] = 128 + 32 * q + lane;
+    for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
+        uint32_t d = 0;
+        if (j0 + lane < cnt) {
+            const uint32_t e = t[j0 + lane];
+            d = s_tab[e & 0x7ff] | ((e >> 15) << 8);
+        }
+        const int m = (int)min(32u, cnt - j0);
+        for (int j = 0; j < m; ++j) {
+            const uint32_t dj = __shfl_sync(0xffffffffu, d, j);
+            const uint32_t prob = dj & 255u;
+            const bool bit = (dj >> 8) != 0;  // warp-uniform
+            uint32_t split;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) R[q] = bc_step(R[q], prob, bit, T[q], split);
+        }
+    }
+    const size_t c = (size_t)bc_chunk_base(part_info, P, p) + k;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        sc.map_range[c * 128 + 32 * q + lane] = (uint8_t)R[q];
+        sc.map_shift[c * 128 + 32 * q + lane] = (uint16_t)T[q];
+    }
+}
+
+// B: one CTA per partition; warp 0 chains the maps, then everybody clears the partition's words
+__global__ void __launch_bounds__(256) k_boolcode_chain(const uint32_t *__restrict__ part_info, int P, BoolcodeScratch sc,
+                                                        int partition_step) {
+    __shared__ uint32_t s_words;
+    const int p = blockIdx.x, lane = threadIdx.x & 31;
+    if (threadIdx.x < 32) {
+        const uint32_t n = part_info[P + p];
+        const uint32_t K = (n + BC_CHUNK - 1) / BC_CHUNK;
+        const size_t cb = bc_chunk_base(part_info, P, p);
+        uint32_t state = 255, T = 0;
+        uint32_t mr[4], ms[4];
+        auto load = [&](uint32_t k) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                mr[q] = sc.map_range[(cb + k) * 128 + 32 * q + lane];
+                ms[q] = sc.map_shift[(cb + k) * 128 + 32 * q + lane];
             }
+        };
+        if (K) load(0);
+        for (uint32_t k = 0; k < K; ++k) {
+            if (lane == 0) {
+                sc.start_range[cb + k] = (uint8_t)state;
+                sc.start_shift[cb + k] = T;
+            }
+            const uint32_t cr[4] = {mr[0], mr[1], mr[2], mr[3]}, cs[4] = {ms[0], ms[1], ms[2], ms[3]};
+            if (k + 1 < K) load(k + 1);  // in flight while this chunk's entry is looked up
+            const int idx = (int)state - 128, src = idx & 31, q = idx >> 5;
+            uint32_t nr = 0, ns = 0;
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) {
+                const uint32_t a = __shfl_sync(0xffffffffu, cr[qq], src), b = __shfl_sync(0xffffffffu, cs[qq], src);
+                if (qq == q) {
+                    nr = a;
+                    ns = b;
+                }
+            }
+            state = nr;
+            T += ns;
+        }
+        const uint32_t m = T >= 24 ? (T - 24) / 8 + 1 : 0;
+        const uint32_t bytes = m + 4, words = (bytes + 3) / 4;
+        if (lane == 0) {
+            // (a partition that does not fit its slot cannot be written; the reference has the same limit)
+            const bool fits = bytes <= (uint32_t)partition_step && words + 2 <= sc.words_per_partition;
+            sc.params[4 * p + 0] = 24 + 8 * m;
+            sc.params[4 * p + 1] = fits ? bytes : 0;
+            sc.params[4 * p + 2] = fits ? words : 0;
+            s_words = fits ? words + 2 : 0;
+        }
+    }
+    __syncthreads();
+    unsigned long long *w = sc.words + (size_t)p * sc.words_per_partition;
+    for (uint32_t i = threadIdx.x; i < s_words; i += blockDim.x) w[i] = 0ull;
+}
+
+// C: one thread per chunk
+__global__ void __launch_bounds__(128) k_boolcode_terms(const uint16_t *__restrict__ tokens, const uint32_t *__restrict__ part_info,
+                                                        const uint32_t *__restrict__ coeff_probs, int P, BoolcodeScratch sc) {
+    __shared__ uint8_t s_tab[1056 + 256];
+    for (int i = threadIdx.x; i < 1056 + 256; i += blockDim.x) s_tab[i] = i < 1056 ? (uint8_t)coeff_probs[i] : (uint8_t)(i - 1056);
+    __syncthreads();
+    const int p = blockIdx.y;
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n = part_info[P + p];
+    if (k * BC_CHUNK >= n || sc.params[4 * p + 2] == 0) return;
+    const size_t c = (size_t)bc_chunk_base(part_info, P, p) + k;
+    const uint16_t *t = tokens + part_info[p] + (size_t)k * BC_CHUNK;
+    const uint32_t cnt = min((uint32_t)BC_CHUNK, n - k * BC_CHUNK);
+    const uint32_t Tend = sc.params[4 * p + 0];
+    unsigned long long *words = sc.words + (size_t)p * sc.words_per_partition;
+    uint32_t R = sc.start_range[c], T = sc.start_shift[c];
+    int cur = -1;
+    unsigned long long acc = 0;
+    auto flush = [&]() {
+        if (cur >= 0 && acc) {
+            atomicAdd(words + cur, acc & 0xffffffffull);
+            if (acc >> 32) atomicAdd(words + cur + 1, acc >> 32);
         }
     };
-    BoolCoder bc;
-    bc.out = output + (size_t)partition_step * p;
-    if (n) resolve(0, 0);
-    __syncwarp();
-    int buf = 0;
-    for (uint32_t base = 0; base < n; base += BC_CHUNK, buf ^= 1) {
-        if (lane == 0) {
-            const uint32_t m = min((uint32_t)BC_CHUNK, n - base);
-            uint32_t j = 0;
-            for (; j + 8 <= m; j += 8) {  // eight decisions per 16-byte shared load
-                const uint4 q = *reinterpret_cast<const uint4 *>(&s_dec[buf][j]);
-                const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    bc.put(w[e] & 255u, (w[e] >> 8) & 1u);
-                    bc.put((w[e] >> 16) & 255u, w[e] >> 24);
-                }
+    for (uint32_t j = 0; j < cnt; ++j) {
+        const uint32_t e = t[j];
+        const uint32_t prob = s_tab[e & 0x7ff];
+        const bool bit = (e >> 15) != 0;
+        const uint32_t E = Tend - T;  // exponent of this decision's split
+        uint32_t split;
+        R = bc_step(R, prob, bit, T, split);
+        if (bit) {
+            const int w = (int)(E >> 5);
+            if (w != cur) {
+                flush();
+                cur = w;
+                acc = 0;
             }
-            for (; j < m; ++j) {
-                const uint32_t d = s_dec[buf][j];
-                bc.put(d & 255u, d >> 8);
-            }
-        } else if (base + BC_CHUNK < n) {
-            resolve(base + BC_CHUNK, buf ^ 1);  // the other 31 lanes prepare the next chunk (lane 0's share: below)
+            acc += (unsigned long long)split << (E & 31);
         }
-        __syncwarp();
-        if (base + BC_CHUNK < n) {  // entries of lane 0 of the next chunk
-#pragma unroll
-            for (int k = 0; k < BC_CHUNK / 32; ++k) {
-                const uint32_t i = base + BC_CHUNK + k * 32;
-                if (lane == 0 && i < n) {
-                    const uint32_t e = t[i];
-                    s_dec[buf ^ 1][k * 32] = (uint16_t)(s_tab[e & 0x7ff] | ((e >> 15) << 8));
-                }
-            }
-        }
-        __syncwarp();
     }
-    if (lane == 0) {
-        bc.finish();
-        partition_sizes[p] = (int32_t)bc.count;
+    flush();
+}
+
+// D: one CTA per partition: words -> 32 bits each, carries, bytes
+constexpr int BC_D_THREADS = 1024;
+__global__ void __launch_bounds__(BC_D_THREADS) k_boolcode_emit(BoolcodeScratch sc, uint8_t *output, int32_t *partition_sizes,
+                                                                int partition_step) {
+    __shared__ uint32_t s_g[32], s_p[32];
+    const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t bytes = sc.params[4 * p + 1], W = sc.params[4 * p + 2] + 2;  // (two spare words: always zero at the end)
+    if (tid == 0) partition_sizes[p] = (int32_t)bytes;
+    if (bytes == 0) return;
+    const unsigned long long *A = sc.words + (size_t)p * sc.words_per_partition;
+    uint8_t *out = output + (size_t)partition_step * p;
+    // a thread owns `per` consecutive words; blocks of per * BC_D_THREADS words are chained through carry_in
+    const uint32_t per = (W + BC_D_THREADS - 1) / BC_D_THREADS;
+    const uint32_t w0 = min(W, tid * per), w1 = min(W, w0 + per);
+    // local pass with carry-in 0: generate / propagate of the thread's words
+    uint32_t g = 0, pr = 1, c = 0;
+    for (uint32_t w = w0; w < w1; ++w) {
+        const unsigned long long v = (A[w] & 0xffffffffull) + (w ? A[w - 1] >> 32 : 0ull) + c;
+        c = (uint32_t)(v >> 32);
+        pr &= (uint32_t)v == 0xffffffffu;
+    }
+    g = c;
+    if (w0 == w1) pr = 1;  // no words: passes a carry through (there is none to pass)
+    // inclusive scan of (g, p) over the threads: carry out of everything up to and including this thread
+    uint32_t G = g, Pp = pr;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t g2 = __shfl_up_sync(0xffffffffu, G, o), p2 = __shfl_up_sync(0xffffffffu, Pp, o);
+        if (lane >= o) {
+            G = G | (Pp & g2);
+            Pp = Pp & p2;
+        }
+    }
+    if (lane == 31) {
+        s_g[warp] = G;
+        s_p[warp] = Pp;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t wg = s_g[lane], wp = s_p[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t g2 = __shfl_up_sync(0xffffffffu, wg, o), p2 = __shfl_up_sync(0xffffffffu, wp, o);
+            if (lane >= o) {
+                wg = wg | (wp & g2);
+                wp = wp & p2;
+            }
+        }
+        s_g[lane] = wg;
+    }
+    __syncthreads();
+    // carry into this thread = carry out of the previous thread (inclusive value of lane - 1, combined with the warps before)
+    uint32_t cin_warp = warp ? s_g[warp - 1] : 0;
+    uint32_t Gprev = __shfl_up_sync(0xffffffffu, G, 1), Pprev = __shfl_up_sync(0xffffffffu, Pp, 1);
+    uint32_t cin = lane ? (Gprev | (Pprev & cin_warp)) : cin_warp;
+    // final pass: the words with the true carry-in, bytes most significant first
+    c = cin;
+    for (uint32_t w = w0; w < w1; ++w) {
+        const unsigned long long v = (A[w] & 0xffffffffull) + (w ? A[w - 1] >> 32 : 0ull) + c;
+        c = (uint32_t)(v >> 32);
+        const uint32_t word = (uint32_t)v;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const uint32_t idx = 4 * w + b;  // byte index counted from the least significant end
+            if (idx < bytes) out[bytes - 1 - idx] = (uint8_t)(word >> (8 * b));
+        }
     }
 }
 
 }  // namespace vp8
 
 using namespace vp8;
-
-extern "C" int vp8b200_entropy_boolcode(void *stream, const uint16_t *tokens, const uint32_t *part_info,
-                                        const uint32_t *coeff_probs, uint8_t *output, int32_t *partition_sizes,
-                                        int num_partitions, int partition_step) {
-    if (num_partitions < 1 || num_partitions > 8) return -(int)cudaErrorInvalidValue;
-    k_entropy_boolcode<<<num_partitions, 32, 0, (cudaStream_t)stream>>>(tokens, part_info, coeff_probs, output, partition_sizes,
-                                                                         num_partitions, partition_step);
-    VP8_LAUNCH_CHECK();
-}
 
 extern "C" int vp8b200_entropy_tokens(void *stream, const int16_t *MB, const int32_t *MB_non_zero_coeffs,
                                       const int32_t *MB_parts, int mb_width, int mb_height, int num_partitions,
@@ -508,5 +620,45 @@ extern "C" int vp8b200_entropy_tokens(void *stream, const int16_t *MB, const int
     k_entropy_scan<true><<<grid, ENT_WARPS * 32, 0, st>>>(MB, MB_non_zero_coeffs, MB_parts, mb_width, mb_height, P, nullptr,
                                                          nullptr, nullptr, nullptr, nullptr, mb_offset, part_info, tokens,
                                                          capacity);
+    VP8_LAUNCH_CHECK();
+}
+
+static size_t bc_align(size_t x) { return (x + 255) & ~(size_t)255; }
+static void bc_carve(BoolcodeScratch &sc, void *scratch, uint32_t max_decisions, int P, int partition_step, size_t *total) {
+    const size_t chunks = (size_t)max_decisions / BC_CHUNK + P + 1;
+    const uint32_t wpp = (uint32_t)(partition_step / 4 + 4);
+    char *base = (char *)scratch;
+    size_t off = 0;
+    sc.map_range = (uint8_t *)(base + off); off += bc_align(chunks * 128);
+    sc.map_shift = (uint16_t *)(base + off); off += bc_align(chunks * 128 * 2);
+    sc.start_range = (uint8_t *)(base + off); off += bc_align(chunks);
+    sc.start_shift = (uint32_t *)(base + off); off += bc_align(chunks * 4);
+    sc.params = (uint32_t *)(base + off); off += bc_align(8 * 4 * 4);
+    sc.words = (unsigned long long *)(base + off); off += bc_align((size_t)P * wpp * 8);
+    sc.words_per_partition = wpp;
+    *total = off;
+}
+
+extern "C" size_t vp8b200_entropy_boolcode_scratch_bytes(uint32_t max_decisions, int num_partitions, int partition_step) {
+    BoolcodeScratch sc;
+    size_t total = 0;
+    bc_carve(sc, nullptr, max_decisions, num_partitions, partition_step, &total);
+    return total;
+}
+
+extern "C" int vp8b200_entropy_boolcode(void *stream, const uint16_t *tokens, const uint32_t *part_info,
+                                        const uint32_t *coeff_probs, uint8_t *output, int32_t *partition_sizes,
+                                        int num_partitions, int partition_step, uint32_t max_decisions, void *scratch) {
+    const int P = num_partitions;
+    if (P < 1 || P > 8 || partition_step < 4 || !scratch) return -(int)cudaErrorInvalidValue;
+    cudaStream_t st = (cudaStream_t)stream;
+    BoolcodeScratch sc;
+    size_t total = 0;
+    bc_carve(sc, scratch, max_decisions, P, partition_step, &total);
+    const unsigned chunks = max_decisions / BC_CHUNK + 1;  // per partition, at most
+    k_boolcode_maps<<<dim3((chunks + BC_A_WARPS - 1) / BC_A_WARPS, P), BC_A_WARPS * 32, 0, st>>>(tokens, part_info, coeff_probs, P, sc);
+    k_boolcode_chain<<<P, 256, 0, st>>>(part_info, P, sc, partition_step);
+    k_boolcode_terms<<<dim3((chunks + 127) / 128, P), 128, 0, st>>>(tokens, part_info, coeff_probs, P, sc);
+    k_boolcode_emit<<<P, BC_D_THREADS, 0, st>>>(sc, output, partition_sizes, partition_step);
     VP8_LAUNCH_CHECK();
 }

@@ -149,11 +149,19 @@ def entropy_tokens(MB, MB_non_zero_coeffs, MB_parts, mb_width, mb_height, num_pa
                                         _p(part_info), _p(tail_scratch)), "entropy_tokens")
 
 
-def entropy_boolcode(tokens, part_info, coeff_probs, output, partition_sizes, num_partitions, partition_step):
+def entropy_boolcode(tokens, part_info, coeff_probs, output, partition_sizes, num_partitions, partition_step, max_decisions):
     """encode_coefficients (src/CPU_kernels.cl:541-778) over the decision streams of entropy_tokens: RFC 6386's
-    boolean coder on the GPU, one warp per partition; partition p lands at output[p * partition_step:]"""
-    _check(lib().vp8b200_entropy_boolcode(_stream(), _p(tokens), _p(part_info), _p(coeff_probs), _p(output),
-                                          _p(partition_sizes), num_partitions, partition_step), "entropy_boolcode")
+    boolean coder on the GPU in parallel; partition p lands at output[p * partition_step:].  max_decisions: upper
+    bound of the decisions of one partition (the total of part_info will do)"""
+    import torch
+    L = lib()
+    L.vp8b200_entropy_boolcode_scratch_bytes.restype = ctypes.c_size_t
+    need = L.vp8b200_entropy_boolcode_scratch_bytes(ctypes.c_uint32(max_decisions), num_partitions, partition_step)
+    scratch = torch.empty(need, dtype=torch.uint8, device=tokens.device)
+    _check(L.vp8b200_entropy_boolcode(_stream(), _p(tokens), _p(part_info), _p(coeff_probs), _p(output),
+                                      _p(partition_sizes), num_partitions, partition_step,
+                                      ctypes.c_uint32(max_decisions), _p(scratch)), "entropy_boolcode")
+    return scratch  # (keep it alive until the stream has run)
 
 
 # ---------------------------------------------------------------------------------------------
