@@ -10,9 +10,10 @@
 //  * clCreateProgramWithSource ignores the text; clCreateKernel(name) resolves to a native
 //    launcher; clSetKernelArg records the bytes; clEnqueueNDRangeKernel dispatches.
 //  * Kernels of the "GPU program" and the loop filter / filter mask of the "CPU program" are
-//    CUDA kernels.  The three boolean-coder kernels of the CPU program run on host threads
-//    (entropy_host.cpp).  There is no CPU fallback for anything else: without a CUDA device
-//    platform discovery fails.
+//    CUDA kernels.  Of the three boolean-coder kernels of the CPU program, count_probs and
+//    encode_coefficients are CUDA as well (entropy_kernels.cu: statistics, decision streams, parallel bool
+//    coder), num_div_denom runs on the host; entropy_host.cpp holds the host implementation of all three
+//    (fallback and test pin).  Without a CUDA device platform discovery fails.
 //  * Every buffer has a device allocation and, on demand, a pinned host mirror with validity
 //    flags; map/unmap and the host-executed kernels use the mirror, everything else the device.
 //  * Kernel enqueues and device-to-device copies are DEFERRED: they collect in a command list that
@@ -530,8 +531,9 @@ template <class T> static inline T *hout(cl_kernel k, int i) { return (T *)host_
 
 // ---- coefficient entropy coding with the GPU doing everything but the bool coder --------
 // count_probs      -> vp8b200_entropy_tokens on the stream: statistics, contexts, decision streams
-// num_div_denom    -> host (1056 divisions), then the streams are fetched (sizes are known by then)
-// encode_coefficients -> host threads run the bool coder over the streams
+// num_div_denom    -> host (1056 divisions); the stream sizes are known by then
+// encode_coefficients -> vp8b200_entropy_boolcode on the stream (VP8B200_GPU_BOOLCODER=0: the streams are fetched and
+//                     host threads run the bool coder over them)
 // Streams larger than the scratch (dense key frames) make the scratch grow and the streams are written again.
 // Only a mismatch between the three calls (other buffers or geometry), an allocation failure or
 // VP8B200_GPU_TOKENS=0 select the host-only path of entropy_host.cpp.
