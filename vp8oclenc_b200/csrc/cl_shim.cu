@@ -71,6 +71,7 @@ struct _cl_mem {
     void *shadow;                // device snapshot, mirror-sized, allocated on first use
     bool shadow_valid;           // the shadow holds exactly what the (clean) mirror holds / would hold
     volatile bool lazy;          // the mirror has not been filled: PROT_NONE, fetch from the shadow on access
+    bool host_staged;            // the ranges the host is about to read are in the mirror already (stage_partitions)
 };
 
 enum KernelId {
@@ -242,7 +243,18 @@ static void start_gate(bool inter_frame_start) {
 // Waits for everything issued on the stream.  VP8B200_SYNC=sleep polls an event with short sleeps in
 // between instead of spinning: when more encoder instances than cores share the machine, the cores go
 // to the instances that have host work to do.
+// Asynchronous device-to-host copies the host may look at after its next map: an event behind the last of them
+// (clEnqueueMapBuffer waits for that, not for the kernels enqueued after it -- the loop filter of the frame before).
+static cudaEvent_t g_d2h_event = nullptr;
+static bool g_d2h_pending = false;
+static void note_async_d2h() {
+    if (!g_d2h_event) cudaEventCreateWithFlags(&g_d2h_event, cudaEventDisableTiming);
+    cudaEventRecord(g_d2h_event, g_stream);
+    g_d2h_pending = true;
+}
+
 static cudaError_t stream_sync() {
+    g_d2h_pending = false;
     if (g_sync_sleep_us <= 0) return cudaStreamSynchronize(g_stream);
     if (!g_sync_event) cudaEventCreateWithFlags(&g_sync_event, cudaEventDisableTiming);
     cudaError_t e = cudaEventRecord(g_sync_event, g_stream);
@@ -381,8 +393,10 @@ static bool park_download(_cl_mem *m, const void *src) {
     m->shadow_valid = true;
     m->host_dirty = false;
     m->guarded = false;
-    m->lazy = true;
-    mprotect(m->host, m->host_bytes, PROT_NONE);
+    if (!m->lazy) {  // (a mirror the host has not touched since the last download is still inaccessible)
+        m->lazy = true;
+        mprotect(m->host, m->host_bytes, PROT_NONE);
+    }
     return true;
 }
 static void drop_shadow(_cl_mem *m) { m->shadow_valid = false; }
@@ -468,6 +482,7 @@ static void *dev_ptr(cl_mem m, bool will_write) {
     }
     if (will_write) {
         m->host_valid = false;
+        m->host_staged = false;
         m->dev_matches_mirror = false;
         ++m->dev_version;
     }
@@ -503,11 +518,15 @@ static void *host_ptr(cl_mem m, bool will_write, bool discard = false, bool lazy
     return m->host;
 }
 
+// gather_frame() reads the partition sizes and then every partition with a blocking read of its own
+// (src/encIO.h:4-27).  When the sizes arrive, all partitions are fetched into the mirror behind one wait; the
+// reads that follow are served from there.
+static void stage_partitions(const int32_t *sizes);
+
 static void run_cmds();
 static inline void flush_pending() {
     if (!g_cmds.empty()) run_cmds();
 }
-
 // ---- kernel argument access ----------------------------------------------------------------
 static inline cl_mem arg_mem(cl_kernel k, int i) {
     cl_mem m;
@@ -547,6 +566,9 @@ struct TokenState {
     size_t capacity = 0, mbs = 0;
     void *bool_scratch = nullptr;  // vp8b200_entropy_boolcode's working memory
     size_t bool_scratch_bytes = 0;
+    // the partitions the GPU bool coder has just written: fetched in one go when the host asks for their sizes
+    cl_mem out_parts = nullptr, out_sizes = nullptr;
+    int out_step = 0;
 };
 static TokenState g_tok;
 static bool tokens_alloc_streams(size_t entries);
@@ -672,6 +694,9 @@ static bool tokens_encode(cl_kernel k) {
             cl_mem parts_out = arg_mem(k, 3), sizes = arg_mem(k, 4);
             parts_out->dev_valid = sizes->dev_valid = true;  // (both are only ever read as far as the kernels write them)
             g_kernel_launches += 4;
+            g_tok.out_parts = parts_out;
+            g_tok.out_sizes = sizes;
+            g_tok.out_step = step;
             return vp8b200_entropy_boolcode(g_stream, g_tok.dev_tokens, g_tok.dev_part_info, in<uint32_t>(k, 6),
                                             out<uint8_t>(k, 3), out<int32_t>(k, 4), g_tok.P, step, total,
                                             g_tok.bool_scratch) == 0;
@@ -686,6 +711,26 @@ static bool tokens_encode(cl_kernel k) {
     vp8host::encode_token_streams(g_tok.host_tokens, g_tok.host_part_info, hin<uint32_t>(k, 6), hout<uint8_t>(k, 3),
                                   hout<int32_t>(k, 4), g_tok.P, arg_int(k, 10));
     return true;
+}
+
+static void stage_partitions(const int32_t *sizes) {
+    cl_mem parts = g_tok.out_parts;
+    g_tok.out_sizes = nullptr;
+    g_tok.out_parts = nullptr;
+    if (!parts || !parts->dev_valid || !ensure_host_alloc(parts)) return;
+    materialise(parts);
+    unguard(parts);
+    for (int p = 0; p < g_tok.P; ++p) {
+        const size_t at = (size_t)p * g_tok.out_step;
+        if (sizes[p] <= 0 || sizes[p] > g_tok.out_step || at + sizes[p] > parts->size) return;  // (leave it to the reads)
+    }
+    for (int p = 0; p < g_tok.P; ++p) {
+        const size_t at = (size_t)p * g_tok.out_step;
+        cudaMemcpyAsync((char *)parts->host + at, (char *)parts->dev + at, sizes[p], cudaMemcpyDeviceToHost, g_stream);
+        g_d2h_bytes += sizes[p];
+    }
+    stream_sync();
+    parts->host_staged = true;
 }
 
 // executes one kernel now (GPU kernels: launches on the stream; entropy kernels: runs on host threads)
@@ -1113,6 +1158,7 @@ static cl_mem new_mem(size_t size, bool image, int w, int h, bool want_host, cl_
     m->shadow = nullptr;
     m->shadow_valid = false;
     m->lazy = false;
+    m->host_staged = false;
     // zero-filled like the reference runtime's calloc: block 24 of never-16x16 macroblocks and the
     // nets of never-searched blocks are read before they are first written (Q4, Q9)
     cudaError_t e = cudaMalloc(&m->dev, size ? size : 1);
@@ -1227,31 +1273,34 @@ cl_int clEnqueueReadBuffer(cl_command_queue, cl_mem m, cl_bool blocking, size_t 
         if (cl_mem t = mirror_of(ptr, size, &moff)) {
             const bool whole = moff == 0 && size == t->size;
             t->dev_matches_mirror = false;
-            if (whole) cancel_lazy(t);
-            else materialise(t);
-            drop_shadow(t);
-            if (m->dev_valid && whole && off == 0 && size == m->size && t != m) {
-                if (park_download(t, m->dev)) {  // no copy now: the host may never look (see "lazy downloads")
-                    t->twin = nullptr;
-                    parked = true;
-                } else {
+            if (m->dev_valid && whole && off == 0 && size == m->size && t != m && park_download(t, m->dev)) {
+                // no copy now: the host may never look (see "lazy downloads")
+                t->twin = nullptr;
+                parked = true;
+            } else {
+                if (whole) cancel_lazy(t);
+                else materialise(t);
+                drop_shadow(t);
+                if (m->dev_valid && whole && off == 0 && size == m->size && t != m) {
                     t->twin = m;
                     t->twin_version = m->dev_version;
                     guard(t);  // (the copy below is DMA: page protection does not concern it)
+                } else {
+                    t->twin = nullptr;
+                    unguard(t);
                 }
-            } else {
-                t->twin = nullptr;
-                unguard(t);
             }
         }
     }
     if (parked) {
         // nothing to wait for
-    } else if (m->dev_valid) {
+    } else if (m->dev_valid && !m->host_staged) {
         cudaError_t e = cudaMemcpyAsync(ptr, (char *)m->dev + off, size, cudaMemcpyDeviceToHost, g_stream);
         g_d2h_bytes += size;
         if (e != cudaSuccess) return cuda_rc(e);
         if (blocking || g_trace) stream_sync();
+        else note_async_d2h();
+        if (m == g_tok.out_sizes && blocking && off == 0 && size >= (size_t)g_tok.P * 4) stage_partitions((const int32_t *)ptr);
     } else {
         materialise(m);
         memcpy(ptr, (char *)m->host + off, size);
@@ -1302,6 +1351,7 @@ cl_int clEnqueueWriteBuffer(cl_command_queue, cl_mem m, cl_bool blocking, size_t
         g_h2d_bytes += size;
     }
     m->host_valid = false;
+    m->host_staged = false;
     m->dev_matches_mirror = false;
     ++m->dev_version;
     if (blocking) stream_sync();
@@ -1375,7 +1425,14 @@ void *clEnqueueMapBuffer(cl_command_queue, cl_mem m, cl_bool, cl_map_flags flags
         return nullptr;
     }
     // in-flight asynchronous reads into other mapped buffers must have landed before the host looks
-    stream_sync();
+    if (g_d2h_pending) {
+        if (g_sync_sleep_us > 0) {
+            stream_sync();
+        } else {
+            cudaEventSynchronize(g_d2h_event);
+            g_d2h_pending = false;
+        }
+    }
     m->mapped_for_write = writes;
     if (writes) {
         // the host owns the contents until the unmap; until it writes, the device copy still equals
