@@ -356,12 +356,12 @@ __global__ void k_entropy_finish(unsigned *part_info, unsigned *num, unsigned *d
 // coder of entropy_host.cpp, which is checked against the reference's kernel.)  So:
 //   A  the range is a state machine with 128 states: a warp walks a chunk of BC_CHUNK decisions from all 128
 //      possible ranges at once (4 per lane) and leaves the chunk's map: range in -> range out, sum of shifts;
-//   B  one warp per partition chains the maps (a shuffle per chunk): range and T at the start of every chunk, T_n;
+//   B  one thread per partition chains the maps out of shared memory: range and T at the start of every chunk, T_n;
 //   C  one thread per chunk walks it again from its now known start and adds split_i << (T' - T_i) into the
 //      partition's 32-bit words (64-bit accumulators: a few threads touch a word);
 //   D  per partition the words are reduced to 32 bits each, the remaining 0/1 carries resolved by a
 //      generate/propagate scan, and the bytes written most significant first.
-constexpr int BC_CHUNK = 256;
+constexpr int BC_CHUNK = 128;
 
 struct BoolcodeScratch {  // carved out of one allocation, see vp8b200_entropy_boolcode_scratch_bytes
     uint8_t *map_range;            // [chunks][128]
@@ -412,13 +412,19 @@ __global__ void __launch_bounds__(BC_A_WARPS * 32) k_boolcode_maps(const uint16_
             d = s_tab[e & 0x7ff] | ((e >> 15) << 8);
         }
         const int m = (int)min(32u, cnt - j0);
-        for (int j = 0; j < m; ++j) {
+        auto one = [&](int j) {
             const uint32_t dj = __shfl_sync(0xffffffffu, d, j);
             const uint32_t prob = dj & 255u;
             const bool bit = (dj >> 8) != 0;  // warp-uniform
             uint32_t split;
 #pragma unroll
             for (int q = 0; q < 4; ++q) R[q] = bc_step(R[q], prob, bit, T[q], split);
+        };
+        if (m == 32) {
+#pragma unroll 8
+            for (int j = 0; j < 32; ++j) one(j);
+        } else {
+            for (int j = 0; j < m; ++j) one(j);
         }
     }
     const size_t c = (size_t)bc_chunk_base(part_info, P, p) + k;
@@ -429,59 +435,76 @@ __global__ void __launch_bounds__(BC_A_WARPS * 32) k_boolcode_maps(const uint16_
     }
 }
 
-// B: one CTA per partition; warp 0 chains the maps, then everybody clears the partition's words
+// B: one CTA per partition.  The maps are staged through shared memory in blocks of 32 chunks (warps 1..7 load
+// block b + 1 while lane 0 of warp 0 walks block b: two dependent shared loads per chunk); then everybody clears
+// the partition's words.
+constexpr int BC_B_BLOCK = 32;
 __global__ void __launch_bounds__(256) k_boolcode_chain(const uint32_t *__restrict__ part_info, int P, BoolcodeScratch sc,
                                                         int partition_step) {
-    __shared__ uint32_t s_words;
-    const int p = blockIdx.x, lane = threadIdx.x & 31;
-    if (threadIdx.x < 32) {
-        const uint32_t n = part_info[P + p];
-        const uint32_t K = (n + BC_CHUNK - 1) / BC_CHUNK;
-        const size_t cb = bc_chunk_base(part_info, P, p);
-        uint32_t state = 255, T = 0;
-        uint32_t mr[4], ms[4];
-        auto load = [&](uint32_t k) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                mr[q] = sc.map_range[(cb + k) * 128 + 32 * q + lane];
-                ms[q] = sc.map_shift[(cb + k) * 128 + 32 * q + lane];
-            }
-        };
-        if (K) load(0);
-        for (uint32_t k = 0; k < K; ++k) {
-            if (lane == 0) {
-                sc.start_range[cb + k] = (uint8_t)state;
-                sc.start_shift[cb + k] = T;
-            }
-            const uint32_t cr[4] = {mr[0], mr[1], mr[2], mr[3]}, cs[4] = {ms[0], ms[1], ms[2], ms[3]};
-            if (k + 1 < K) load(k + 1);  // in flight while this chunk's entry is looked up
-            const int idx = (int)state - 128, src = idx & 31, q = idx >> 5;
-            uint32_t nr = 0, ns = 0;
-#pragma unroll
-            for (int qq = 0; qq < 4; ++qq) {
-                const uint32_t a = __shfl_sync(0xffffffffu, cr[qq], src), b = __shfl_sync(0xffffffffu, cs[qq], src);
-                if (qq == q) {
-                    nr = a;
-                    ns = b;
-                }
-            }
-            state = nr;
-            T += ns;
+    __shared__ __align__(16) uint8_t s_r[2][BC_B_BLOCK * 128];
+    __shared__ __align__(16) uint16_t s_s[2][BC_B_BLOCK * 128];
+    __shared__ uint32_t s_words, s_start_t[BC_B_BLOCK];
+    __shared__ uint8_t s_start_r[BC_B_BLOCK];
+    const int p = blockIdx.x, tid = threadIdx.x;
+    const uint32_t n = part_info[P + p];
+    const uint32_t K = (n + BC_CHUNK - 1) / BC_CHUNK;
+    const size_t cb = bc_chunk_base(part_info, P, p);
+    const uint32_t nblocks = (K + BC_B_BLOCK - 1) / BC_B_BLOCK;
+    // (the scratch regions are 256-byte aligned and a chunk's map is 128 entries: word / double-word copies)
+    auto stage = [&](uint32_t b, int buf, int t0, int nthreads) {
+        const uint32_t chunks = min((uint32_t)BC_B_BLOCK, K - b * BC_B_BLOCK);
+        const uint32_t *gr = reinterpret_cast<const uint32_t *>(sc.map_range + (cb + (size_t)b * BC_B_BLOCK) * 128);
+        const uint2 *gs = reinterpret_cast<const uint2 *>(sc.map_shift + (cb + (size_t)b * BC_B_BLOCK) * 128);
+        uint32_t *dr = reinterpret_cast<uint32_t *>(s_r[buf]);
+        uint2 *ds = reinterpret_cast<uint2 *>(s_s[buf]);
+        for (uint32_t i = t0; i < chunks * 32; i += nthreads) {
+            dr[i] = gr[i];
+            ds[i] = gs[i];
         }
+    };
+    if (nblocks) stage(0, 0, tid, 256);
+    __syncthreads();
+    uint32_t state = 255, T = 0;
+    for (uint32_t b = 0; b < nblocks; ++b) {
+        const int buf = b & 1;
+        if (tid >= 32) {
+            if (b + 1 < nblocks) stage(b + 1, buf ^ 1, tid - 32, 224);
+        } else if (tid == 0) {
+            const uint32_t chunks = min((uint32_t)BC_B_BLOCK, K - b * BC_B_BLOCK);
+            const uint8_t *mr = s_r[buf] - 128;    // indexed by the range itself
+            const uint16_t *ms = s_s[buf] - 128;
+#pragma unroll 4
+            for (uint32_t k = 0; k < chunks; ++k) {
+                s_start_r[k] = (uint8_t)state;
+                s_start_t[k] = T;
+                T += ms[k * 128 + state];
+                state = mr[k * 128 + state];
+            }
+        }
+        __syncthreads();
+        {   // the block's starts go out together
+            const uint32_t chunks = min((uint32_t)BC_B_BLOCK, K - b * BC_B_BLOCK);
+            if (tid < (int)chunks) {
+                const size_t c = cb + (size_t)b * BC_B_BLOCK + tid;
+                sc.start_range[c] = s_start_r[tid];
+                sc.start_shift[c] = s_start_t[tid];
+            }
+            if (tid < 32) __syncwarp();  // (all readers sit in warp 0, whose lane 0 refills the arrays next)
+        }
+    }
+    if (tid == 0) {
         const uint32_t m = T >= 24 ? (T - 24) / 8 + 1 : 0;
         const uint32_t bytes = m + 4, words = (bytes + 3) / 4;
-        if (lane == 0) {
-            // (a partition that does not fit its slot cannot be written; the reference has the same limit)
-            const bool fits = bytes <= (uint32_t)partition_step && words + 2 <= sc.words_per_partition;
-            sc.params[4 * p + 0] = 24 + 8 * m;
-            sc.params[4 * p + 1] = fits ? bytes : 0;
-            sc.params[4 * p + 2] = fits ? words : 0;
-            s_words = fits ? words + 2 : 0;
-        }
+        // (a partition that does not fit its slot cannot be written; the reference has the same limit)
+        const bool fits = bytes <= (uint32_t)partition_step && words + 2 <= sc.words_per_partition;
+        sc.params[4 * p + 0] = 24 + 8 * m;
+        sc.params[4 * p + 1] = fits ? bytes : 0;
+        sc.params[4 * p + 2] = fits ? words : 0;
+        s_words = fits ? words + 2 : 0;
     }
     __syncthreads();
     unsigned long long *w = sc.words + (size_t)p * sc.words_per_partition;
-    for (uint32_t i = threadIdx.x; i < s_words; i += blockDim.x) w[i] = 0ull;
+    for (uint32_t i = tid; i < s_words; i += blockDim.x) w[i] = 0ull;
 }
 
 // C: one thread per chunk
@@ -508,14 +531,11 @@ __global__ void __launch_bounds__(128) k_boolcode_terms(const uint16_t *__restri
             if (acc >> 32) atomicAdd(words + cur + 1, acc >> 32);
         }
     };
-    for (uint32_t j = 0; j < cnt; ++j) {
-        const uint32_t e = t[j];
-        const uint32_t prob = s_tab[e & 0x7ff];
-        const bool bit = (e >> 15) != 0;
+    auto one = [&](uint32_t d) {
         const uint32_t E = Tend - T;  // exponent of this decision's split
         uint32_t split;
-        R = bc_step(R, prob, bit, T, split);
-        if (bit) {
+        R = bc_step(R, d & 255u, (d >> 8) != 0, T, split);
+        if (d >> 8) {
             const int w = (int)(E >> 5);
             if (w != cur) {
                 flush();
@@ -524,6 +544,20 @@ __global__ void __launch_bounds__(128) k_boolcode_terms(const uint16_t *__restri
             }
             acc += (unsigned long long)split << (E & 31);
         }
+    };
+    uint32_t j = 0;
+    for (; j + 8 <= cnt; j += 8) {  // eight loads and table look-ups in flight ahead of the serial part
+        uint32_t d[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = t[j + i];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = s_tab[d[i] & 0x7ff] | ((d[i] >> 15) << 8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) one(d[i]);
+    }
+    for (; j < cnt; ++j) {
+        const uint32_t e = t[j];
+        one(s_tab[e & 0x7ff] | ((e >> 15) << 8));
     }
     flush();
 }
