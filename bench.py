@@ -164,7 +164,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ref-frames", type=int, default=6, help="timed frames of the CPU reference sample")
-    ap.add_argument("--segments", type=int, default=8, help="independent segments (engines, streams) per GPU in the `value` run")
+    ap.add_argument("--segments", type=int, default=16, help="independent segments (engines, streams) per GPU in the `value` run")
     ap.add_argument("--size", default="1920x1080", help="frame size WxH (default: the 1080p configuration the metric is quoted on; "
                                                          "other sizes are informational)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -478,7 +478,9 @@ def b200_arm(args, rank, world, local_rank, tmp, config):
                 daemon.active = os.path.exists(os.path.join(daemon.pipe, "control"))
             cores = os.cpu_count() or 2
             if daemon.active:
-                P = args.e2e_procs or max(1, min(32, (2 * cores) // world))
+                # two instances per host core, at most 32 per GPU and 128 on the node (the driver brings contexts up
+                # one after the other, about half a second each)
+                P = args.e2e_procs or max(1, min(32, (2 * cores) // world, max(4, 128 // world)))
             else:
                 P = args.e2e_procs or max(1, min(8, cores // max(2, 2 * world)))
             e2e_error = None

@@ -195,7 +195,7 @@ static bool cuda_init() {
 
 // Start gate for multi-instance throughput measurements (VP8B200_START_GATE=<dir>:<count>[:<frame>]): when the
 // host starts its <frame>-th inter frame (its <frame>-th reset_vectors launch; default 0 = at its first enqueue
-// call) an instance drops a file into <dir> and waits until <count> instances have done so (or 180 s have
+// call) an instance drops a file into <dir> and waits until <count> instances have done so (or 300 s have
 // passed).  Bringing up 32 instances takes the driver 15-30 s, one after the other (context creation, then module
 // loading and page pinning during the first frames); without the gate the first instances are done before the
 // last ones start and a short run never sees all of them encoding at the same time.  Not set: no effect.
@@ -226,7 +226,7 @@ static void start_gate(bool inter_frame_start) {
     snprintf(name, sizeof(name), "/ready.%d", (int)getpid());
     if (FILE *f = fopen((dir + name).c_str(), "w")) fclose(f);
     const unsigned long long t0 = now_ns();
-    while (now_ns() - t0 < 180ull * 1000000000ull) {
+    while (now_ns() - t0 < 300ull * 1000000000ull) {
         int n = 0;
         if (DIR *d = opendir(dir.c_str())) {
             while (dirent *e = readdir(d)) n += !strncmp(e->d_name, "ready.", 6);
