@@ -79,3 +79,55 @@ def test_entropy_kernels_match_reference(shim, nparts, seed, density, big):
     assert np.array_equal(sz_r, sz_o), "partition sizes"
     assert np.array_equal(out_r, out_o), "partition bytes"
     assert sz_r[:nparts].min() >= 4
+
+
+def _clz8(r):
+    s = 0
+    while r < 128:
+        r <<= 1
+        s += 1
+    return s
+
+
+@pytest.mark.parametrize("seed,n,mode", [(1, 0, "random"), (2, 1, "random"), (3, 7, "random"), (4, 300, "likely"),
+                                         (5, 3000, "likely"), (6, 3000, "extreme"), (7, 2500, "random"),
+                                         (8, 4000, "carries")])
+def test_bool_coder_output_is_one_big_sum(shim, seed, n, mode):
+    """The identity the GPU bool coder (entropy_kernels.cu) is built on, checked here on
+    the CPU against the serial coder of entropy_host.cpp (itself pinned against the reference's kernel): the
+    bytes of a partition are the big-endian digits of  sum_{bit_i = 1} split_i << (T' - T_i),  T' = 24 + 8 m,
+    m + 4 bytes, m = the bytes that leave during coding.  Carry propagation is just the carries of the sum."""
+    r = np.random.default_rng(seed)
+    if mode == "random":
+        prob = r.integers(1, 256, size=n)
+        bit = r.integers(0, 2, size=n)
+    elif mode == "likely":  # decisions that follow their probabilities
+        prob = r.integers(1, 256, size=n)
+        bit = (r.random(n) > prob / 256.0).astype(np.int64)
+    elif mode == "extreme":
+        prob = r.choice(np.array([1, 2, 128, 250, 254, 255]), size=n)
+        bit = r.integers(0, 2, size=n)
+    else:  # long runs of the improbable value: bottom creeps up to the top of the range, carries ripple
+        prob = np.full(n, 255)
+        bit = (r.random(n) < 0.97).astype(np.int64)
+    # the stream format of the GPU tokens: bit 15 value, bits 0-10 = 1056 + fixed probability
+    tokens = ((bit.astype(np.uint32) << 15) | (1056 + prob.astype(np.uint32))).astype(np.uint16)
+    info = np.array([0, n, n], np.uint32)
+    probs = np.zeros(1056, np.uint32)
+    out = np.zeros(n + 64, np.uint8)
+    size = np.zeros(8, np.int32)
+    shim.vp8b200_host_encode_token_streams(P(tokens), P(info), P(probs), P(out), P(size), 1, int(out.size))
+    # the sum
+    R, T, L = 255, 0, []
+    for p, b in zip(prob.tolist(), bit.tolist()):
+        split = 1 + (((R - 1) * p) >> 8)
+        if b:
+            L.append((split, T))
+        rr = R - split if b else split
+        s = _clz8(rr)
+        R, T = rr << s, T + s
+    m = (T - 24) // 8 + 1 if T >= 24 else 0
+    total = sum(a << (24 + 8 * m - t) for a, t in L)
+    assert total < 1 << (8 * (m + 4))
+    assert int(size[0]) == m + 4
+    assert bytes(out[:m + 4]) == total.to_bytes(m + 4, "big")
