@@ -435,64 +435,89 @@ __global__ void __launch_bounds__(BC_A_WARPS * 32) k_boolcode_maps(const uint16_
     }
 }
 
-// B: one CTA per partition.  The maps are staged through shared memory in blocks of 32 chunks (warps 1..7 load
-// block b + 1 while lane 0 of warp 0 walks block b: two dependent shared loads per chunk); then everybody clears
+// B: one CTA of eight warps per partition.  A round takes eight blocks of 32 chunks: all threads stage their
+// maps into shared memory; warp w composes block w for all 128 ranges at once (4 per lane: the block's own map);
+// one thread chains the eight block maps; then lane 0 of warp w walks block w from its now known start and leaves
+// the start of every chunk.  Range and sum of shifts carry over from round to round.  At the end everybody clears
 // the partition's words.
-constexpr int BC_B_BLOCK = 32;
-__global__ void __launch_bounds__(256) k_boolcode_chain(const uint32_t *__restrict__ part_info, int P, BoolcodeScratch sc,
-                                                        int partition_step) {
-    __shared__ __align__(16) uint8_t s_r[2][BC_B_BLOCK * 128];
-    __shared__ __align__(16) uint16_t s_s[2][BC_B_BLOCK * 128];
-    __shared__ uint32_t s_words, s_start_t[BC_B_BLOCK];
-    __shared__ uint8_t s_start_r[BC_B_BLOCK];
-    const int p = blockIdx.x, tid = threadIdx.x;
+constexpr int BC_B_BLOCK = 32, BC_B_WARPS = 8;
+constexpr size_t BC_B_SMEM = (size_t)BC_B_WARPS * BC_B_BLOCK * 128 * 3;  // ranges (1 byte) + shifts (2 bytes)
+__global__ void __launch_bounds__(BC_B_WARPS * 32) k_boolcode_chain(const uint32_t *__restrict__ part_info, int P,
+                                                                    BoolcodeScratch sc, int partition_step) {
+    extern __shared__ __align__(16) uint8_t s_dyn[];
+    uint16_t *s_s = reinterpret_cast<uint16_t *>(s_dyn);                           // [8][32][128]
+    uint8_t *s_r = s_dyn + (size_t)BC_B_WARPS * BC_B_BLOCK * 128 * 2;              // [8][32][128]
+    __shared__ uint8_t s_comp_r[BC_B_WARPS][128];
+    __shared__ uint32_t s_comp_t[BC_B_WARPS][128];
+    __shared__ uint32_t s_block_r[BC_B_WARPS], s_block_t[BC_B_WARPS], s_carry[2], s_words;
+    const int p = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t n = part_info[P + p];
     const uint32_t K = (n + BC_CHUNK - 1) / BC_CHUNK;
     const size_t cb = bc_chunk_base(part_info, P, p);
-    const uint32_t nblocks = (K + BC_B_BLOCK - 1) / BC_B_BLOCK;
-    // (the scratch regions are 256-byte aligned and a chunk's map is 128 entries: word / double-word copies)
-    auto stage = [&](uint32_t b, int buf, int t0, int nthreads) {
-        const uint32_t chunks = min((uint32_t)BC_B_BLOCK, K - b * BC_B_BLOCK);
-        const uint32_t *gr = reinterpret_cast<const uint32_t *>(sc.map_range + (cb + (size_t)b * BC_B_BLOCK) * 128);
-        const uint2 *gs = reinterpret_cast<const uint2 *>(sc.map_shift + (cb + (size_t)b * BC_B_BLOCK) * 128);
-        uint32_t *dr = reinterpret_cast<uint32_t *>(s_r[buf]);
-        uint2 *ds = reinterpret_cast<uint2 *>(s_s[buf]);
-        for (uint32_t i = t0; i < chunks * 32; i += nthreads) {
-            dr[i] = gr[i];
-            ds[i] = gs[i];
+    constexpr uint32_t ROUND = BC_B_WARPS * BC_B_BLOCK;  // chunks per round
+    if (tid == 0) {
+        s_carry[0] = 255;
+        s_carry[1] = 0;
+    }
+    for (uint32_t k0 = 0; k0 < K; k0 += ROUND) {
+        const uint32_t chunks = min(ROUND, K - k0);
+        {   // stage (the scratch regions are 256-byte aligned and a chunk's map is 128 entries: 16-byte copies)
+            const uint4 *gr = reinterpret_cast<const uint4 *>(sc.map_range + (cb + k0) * 128);
+            const uint4 *gs = reinterpret_cast<const uint4 *>(sc.map_shift + (cb + k0) * 128);
+            uint4 *dr = reinterpret_cast<uint4 *>(s_r), *ds = reinterpret_cast<uint4 *>(s_s);
+            for (uint32_t i = tid; i < chunks * 8; i += blockDim.x) dr[i] = gr[i];
+            for (uint32_t i = tid; i < chunks * 16; i += blockDim.x) ds[i] = gs[i];
         }
-    };
-    if (nblocks) stage(0, 0, tid, 256);
-    __syncthreads();
-    uint32_t state = 255, T = 0;
-    for (uint32_t b = 0; b < nblocks; ++b) {
-        const int buf = b & 1;
-        if (tid >= 32) {
-            if (b + 1 < nblocks) stage(b + 1, buf ^ 1, tid - 32, 224);
-        } else if (tid == 0) {
-            const uint32_t chunks = min((uint32_t)BC_B_BLOCK, K - b * BC_B_BLOCK);
-            const uint8_t *mr = s_r[buf] - 128;    // indexed by the range itself
-            const uint16_t *ms = s_s[buf] - 128;
-#pragma unroll 4
-            for (uint32_t k = 0; k < chunks; ++k) {
-                s_start_r[k] = (uint8_t)state;
-                s_start_t[k] = T;
-                T += ms[k * 128 + state];
-                state = mr[k * 128 + state];
+        __syncthreads();
+        const uint32_t first = warp * BC_B_BLOCK;                       // this warp's block inside the round
+        const uint32_t mine = first < chunks ? min((uint32_t)BC_B_BLOCK, chunks - first) : 0;
+        {   // the block's own map
+            uint32_t R[4], T[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) R[q] = 128 + 32 * q + lane;
+            for (uint32_t k = 0; k < mine; ++k) {
+                const uint8_t *mr = s_r + (size_t)(first + k) * 128 - 128;
+                const uint16_t *ms = s_s + (size_t)(first + k) * 128 - 128;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    T[q] += ms[R[q]];
+                    R[q] = mr[R[q]];
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                s_comp_r[warp][32 * q + lane] = (uint8_t)R[q];
+                s_comp_t[warp][32 * q + lane] = T[q];
             }
         }
         __syncthreads();
-        {   // the block's starts go out together
-            const uint32_t chunks = min((uint32_t)BC_B_BLOCK, K - b * BC_B_BLOCK);
-            if (tid < (int)chunks) {
-                const size_t c = cb + (size_t)b * BC_B_BLOCK + tid;
-                sc.start_range[c] = s_start_r[tid];
-                sc.start_shift[c] = s_start_t[tid];
+        if (tid == 0) {  // where every block starts
+            uint32_t state = s_carry[0], T = s_carry[1];
+            for (int w = 0; w < BC_B_WARPS; ++w) {
+                s_block_r[w] = state;
+                s_block_t[w] = T;
+                T += s_comp_t[w][state - 128];
+                state = s_comp_r[w][state - 128];   // (blocks past the end are the identity with no shift)
             }
-            if (tid < 32) __syncwarp();  // (all readers sit in warp 0, whose lane 0 refills the arrays next)
+            s_carry[0] = state;
+            s_carry[1] = T;
         }
+        __syncthreads();
+        if (lane == 0 && mine) {  // the starts of this block's chunks
+            uint32_t state = s_block_r[warp], T = s_block_t[warp];
+            for (uint32_t k = 0; k < mine; ++k) {
+                const size_t c = cb + k0 + first + k;
+                sc.start_range[c] = (uint8_t)state;
+                sc.start_shift[c] = T;
+                const uint32_t at = (first + k) * 128 + state - 128;
+                T += s_s[at];
+                state = s_r[at];
+            }
+        }
+        __syncthreads();
     }
     if (tid == 0) {
+        const uint32_t T = s_carry[1];
         const uint32_t m = T >= 24 ? (T - 24) / 8 + 1 : 0;
         const uint32_t bytes = m + 4, words = (bytes + 3) / 4;
         // (a partition that does not fit its slot cannot be written; the reference has the same limit)
@@ -691,7 +716,10 @@ extern "C" int vp8b200_entropy_boolcode(void *stream, const uint16_t *tokens, co
     bc_carve(sc, scratch, max_decisions, P, partition_step, &total);
     const unsigned chunks = max_decisions / BC_CHUNK + 1;  // per partition, at most
     k_boolcode_maps<<<dim3((chunks + BC_A_WARPS - 1) / BC_A_WARPS, P), BC_A_WARPS * 32, 0, st>>>(tokens, part_info, coeff_probs, P, sc);
-    k_boolcode_chain<<<P, 256, 0, st>>>(part_info, P, sc, partition_step);
+    // (96 KB of dynamic shared memory: above the default limit; per device, so it is set on every call)
+    if (cudaFuncSetAttribute(k_boolcode_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BC_B_SMEM) != cudaSuccess)
+        return -(int)cudaGetLastError();
+    k_boolcode_chain<<<P, BC_B_WARPS * 32, BC_B_SMEM, st>>>(part_info, P, sc, partition_step);
     k_boolcode_terms<<<dim3((chunks + 127) / 128, P), 128, 0, st>>>(tokens, part_info, coeff_probs, P, sc);
     k_boolcode_emit<<<P, BC_D_THREADS, 0, st>>>(sc, output, partition_sizes, partition_step);
     VP8_LAUNCH_CHECK();
