@@ -128,10 +128,6 @@ def run_encoder_timed(host_bin, lib_dir, workdir, y4m, ivf, frames_total, env_ex
     return stamps, "".join(out)
 
 
-def _tempfile_dir():
-    return tempfile.gettempdir()
-
-
 def reference_arm(args, tmp):
     """the reference's own CPU implementation: its host + its .cl kernels compiled for the CPU
     (oracle/_ref), all host cores (OpenMP), on a bounded sample of the same workload"""
@@ -387,13 +383,13 @@ def b200_arm(args, rank, world, local_rank, tmp, config):
     if not args.no_e2e:
         from vp8oclenc_b200 import segments
         if os.path.exists(segments.HOST_BIN):
-            # every instance encodes 1 key + W warm-up + Ke timed frames; Ke >= 80 so that the timed window is long
+            # every instance encodes 1 key + W warm-up + Ke timed frames; Ke >= 120 so that the timed window is long
             # against the scheduling noise of P processes on the host cores
             Ke = max(K, 120)
             n = 1 + W + Ke
             distinct = 8 if world == 1 else (4 if world == 2 else 2)  # clips per rank (they live in /dev/shm)
             clips = []
-            gate_root = "/dev/shm" if os.path.isdir("/dev/shm") else _tempfile_dir()
+            gate_root = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
 
             def run(P, tag, env_more=None):
                 # a few distinct segments per rank, written once; further instances re-encode one of them into their
