@@ -107,6 +107,22 @@ def test_shim_modes_same_bitstream(env, tmp_path):
     assert open(os.path.join(d, "ref.ivf"), "rb").read() == open(os.path.join(d, "b200.ivf"), "rb").read()
 
 
+def test_cif_60_frames_baseline_configuration_byte_identical(tmp_path):
+    """BASELINE configs[0]: 352x288 CIF, 60 frames, fixed q, against the reference's own kernels on the CPU"""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_y4m
+    args = ["-qmin", 24, "-qmax", 24, "-g", 60, "-altref-range", 5, "-partitions", 4, "-threads", 4]
+    d = str(tmp_path)
+    y4m = os.path.join(d, "clip.y4m")
+    gen_y4m.write_y4m(y4m, 352, 288, 60)
+    _trace.run_host(_trace.REF_DIR, d, y4m, os.path.join(d, "ref.ivf"), args)
+    _trace.run_host(SHIM_DIR, d, y4m, os.path.join(d, "b200.ivf"), args)
+    a = open(os.path.join(d, "ref.ivf"), "rb").read()
+    assert len(a) > 32 + 12 * 60
+    assert a == open(os.path.join(d, "b200.ivf"), "rb").read()
+
+
 def test_1080p_bench_configuration_byte_identical(tmp_path):
     """BASELINE configs[1] at full size (1920x1080 padded to 1088 lines, LAST+GOLDEN+ALTREF, 8 partitions, the
     options bench.py uses): a key frame and seven inter frames through the shim give the reference's bytes.
