@@ -137,3 +137,58 @@ def test_token_stream_overflow_is_reported():
     torch.cuda.synchronize()
     assert int(d_info.cpu().numpy().view(np.uint32)[2 * nparts]) > cap
     assert bool((d_tok == 0x5a5a).all())
+
+
+@pytest.mark.parametrize("seed,counts,mode", [(1, [0, 5, 1000], "random"), (2, [0, 0, 0, 0], "random"),
+                                              (3, [127, 128, 129, 255, 256, 257, 1, 4097], "likely"),
+                                              (4, [9000, 0, 33000], "carries"), (5, [70000], "likely")])
+def test_boolcode_synthetic_streams(seed, counts, mode):
+    """vp8b200_entropy_boolcode on hand-made decision streams -- empty partitions, chunk-boundary lengths, long
+    runs of 0xff bytes that carries ripple through, more than one round of the chain kernel -- against the host
+    bool coder"""
+    import torch
+    from vp8oclenc_b200 import host as eng
+    L = eng.lib()
+    H = ctypes.CDLL(SHIM)
+    r = np.random.default_rng(seed)
+    P_ = len(counts)
+    toks = []
+    for n in counts:
+        if mode == "random":
+            prob, bit = r.integers(1, 256, size=n), r.integers(0, 2, size=n)
+        elif mode == "likely":
+            prob = r.integers(1, 256, size=n)
+            bit = (r.random(n) > prob / 256.0).astype(np.int64)
+        else:
+            prob, bit = np.full(n, 255), (r.random(n) < 0.97).astype(np.int64)
+        toks.append(((bit.astype(np.uint32) << 15) | (1056 + prob.astype(np.uint32))).astype(np.uint16))
+    tokens = np.concatenate(toks + [np.zeros(8, np.uint16)])
+    total = int(sum(counts))
+    info = np.zeros(32, np.uint32)
+    info[:P_] = np.concatenate([[0], np.cumsum(counts)[:-1]])
+    info[P_:2 * P_] = counts
+    info[2 * P_] = total
+    step = 2 * max(counts) + 64
+    probs = np.zeros(1056, np.uint32)
+    pp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    out_h = np.zeros(step * P_ + 64, np.uint8)
+    size_h = np.zeros(8, np.int32)
+    H.vp8b200_host_encode_token_streams(pp(tokens), pp(info), pp(probs), pp(out_h), pp(size_h), P_, step)
+
+    dev = lambda a: torch.from_numpy(a).cuda()
+    D = lambda t: ctypes.c_void_p(t.data_ptr())
+    d_tok, d_info, d_probs = dev(tokens.view(np.int16)), dev(info.view(np.int32)), dev(probs.view(np.int32))
+    d_out = torch.zeros(step * P_ + 64, dtype=torch.uint8, device="cuda")
+    d_size = torch.zeros(8, dtype=torch.int32, device="cuda")
+    L.vp8b200_entropy_boolcode_scratch_bytes.restype = ctypes.c_size_t
+    need = L.vp8b200_entropy_boolcode_scratch_bytes(ctypes.c_uint32(total), P_, step)
+    d_scratch = torch.empty(need, dtype=torch.uint8, device="cuda")
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    assert L.vp8b200_entropy_boolcode(st, D(d_tok), D(d_info), D(d_probs), D(d_out), D(d_size), P_, step,
+                                      ctypes.c_uint32(total), D(d_scratch)) == 0
+    torch.cuda.synchronize()
+    size_d = d_size.cpu().numpy()
+    assert np.array_equal(size_d[:P_], size_h[:P_]), (size_d, size_h)
+    out_d = d_out.cpu().numpy()
+    for p in range(P_):
+        assert np.array_equal(out_d[p * step:p * step + size_h[p]], out_h[p * step:p * step + size_h[p]]), "partition %d" % p
