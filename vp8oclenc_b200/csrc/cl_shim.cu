@@ -360,7 +360,9 @@ static void unguard(_cl_mem *m) {
 // looks at those bytes: for inter frames it forwards the pointers to other device objects.  In this mode a
 // download that fills a whole mirror is parked in a device-side shadow copy (a device-to-device copy on the
 // stream) and the mirror is made inaccessible; forwarding uses the shadow (see device_twin_of_mirror), and the
-// first load or store of the host faults and fetches the bytes then (guard_fault).
+// first load or store of the host faults and fetches the bytes then (guard_fault).  Limitation, as for the dirty
+// tracking: a system call handed a pointer into a parked mirror (write(2) of a mapped buffer) gets EFAULT instead
+// of a fault; the reference host only ever touches these buffers with its own loads and stores.
 static void fill_from_shadow(_cl_mem *m) {
     mprotect(m->host, m->host_bytes, PROT_READ | PROT_WRITE);
     cudaMemcpyAsync(m->host, m->shadow, m->size, cudaMemcpyDeviceToHost, g_stream);
