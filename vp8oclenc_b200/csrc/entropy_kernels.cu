@@ -334,12 +334,29 @@ __global__ void k_entropy_finish(unsigned *part_info, unsigned *num, unsigned *d
     }
     if (t < P * 4) {
         const int p = t >> 2, type = t & 3;
+        // (loads first, then the sums per coefficient band, then one update per band: the fifteen positions
+        // share seven bands, and nothing here waits for a store it has just issued)
+        unsigned tl[16], add[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int i = 1; i < 16; ++i) tl[i] = tail[p * 68 + type * 17 + i];
         unsigned running = 0;
+#pragma unroll
         for (int i = 1; i < 16; ++i) {
-            running += tail[p * 68 + type * 17 + i];
-            const int idx = ent_ctx_index(type, ent_band(i), 2, 0);
-            num[(size_t)p * 1056 + idx] += running;
-            den[(size_t)p * 1056 + idx] += running;
+            running += tl[i];
+            add[ent_band(i)] += running;
+        }
+        unsigned n0[8], d0[8];
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int idx = ent_ctx_index(type, b, 2, 0);
+            n0[b] = num[(size_t)p * 1056 + idx];
+            d0[b] = den[(size_t)p * 1056 + idx];
+        }
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int idx = ent_ctx_index(type, b, 2, 0);
+            num[(size_t)p * 1056 + idx] = n0[b] + add[b];
+            den[(size_t)p * 1056 + idx] = d0[b] + add[b];
         }
     }
 }
