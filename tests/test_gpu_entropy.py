@@ -141,11 +141,12 @@ def test_token_stream_overflow_is_reported():
 
 @pytest.mark.parametrize("seed,counts,mode", [(1, [0, 5, 1000], "random"), (2, [0, 0, 0, 0], "random"),
                                               (3, [127, 128, 129, 255, 256, 257, 1, 4097], "likely"),
-                                              (4, [9000, 0, 33000], "carries"), (5, [70000], "likely")])
+                                              (4, [9000, 0, 33000], "carries"), (5, [70000], "likely"),
+                                              (6, [3000, 40, 700], "nomerge")])
 def test_boolcode_synthetic_streams(seed, counts, mode):
     """vp8b200_entropy_boolcode on hand-made decision streams -- empty partitions, chunk-boundary lengths, long
-    runs of 0xff bytes that carries ripple through, more than one round of the chain kernel -- against the host
-    bool coder"""
+    runs of 0xff bytes that carries ripple through, more than one round of the chain kernel, trajectories that never
+    merge -- against the host bool coder"""
     import torch
     from vp8oclenc_b200 import host as eng
     L = eng.lib()
@@ -159,6 +160,8 @@ def test_boolcode_synthetic_streams(seed, counts, mode):
         elif mode == "likely":
             prob = r.integers(1, 256, size=n)
             bit = (r.random(n) > prob / 256.0).astype(np.int64)
+        elif mode == "nomerge":  # the range only ever steps down by one: the 128 trajectories never fall together
+            prob, bit = np.full(n, 1), np.ones(n, np.int64)
         else:
             prob, bit = np.full(n, 255), (r.random(n) < 0.97).astype(np.int64)
         toks.append(((bit.astype(np.uint32) << 15) | (1056 + prob.astype(np.uint32))).astype(np.uint16))

@@ -372,7 +372,8 @@ __global__ void k_entropy_finish(unsigned *part_info, unsigned *num, unsigned *d
 // Carry propagation into bytes already written is just the carries of this sum.  (Checked against the serial
 // coder of entropy_host.cpp, which is checked against the reference's kernel.)  So:
 //   A  the range is a state machine with 128 states: a warp walks a chunk of BC_CHUNK decisions from all 128
-//      possible ranges at once (4 per lane) and leaves the chunk's map: range in -> range out, sum of shifts;
+//      possible ranges at once (4 per lane; after 32 decisions one per lane for the ranges that are still
+//      distinct) and leaves the chunk's map: range in -> range out, sum of shifts;
 //   B  one thread per partition chains the maps out of shared memory: range and T at the start of every chunk, T_n;
 //   C  one thread per chunk walks it again from its now known start and adds split_i << (T' - T_i) into the
 //      partition's 32-bit words (64-bit accumulators: a few threads touch a word);
@@ -419,10 +420,14 @@ __global__ void __launch_bounds__(BC_A_WARPS * 32) k_boolcode_maps(const uint16_
     if (k * BC_CHUNK >= n) return;  // whole warp
     const uint16_t *t = tokens + part_info[p] + (size_t)k * BC_CHUNK;
     const uint32_t cnt = min((uint32_t)BC_CHUNK, n - k * BC_CHUNK);
+    __shared__ uint32_t s_seen[BC_A_WARPS][4];
+    const int warp = threadIdx.x >> 5;
     uint32_t R[4], T[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int q = 0; q < 4; ++q) R[q] = 128 + 32 * q + lane;
-    for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
+    // 32 decisions (one coalesced read of the stream) applied to NS ranges per lane
+    auto batch = [&](uint32_t j0, uint32_t *Rs, uint32_t *Ts, auto ns) {
+        constexpr int NS = decltype(ns)::value;
         uint32_t d = 0;
         if (j0 + lane < cnt) {
             const uint32_t e = t[j0 + lane];
@@ -435,13 +440,54 @@ __global__ void __launch_bounds__(BC_A_WARPS * 32) k_boolcode_maps(const uint16_
             const bool bit = (dj >> 8) != 0;  // warp-uniform
             uint32_t split;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) R[q] = bc_step(R[q], prob, bit, T[q], split);
+            for (int q = 0; q < NS; ++q) Rs[q] = bc_step(Rs[q], prob, bit, Ts[q], split);
         };
         if (m == 32) {
 #pragma unroll 8
             for (int j = 0; j < 32; ++j) one(j);
         } else {
             for (int j = 0; j < m; ++j) one(j);
+        }
+    };
+    struct Four { enum { value = 4 }; };
+    struct One { enum { value = 1 }; };
+    batch(0, R, T, Four());
+    if (cnt > 32) {
+        // The 128 trajectories fall together quickly (about 15 distinct ranges are left after 32 decisions of a
+        // typical stream).  If at most 32 are left, the rest of the chunk is walked once per distinct range, one per
+        // lane, and every start range inherits the outcome of the one it has merged with.
+        if (lane < 4) s_seen[warp][lane] = 0;
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) atomicOr(&s_seen[warp][(R[q] - 128) >> 5], 1u << ((R[q] - 128) & 31));
+        __syncwarp();
+        const uint32_t m0 = s_seen[warp][0], m1 = s_seen[warp][1], m2 = s_seen[warp][2], m3 = s_seen[warp][3];
+        const int c0 = __popc(m0), c1 = __popc(m1), c2 = __popc(m2), c3 = __popc(m3);
+        if (c0 + c1 + c2 + c3 <= 32) {  // warp-uniform
+            int rep[4];  // which lane carries the range this one has become
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int idx = (int)R[q] - 128, w = idx >> 5, b = idx & 31;
+                const uint32_t mw = w == 0 ? m0 : w == 1 ? m1 : w == 2 ? m2 : m3;
+                rep[q] = (w > 0 ? c0 : 0) + (w > 1 ? c1 : 0) + (w > 2 ? c2 : 0) + __popc(mw & ((1u << b) - 1u));
+            }
+            // lane r carries the r-th distinct range (lanes past the count carry a dummy)
+            uint32_t Rr = 128, Tr = 0;
+            {
+                int r = lane;
+                if (r < c0) Rr = 128 + __fns(m0, 0, r + 1);
+                else if ((r -= c0) < c1) Rr = 160 + __fns(m1, 0, r + 1);
+                else if ((r -= c1) < c2) Rr = 192 + __fns(m2, 0, r + 1);
+                else if ((r -= c2) < c3) Rr = 224 + __fns(m3, 0, r + 1);
+            }
+            for (uint32_t j0 = 32; j0 < cnt; j0 += 32) batch(j0, &Rr, &Tr, One());
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                R[q] = __shfl_sync(0xffffffffu, Rr, rep[q]);
+                T[q] += __shfl_sync(0xffffffffu, Tr, rep[q]);
+            }
+        } else {
+            for (uint32_t j0 = 32; j0 < cnt; j0 += 32) batch(j0, R, T, Four());
         }
     }
     const size_t c = (size_t)bc_chunk_base(part_info, P, p) + k;
