@@ -46,6 +46,64 @@ static void trace_init() {
     if (p && *p) g_trace = fopen(p, "wb");
 }
 
+// ---- host-gap profiler (VP8CL_GAPS=<file>): where does the HOST PROGRAM spend its own time? ---------------
+// The time between the return of one entry point and the call of the next is the host program's own work.  It is
+// accumulated per (previous call, next call) pair, labels = entry point + object index / kernel name, and the
+// largest pairs are written at exit.  The host is the same code whatever runtime it is linked against, so this
+// profile (taken on the CPU runtime) says what the unmodified host costs per frame next to the CUDA shim.
+#include <time.h>
+#include <map>
+#include <string>
+#include <vector>
+#include <algorithm>
+static bool g_gaps_on = false;
+static std::string g_gap_prev = "start";
+static unsigned long long g_gap_t = 0, g_gap_frames = 0;
+static std::map<std::string, std::pair<unsigned long long, unsigned long long>> g_gaps;
+static unsigned long long gap_now() {
+    timespec ts;
+    clock_gettime(CLOCK_THREAD_CPUTIME_ID, &ts);
+    return (unsigned long long)ts.tv_sec * 1000000000ull + ts.tv_nsec;
+}
+static void gaps_write() {
+    const char *p = getenv("VP8CL_GAPS");
+    FILE *f = p ? fopen(p, "w") : nullptr;
+    if (!f) return;
+    std::vector<std::pair<unsigned long long, std::string>> v;
+    unsigned long long total = 0;
+    for (auto &kv : g_gaps) { v.push_back({kv.second.first, kv.first}); total += kv.second.first; }
+    std::sort(v.rbegin(), v.rend());
+    fprintf(f, "host program between OpenCL calls: %.3f ms total over %llu inter frames (+ key frames)\n", total * 1e-6, g_gap_frames);
+    for (size_t i = 0; i < v.size() && i < 40; ++i)
+        fprintf(f, "%10.3f ms %8llu x  %s\n", v[i].first * 1e-6, g_gaps[v[i].second].second, v[i].second.c_str());
+    fclose(f);
+}
+struct GapScope {  // at entry: close the gap; at exit: start the next one
+    const char *fn;
+    std::string label;
+    GapScope(const char *f, const char *what, long idx) : fn(f) {
+        if (!g_gaps_on) return;
+        char b[96];
+        if (what) snprintf(b, sizeof(b), "%s(%s)", f, what); else if (idx >= 0) snprintf(b, sizeof(b), "%s(#%ld)", f, idx); else snprintf(b, sizeof(b), "%s", f);
+        label = b;
+        const unsigned long long t = gap_now();
+        auto &g = g_gaps[g_gap_prev + " -> " + label];
+        g.first += t - g_gap_t;
+        g.second += 1;
+    }
+    ~GapScope() {
+        if (!g_gaps_on) return;
+        g_gap_prev = label;
+        g_gap_t = gap_now();
+    }
+};
+static void gaps_init() {
+    static bool done = false;
+    if (done) return;
+    done = true;
+    if (getenv("VP8CL_GAPS")) { g_gaps_on = true; g_gap_t = gap_now(); atexit(gaps_write); }
+}
+
 extern "C" const clc::kernel_desc vp8ref_gpu_kernels[];
 extern "C" const clc::kernel_desc vp8ref_cpu_kernels[];
 
@@ -83,6 +141,7 @@ static cl_int put_info(const void *src, size_t n, size_t cap, void *dst, size_t 
 extern "C" {
 
 cl_int clGetPlatformIDs(cl_uint num_entries, cl_platform_id *platforms, cl_uint *num_platforms) {
+    gaps_init();
     if (num_platforms) *num_platforms = 1;
     if (platforms && num_entries >= 1) platforms[0] = &g_platform;
     return CL_SUCCESS;
@@ -203,6 +262,7 @@ cl_kernel clCreateKernel(cl_program prog, const char *name, cl_int *err) {
 cl_int clReleaseKernel(cl_kernel k) { delete k; return CL_SUCCESS; }
 
 cl_int clSetKernelArg(cl_kernel k, cl_uint idx, size_t size, const void *value) {
+    GapScope gs("setarg", nullptr, -1);
     if (!k) return CL_INVALID_KERNEL;
     if ((int)idx >= k->desc->nargs) return CL_INVALID_ARG_INDEX;
     if (size > 16) return CL_INVALID_ARG_SIZE;
@@ -214,6 +274,7 @@ cl_int clSetKernelArg(cl_kernel k, cl_uint idx, size_t size, const void *value) 
 
 cl_int clEnqueueNDRangeKernel(cl_command_queue, cl_kernel k, cl_uint dim, const size_t *, const size_t *gsz,
                               const size_t *lsz, cl_uint, const cl_event *, cl_event *) {
+    GapScope gs("kernel", k ? k->desc->name : "?", -1); if (g_gaps_on && k && !strcmp(k->desc->name, "reset_vectors")) ++g_gap_frames;
     if (!k) return CL_INVALID_KERNEL;
     if (dim != 1) return CL_INVALID_WORK_DIMENSION;
     const int n = k->desc->nargs;
@@ -249,6 +310,7 @@ cl_int clEnqueueNDRangeKernel(cl_command_queue, cl_kernel k, cl_uint dim, const 
 
 cl_int clEnqueueReadBuffer(cl_command_queue, cl_mem m, cl_bool, size_t off, size_t size, void *ptr, cl_uint,
                            const cl_event *, cl_event *) {
+    GapScope gs("read", nullptr, m ? (long)m->index : -1);
     if (!m || off + size > m->size) return CL_INVALID_VALUE;
     memcpy(ptr, m->data + off, size);
     trace_rec(3, m->index, off, size, ptr);
@@ -256,6 +318,7 @@ cl_int clEnqueueReadBuffer(cl_command_queue, cl_mem m, cl_bool, size_t off, size
 }
 cl_int clEnqueueWriteBuffer(cl_command_queue, cl_mem m, cl_bool, size_t off, size_t size, const void *ptr, cl_uint,
                             const cl_event *, cl_event *) {
+    GapScope gs("write", nullptr, m ? (long)m->index : -1);
     if (!m || off + size > m->size) return CL_INVALID_VALUE;
     memcpy(m->data + off, ptr, size);
     trace_rec(2, m->index, off, size, ptr);
@@ -263,12 +326,14 @@ cl_int clEnqueueWriteBuffer(cl_command_queue, cl_mem m, cl_bool, size_t off, siz
 }
 cl_int clEnqueueCopyBuffer(cl_command_queue, cl_mem s, cl_mem d, size_t so, size_t dof, size_t size, cl_uint,
                            const cl_event *, cl_event *) {
+    GapScope gs("copy", nullptr, -1);
     if (!s || !d || so + size > s->size || dof + size > d->size) return CL_INVALID_VALUE;
     memmove(d->data + dof, s->data + so, size);
     return CL_SUCCESS;
 }
 cl_int clEnqueueWriteImage(cl_command_queue, cl_mem img, cl_bool, const size_t *origin, const size_t *region,
                            size_t row_pitch, size_t, const void *ptr, cl_uint, const cl_event *, cl_event *) {
+    GapScope gs("writeimage", nullptr, img ? (long)img->index : -1);
     if (!img || !img->is_image) return CL_INVALID_MEM_OBJECT;
     const size_t pitch = row_pitch ? row_pitch : region[0];
     for (size_t y = 0; y < region[1]; ++y)
@@ -279,6 +344,7 @@ cl_int clEnqueueWriteImage(cl_command_queue, cl_mem img, cl_bool, const size_t *
 }
 cl_int clEnqueueCopyImage(cl_command_queue, cl_mem s, cl_mem d, const size_t *so, const size_t *dor,
                           const size_t *region, cl_uint, const cl_event *, cl_event *) {
+    GapScope gs("copyimage", nullptr, -1);
     if (!s || !d || !s->is_image || !d->is_image) return CL_INVALID_MEM_OBJECT;
     for (size_t y = 0; y < region[1]; ++y)
         memmove(d->data + (dor[1] + y) * d->img.width + dor[0], s->data + (so[1] + y) * s->img.width + so[0],
@@ -287,6 +353,7 @@ cl_int clEnqueueCopyImage(cl_command_queue, cl_mem s, cl_mem d, const size_t *so
 }
 void *clEnqueueMapBuffer(cl_command_queue, cl_mem m, cl_bool, cl_map_flags, size_t off, size_t size, cl_uint,
                          const cl_event *, cl_event *, cl_int *err) {
+    GapScope gs("map", nullptr, m ? (long)m->index : -1);
     if (!m || off + size > m->size) {
         if (err) *err = CL_INVALID_VALUE;
         return nullptr;
@@ -295,11 +362,16 @@ void *clEnqueueMapBuffer(cl_command_queue, cl_mem m, cl_bool, cl_map_flags, size
     return m->data + off;
 }
 cl_int clEnqueueUnmapMemObject(cl_command_queue, cl_mem m, void *, cl_uint, const cl_event *, cl_event *) {
+    GapScope gs("unmap", nullptr, m ? (long)m->index : -1);
     if (m) trace_rec(5, m->index, 0, m->size, m->data); /* kind 5: contents handed back by the host */
     return CL_SUCCESS;
 }
-cl_int clFlush(cl_command_queue) { return CL_SUCCESS; }
+cl_int clFlush(cl_command_queue) {
+    GapScope gs("flush", nullptr, -1);
+    return CL_SUCCESS;
+}
 cl_int clFinish(cl_command_queue) {
+    GapScope gs("finish", nullptr, -1);
     if (g_trace) fflush(g_trace);
     return CL_SUCCESS;
 }

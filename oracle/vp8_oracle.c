@@ -252,19 +252,58 @@ void vp8o_pack_8x8_into_16x16(const int16_t *MB_vectors, int32_t *MB_parts, floa
 
 /* "predictor flavour" (construct, lines 574-774): source lines Y-2..Y+3 saturate, lines
  * Y+4..Y+6 are stored with a wrapping (uchar) cast (Q5); vertical results saturate */
-static void predict4x4_construct(const uint8_t *img, int w, int h, int ox, int oy, int fx, int fy, int out[16]) {
-    int line[9][4];
+static int predict4x4_construct(const uint8_t *img, int w, int h, int ox, int oy, int fx, int fy, int out[16]) {
+    int line[9][4], wrapped = 0;
     for (int l = 0; l < 9; ++l)
         for (int c = 0; c < 4; ++c) {
             const int v = hraw(img, w, h, ox + c, oy - 2 + l, fx);
             line[l][c] = (l < 6) ? sat8(v) : (v & 255);
+            wrapped |= (l >= 6) && (v < 0 || v > 255);
         }
+    int differs = 0;
     for (int r = 0; r < 4; ++r)
         for (int c = 0; c < 4; ++c) {
             int s = 64;
             for (int t = 0; t < 6; ++t) s += sixtap[fy][t] * line[r + t][c];
             out[4 * r + c] = sat8(s / 128);
+            if (wrapped) { /* test aid: what a conforming decoder predicts here (all lines saturate) */
+                int s2 = 64;
+                for (int t = 0; t < 6; ++t) {
+                    const int l = r + t;
+                    const int v = hraw(img, w, h, ox + c, oy - 2 + l, fx);
+                    s2 += sixtap[fy][t] * sat8(v);
+                }
+                differs |= sat8(s2 / 128) != out[4 * r + c];
+            }
         }
+    return differs; /* Q5 changed the predictor of this block */
+}
+
+/* ---- test aid: where did the reference's non-conforming arithmetic change a result? -------------------------
+ * Q5 (wrapping lines of `construct`) and Q7 (unclamped chaining in the loop filter) make the encoder's
+ * reconstruction differ from what a VP8 decoder computes from the same bitstream.  The log records the first
+ * events of each kind as (x, y, plane size tag) so that tests/test_decoder_pin.py can say exactly from which
+ * frame on a libvpx decode may legitimately differ.  Not part of any result. */
+#define VP8O_QUIRK_LOG_CAP 64
+static int quirk_count[2];
+static int quirk_pos[2][VP8O_QUIRK_LOG_CAP][3];
+static void quirk_event(int which, int x, int y, int tag) {
+#pragma omp critical(vp8o_quirk)
+    {
+        if (quirk_count[which] < VP8O_QUIRK_LOG_CAP) {
+            quirk_pos[which][quirk_count[which]][0] = x;
+            quirk_pos[which][quirk_count[which]][1] = y;
+            quirk_pos[which][quirk_count[which]][2] = tag;
+        }
+        ++quirk_count[which];
+    }
+}
+void vp8o_quirk_log_reset(void) { quirk_count[0] = quirk_count[1] = 0; }
+int vp8o_quirk_log_get(int which, int *xyt, int cap) {
+    const int n = quirk_count[which] < VP8O_QUIRK_LOG_CAP ? quirk_count[which] : VP8O_QUIRK_LOG_CAP;
+    for (int i = 0; i < n && i < cap; ++i)
+        for (int k = 0; k < 3; ++k) xyt[3 * i + k] = quirk_pos[which][i][k];
+    return quirk_count[which];
 }
 
 void vp8o_prepare_predictors_and_residual(const uint8_t *cur, const uint8_t *ref, uint8_t *predictor,
@@ -288,7 +327,7 @@ void vp8o_prepare_predictors_and_residual(const uint8_t *cur, const uint8_t *ref
         if (dx < 0) dx = 0;
         if (dy < 0) dy = 0;
         int pred[16];
-        predict4x4_construct(ref, width, height, tx / g, ty / g, dx, dy, pred);
+        if (predict4x4_construct(ref, width, height, tx / g, ty / g, dx, dy, pred)) quirk_event(0, x, y, plane);
         for (int r = 0; r < 4; ++r)
             for (int c = 0; c < 4; ++c) {
                 const int i = (y + r) * width + x + c;
@@ -618,6 +657,8 @@ void vp8o_loop_filter_frame(uint8_t *frame, const int32_t *MB_segment_ids, const
                     p2 = q1;
                     p1 = q2;
                     p0 = q3;
+                    if (p3 < -128 || p3 > 127 || p2 < -128 || p2 > 127 || p1 < -128 || p1 > 127) /* (p0 = q3 is never modified) */
+                        quirk_event(1, dir == 0 ? x0 + e : x0 + k, dir == 0 ? y0 + k : y0 + e, n);
                     q0 = s16(eb[0] - 128);
                     q1 = s16(eb[along] - 128);
                     q2 = s16(eb[2 * along] - 128);

@@ -121,6 +121,12 @@ void vp8o_loop_filter_planes(uint8_t *y, uint8_t *u, uint8_t *v, const int16_t *
                              const int32_t *MB_parts, const int32_t *MB_segment_id, const vp8o_segment_data *SD,
                              int32_t *MB_non_zero_coeffs, int width, int height);
 
+/* test aid (tests/test_decoder_pin.py): which = 0 -> blocks whose predictor Q5 changed (x, y, plane), which = 1 ->
+ * loop-filter edges that chained an unclamped value, Q7 (x, y, macroblock size).  Returns the number of events
+ * since the last reset; at most `cap` positions are copied. */
+void vp8o_quirk_log_reset(void);
+int vp8o_quirk_log_get(int which, int *xyt, int cap);
+
 #ifdef __cplusplus
 }
 #endif

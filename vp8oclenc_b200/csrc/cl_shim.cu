@@ -29,6 +29,7 @@
 #include <dirent.h>
 #include <signal.h>
 #include <sys/mman.h>
+#include <sys/prctl.h>
 #include <sys/resource.h>
 #include <unistd.h>
 #include <time.h>
@@ -119,30 +120,91 @@ static unsigned long long g_h2d_bytes = 0, g_d2h_bytes = 0, g_kernel_launches = 
 // wall-clock time the calling thread spent inside the entry points, by kind
 enum TimedKind { T_LAUNCH, T_HOST_KERNEL, T_READ, T_WRITE, T_MAP, T_FINISH, T_KINDS };
 static const char *const kTimedNames[T_KINDS] = {"launch", "host_kernel", "read", "write", "map", "finish"};
-static unsigned long long g_ns[T_KINDS] = {0}, g_ns_start = 0;
+static unsigned long long g_ns[T_KINDS] = {0}, g_cpu_ns[T_KINDS] = {0}, g_ns_start = 0;
+// host-cost accounting (VP8B200_STATS): page faults taken by the mirror tracking, mprotect calls, waits for the
+// stream (count, wall time, CPU time the waiting thread burned), CPU time of the calling thread inside the shim
+static unsigned long long g_faults = 0, g_mprotects = 0, g_waits = 0, g_waits_skipped = 0, g_wait_ns = 0, g_wait_cpu_ns = 0, g_frames = 0;
+static bool g_account_cpu = false;  // (CLOCK_THREAD_CPUTIME_ID is a real system call: only when statistics are asked for)
 static inline unsigned long long now_ns() {
     timespec ts;
     clock_gettime(CLOCK_MONOTONIC, &ts);
     return (unsigned long long)ts.tv_sec * 1000000000ull + (unsigned long long)ts.tv_nsec;
 }
+static inline unsigned long long thread_cpu_ns() {
+    if (!g_account_cpu) return 0;
+    timespec ts;
+    clock_gettime(CLOCK_THREAD_CPUTIME_ID, &ts);
+    return (unsigned long long)ts.tv_sec * 1000000000ull + (unsigned long long)ts.tv_nsec;
+}
+static inline int counted_mprotect(void *p, size_t n, int prot) {
+    ++g_mprotects;
+    return mprotect(p, n, prot);
+}
 struct ScopedTimer {
     TimedKind kind;
-    unsigned long long t0;
-    explicit ScopedTimer(TimedKind k) : kind(k), t0(now_ns()) {}
-    ~ScopedTimer() { g_ns[kind] += now_ns() - t0; }
+    unsigned long long t0, c0;
+    explicit ScopedTimer(TimedKind k) : kind(k), t0(now_ns()), c0(thread_cpu_ns()) {}
+    ~ScopedTimer() {
+        g_ns[kind] += now_ns() - t0;
+        g_cpu_ns[kind] += thread_cpu_ns() - c0;
+    }
 };
+// every counter as one vector of (name, value): written as JSON at exit, minus the snapshot taken at the start of
+// inter frame $VP8B200_STATS_FROM (so that start-up and the host-coded key frame can be left out of a steady-state
+// account; "window_frames" is the number of inter frames the difference covers)
+struct StatItem { const char *name; double value; };
+static int collect_stats(StatItem *out) {
+    static char names[2 * T_KINDS][32];
+    int n = 0;
+    out[n++] = {"h2d_bytes", (double)g_h2d_bytes};
+    out[n++] = {"d2h_bytes", (double)g_d2h_bytes};
+    out[n++] = {"elided_bytes", (double)g_elided_bytes};
+    out[n++] = {"kernel_launches", (double)g_kernel_launches};
+    out[n++] = {"host_kernels", (double)g_host_kernels};
+    for (int i = 0; i < T_KINDS; ++i) {
+        snprintf(names[i], sizeof(names[i]), "ms_%s", kTimedNames[i]);
+        out[n++] = {names[i], g_ns[i] * 1e-6};
+    }
+    for (int i = 0; i < T_KINDS; ++i) {
+        snprintf(names[T_KINDS + i], sizeof(names[i]), "cpu_ms_%s", kTimedNames[i]);
+        out[n++] = {names[T_KINDS + i], g_cpu_ns[i] * 1e-6};
+    }
+    out[n++] = {"window_frames", (double)g_frames};
+    out[n++] = {"faults", (double)g_faults};
+    out[n++] = {"mprotects", (double)g_mprotects};
+    out[n++] = {"waits", (double)g_waits};
+    out[n++] = {"waits_skipped", (double)g_waits_skipped};
+    out[n++] = {"ms_wait", g_wait_ns * 1e-6};
+    out[n++] = {"cpu_ms_wait", g_wait_cpu_ns * 1e-6};
+    out[n++] = {"cpu_ms_calling_thread", thread_cpu_ns() * 1e-6};
+    rusage ru;
+    getrusage(RUSAGE_SELF, &ru);  // all threads of the encoder instance
+    out[n++] = {"cpu_user_ms", ru.ru_utime.tv_sec * 1e3 + ru.ru_utime.tv_usec * 1e-3};
+    out[n++] = {"cpu_sys_ms", ru.ru_stime.tv_sec * 1e3 + ru.ru_stime.tv_usec * 1e-3};
+    out[n++] = {"vol_ctx_switches", (double)ru.ru_nvcsw};
+    out[n++] = {"invol_ctx_switches", (double)ru.ru_nivcsw};
+    out[n++] = {"ms_total", (now_ns() - g_ns_start) * 1e-6};
+    return n;
+}
+constexpr int kMaxStatItems = 48;
+static StatItem g_stats_base[kMaxStatItems];
+static int g_stats_base_n = 0;
+static long g_stats_from = 0;
+static int g_wait_hint;
+static void stats_frame_start() {  // called at the start of every inter frame (its reset_vectors enqueue)
+    g_wait_hint = 0;
+    if (g_account_cpu && g_stats_from > 0 && (long)g_frames == g_stats_from) g_stats_base_n = collect_stats(g_stats_base);
+    ++g_frames;
+}
 static void write_stats() {
     const char *p = getenv("VP8B200_STATS");
     if (!p || !*p) return;
+    StatItem now[kMaxStatItems];
+    const int n = collect_stats(now);
     if (FILE *f = fopen(p, "w")) {
-        fprintf(f, "{\"h2d_bytes\": %llu, \"d2h_bytes\": %llu, \"elided_bytes\": %llu, \"kernel_launches\": %llu, \"host_kernels\": %llu",
-                g_h2d_bytes, g_d2h_bytes, g_elided_bytes, g_kernel_launches, g_host_kernels);
-        for (int i = 0; i < T_KINDS; ++i) fprintf(f, ", \"ms_%s\": %.3f", kTimedNames[i], g_ns[i] * 1e-6);
-        rusage ru;
-        getrusage(RUSAGE_SELF, &ru);  // all threads of the encoder instance
-        fprintf(f, ", \"cpu_user_ms\": %.3f, \"cpu_sys_ms\": %.3f", ru.ru_utime.tv_sec * 1e3 + ru.ru_utime.tv_usec * 1e-3,
-                ru.ru_stime.tv_sec * 1e3 + ru.ru_stime.tv_usec * 1e-3);
-        fprintf(f, ", \"ms_total\": %.3f}\n", (now_ns() - g_ns_start) * 1e-6);
+        for (int i = 0; i < n; ++i)
+            fprintf(f, "%s\"%s\": %.3f", i ? ", " : "{", now[i].name, now[i].value - (i < g_stats_base_n ? g_stats_base[i].value : 0.0));
+        fprintf(f, ", \"inter_frames\": %llu}\n", g_frames);
         fclose(f);
     }
 }
@@ -154,7 +216,9 @@ static std::vector<cl_mem> g_mirrors;  // objects that own a pinned mirror
 static std::vector<Cmd> g_cmds;  // the deferred command list
 static bool g_fuse = true;       // VP8B200_FUSED=0: execute the list kernel by kernel
 
-static int g_sync_sleep_us = 0;  // VP8B200_SYNC=sleep<us>
+static bool g_pin_host = false;  // VP8B200_PIN_HOST=1 (see maybe_pin)
+static int g_sync_sleep_us = 0;  // VP8B200_SYNC=poll<us> (see "waiting")
+static int g_sync_spin_us = 15;
 static cudaEvent_t g_sync_event = nullptr;
 
 static void install_guard_handler();
@@ -175,12 +239,18 @@ static bool cuda_init() {
         if (!strcmp(sync, "block")) cudaSetDeviceFlags(cudaDeviceScheduleBlockingSync);
         else if (!strcmp(sync, "yield")) cudaSetDeviceFlags(cudaDeviceScheduleYield);
         else if (!strncmp(sync, "sleep", 5)) g_sync_sleep_us = sync[5] ? atoi(sync + 5) : 20;
+        else if (!strncmp(sync, "poll", 4)) g_sync_sleep_us = sync[4] ? atoi(sync + 4) : 40;
+    }
+    if (g_sync_sleep_us > 0) {
+        prctl(PR_SET_TIMERSLACK, 1000UL, 0UL, 0UL, 0UL);  // nanosleep(40 us) would otherwise sleep 40 + 50 us
+        if (const char *sp = getenv("VP8B200_SYNC_SPIN_US")) g_sync_spin_us = atoi(sp);
     }
     if (cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking) != cudaSuccess) return false;
     vp8b200_device_info(g_dev_name, sizeof(g_dev_name), &g_sm_count, nullptr, nullptr);
     if (const char *f = getenv("VP8B200_FUSED")) g_fuse = f[0] != '0';
     if (const char *f = getenv("VP8B200_GPU_TOKENS")) g_gpu_tokens = f[0] != '0';
     if (const char *f = getenv("VP8B200_GPU_BOOLCODER")) g_gpu_boolcoder = f[0] != '0';
+    if (const char *f = getenv("VP8B200_PIN_HOST")) g_pin_host = f[0] == '1';
     if (const char *f = getenv("VP8B200_ELIDE"))
         g_elide = !strcmp(f, "assume") ? 1 : (!strcmp(f, "track") ? 2 : (!strcmp(f, "lazy") ? 3 : 0));
     if (getenv("VP8CL_TRACE") && g_elide == 3) g_elide = 2;  // the trace records what every read delivered
@@ -188,6 +258,8 @@ static bool cuda_init() {
     const char *tr = getenv("VP8CL_TRACE");
     if (tr && *tr) g_trace = fopen(tr, "wb");
     atexit(write_stats);
+    if (const char *st = getenv("VP8B200_STATS")) g_account_cpu = *st != 0;
+    if (const char *st = getenv("VP8B200_STATS_FROM")) g_stats_from = atol(st);
     g_ns_start = now_ns();
     g_cuda_ok = true;
     return true;
@@ -240,32 +312,159 @@ static void start_gate(bool inter_frame_start) {
     }
 }
 
-// Waits for everything issued on the stream.  VP8B200_SYNC=sleep polls an event with short sleeps in
-// between instead of spinning: when more encoder instances than cores share the machine, the cores go
-// to the instances that have host work to do.
-// Asynchronous device-to-host copies the host may look at after its next map: an event behind the last of them
-// (clEnqueueMapBuffer waits for that, not for the kernels enqueued after it -- the loop filter of the frame before).
-static cudaEvent_t g_d2h_event = nullptr;
-static bool g_d2h_pending = false;
-static void note_async_d2h() {
-    if (!g_d2h_event) cudaEventCreateWithFlags(&g_d2h_event, cudaEventDisableTiming);
-    cudaEventRecord(g_d2h_event, g_stream);
-    g_d2h_pending = true;
-}
+// ---- waiting ---------------------------------------------------------------------------------------------------
+// The host program waits for the device a few times per frame (SURVEY 8b call stacks) and calls clFinish dozens
+// of times.  Three things keep that cheap when many encoder instances share the host cores:
+//  * g_stream_pending: nothing has been issued since the last complete wait -> a wait returns at once.
+//  * clFinish and clEnqueueMapBuffer only wait for transfers the HOST can observe (uploads out of its memory,
+//    downloads into it): g_xfer_event sits behind the last of them.  A kernel's completion is not observable except
+//    through such a transfer, and every one of those is ordered behind the kernel on the one stream.
+//  * how a wait waits: VP8B200_SYNC=spin|yield|block are the driver's policies (cudaDeviceSchedule*);
+//    VP8B200_SYNC=poll[<us>] is our own: spin on cudaEventQuery for a few microseconds, then sleep <us> (default 40)
+//    between queries.  Blocking waits of the driver wake up late under MPS (0.3 ms with 32 instances), yield burns
+//    the core the other instances need; polling costs about 3 us of CPU per query.
+// Downloads into pageable host memory (the host's malloc'ed arrays) go through a pinned bounce arena: a direct
+// cudaMemcpyAsync would wait inside the driver, spinning.  The bytes are handed over (memcpy) when the wait that
+// covers them completes, which is when OpenCL allows the host to look.
+static cudaEvent_t g_xfer_event = nullptr;
+static bool g_stream_pending = false;     // something was issued on the stream since the last complete wait
+static bool g_host_xfer_pending = false;  // ... and a host-visible transfer among it
+struct PendingOut { void *user; const char *src; size_t bytes; };
+static std::vector<PendingOut> g_pending_out;
+static char *g_bounce = nullptr;
+static size_t g_bounce_cap = 0, g_bounce_used = 0;
 
-static cudaError_t stream_sync() {
-    g_d2h_pending = false;
-    if (g_sync_sleep_us <= 0) return cudaStreamSynchronize(g_stream);
-    if (!g_sync_event) cudaEventCreateWithFlags(&g_sync_event, cudaEventDisableTiming);
-    cudaError_t e = cudaEventRecord(g_sync_event, g_stream);
-    if (e != cudaSuccess) return e;
-    for (int spins = 0;; ++spins) {
-        e = cudaEventQuery(g_sync_event);
-        if (e != cudaErrorNotReady) return e;
-        if (spins < 20) continue;  // short waits are cheaper spun
-        timespec ts = {0, g_sync_sleep_us * 1000L};
-        nanosleep(&ts, nullptr);
+static inline cudaError_t copy_async(void *dst, const void *src, size_t n, cudaMemcpyKind kind, cudaStream_t st) {
+    g_stream_pending = true;
+    return cudaMemcpyAsync(dst, src, n, kind, st);
+}
+static inline cudaError_t copy2d_async(void *dst, size_t dpitch, const void *src, size_t spitch, size_t w, size_t h,
+                                       cudaMemcpyKind kind, cudaStream_t st) {
+    g_stream_pending = true;
+    if (dpitch == w && spitch == w) return cudaMemcpyAsync(dst, src, w * h, kind, st);  // (contiguous: the cheaper call)
+    return cudaMemcpy2DAsync(dst, dpitch, src, spitch, w, h, kind, st);
+}
+static void note_host_xfer() {
+    if (!g_xfer_event) cudaEventCreateWithFlags(&g_xfer_event, cudaEventDisableTiming);
+    cudaEventRecord(g_xfer_event, g_stream);
+    g_host_xfer_pending = true;
+}
+static char *bounce_alloc(size_t n) {
+    if (!g_bounce) {
+        g_bounce_cap = 4u << 20;
+        if (cudaHostAlloc((void **)&g_bounce, g_bounce_cap, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            g_bounce = nullptr;
+            g_bounce_cap = 0;
+        }
     }
+    const size_t at = (g_bounce_used + 63) & ~(size_t)63;
+    if (!g_bounce || at + n > g_bounce_cap) return nullptr;
+    g_bounce_used = at + n;
+    return g_bounce + at;
+}
+static void deliver_pending_out() {  // (after a wait that covered every transfer issued so far)
+    for (const PendingOut &o : g_pending_out) memcpy(o.user, o.src, o.bytes);
+    g_pending_out.clear();
+    g_bounce_used = 0;
+}
+struct WaitTimer {
+    unsigned long long t0, c0;
+    WaitTimer() : t0(now_ns()), c0(thread_cpu_ns()) { ++g_waits; }
+    ~WaitTimer() {
+        g_wait_ns += now_ns() - t0;
+        g_wait_cpu_ns += thread_cpu_ns() - c0;
+    }
+};
+// VP8B200_SYNC=poll: the waits of a frame happen at the same few places every frame and take about as long as they
+// did the frame before, so every wait site (source line + how many waits the frame has had before it) remembers a running average of its
+// duration; a wait sleeps through most of that in one go and polls the rest in short sleeps.  About two system calls
+// per wait instead of one per 40 us.
+struct WaitSite { int key; float avg_us; };
+static WaitSite g_wait_sites[48];
+static int g_num_wait_sites = 0;
+static inline void sleep_us(long us) {
+    timespec ts = {0, us * 1000L};
+    nanosleep(&ts, nullptr);
+}
+static cudaError_t wait_for(cudaEvent_t ev, int line) {
+    if (g_sync_sleep_us <= 0) return cudaEventSynchronize(ev);
+    const int key = line * 1024 + (g_wait_hint++ & 1023);  // (g_wait_hint: waits since the frame began, see stats_frame_start)
+    cudaError_t e = cudaEventQuery(ev);
+    if (e != cudaErrorNotReady) return e;
+    WaitSite *site = nullptr;
+    for (int i = 0; i < g_num_wait_sites; ++i)
+        if (g_wait_sites[i].key == key) site = &g_wait_sites[i];
+    if (!site && g_num_wait_sites < 48) {
+        site = &g_wait_sites[g_num_wait_sites++];
+        site->key = key;
+        site->avg_us = 0.0f;
+    }
+    const unsigned long long t0 = now_ns();
+    const float expect = site ? site->avg_us : 0.0f;
+    if (expect > 3.0f * g_sync_spin_us) sleep_us((long)(expect * 0.8f));
+    const long step = expect * 0.125f > g_sync_sleep_us ? (long)(expect * 0.125f) : g_sync_sleep_us;
+    for (;;) {
+        e = cudaEventQuery(ev);
+        if (e != cudaErrorNotReady) break;
+        if (now_ns() - t0 < (unsigned long long)g_sync_spin_us * 1000ull) continue;  // short waits are cheaper spun
+        sleep_us(step);
+    }
+    if (site) {
+        const float took = (now_ns() - t0) * 1e-3f;
+        // (a long sleep may overshoot: lean towards the shorter observations so that the estimate can come down)
+        site->avg_us = took < site->avg_us ? 0.5f * (site->avg_us + took) * 0.9f : 0.75f * site->avg_us + 0.25f * took;
+    }
+    return e;
+}
+// waits for everything issued on the stream
+#define stream_sync() stream_sync_at(__LINE__)
+#define xfer_sync() xfer_sync_at(__LINE__)
+static cudaError_t stream_sync_at(int line) {
+    if (!g_stream_pending) {
+        ++g_waits_skipped;
+        return cudaSuccess;
+    }
+    cudaError_t e;
+    {
+        WaitTimer wt;
+        if (g_sync_sleep_us <= 0) {
+            e = cudaStreamSynchronize(g_stream);
+        } else {
+            if (!g_sync_event) cudaEventCreateWithFlags(&g_sync_event, cudaEventDisableTiming);
+            e = cudaEventRecord(g_sync_event, g_stream);
+            if (e == cudaSuccess) e = wait_for(g_sync_event, line);
+        }
+    }
+    g_stream_pending = false;
+    g_host_xfer_pending = false;
+    deliver_pending_out();
+    return e;
+}
+static cudaError_t xfer_sync_at(int line);
+// the shim is about to read host memory [ptr, ptr+n): a download that is still on its way into it must land first
+static void settle_user_range(const void *ptr, size_t n) {
+    for (const PendingOut &o : g_pending_out)
+        if ((const char *)ptr < (const char *)o.user + o.bytes && (const char *)o.user < (const char *)ptr + n) {
+            xfer_sync();
+            if (!g_pending_out.empty()) stream_sync();
+            return;
+        }
+}
+// waits for the transfers the host can observe (see above); kernels issued behind them keep running
+static cudaError_t xfer_sync_at(int line) {
+    if (!g_host_xfer_pending) {
+        ++g_waits_skipped;
+        return cudaSuccess;
+    }
+    cudaError_t e;
+    {
+        WaitTimer wt;
+        e = wait_for(g_xfer_event, line);
+    }
+    g_host_xfer_pending = false;
+    deliver_pending_out();
+    return e;
 }
 
 static void trace_rec(unsigned kind, unsigned idx, size_t off, size_t size, const void *payload) {
@@ -304,6 +503,7 @@ static struct sigaction g_prev_segv;
 static void materialise_in_handler(_cl_mem *m);
 static void guard_fault(int sig, siginfo_t *info, void *uctx) {
     char *addr = (char *)info->si_addr;
+    ++g_faults;
     const int n = __atomic_load_n(&g_num_guard_slots, __ATOMIC_ACQUIRE);
     for (int i = 0; i < n; ++i) {
         GuardSlot &g = g_guard_slots[i];
@@ -318,7 +518,7 @@ static void guard_fault(int sig, siginfo_t *info, void *uctx) {
             g.mem->host_dirty = true;
             g.mem->shadow_valid = false;
             g.mem->guarded = false;
-            mprotect(g.base, g.bytes, PROT_READ | PROT_WRITE);
+            counted_mprotect(g.base, g.bytes, PROT_READ | PROT_WRITE);
             return;  // the faulting store is retried
         }
     }
@@ -344,14 +544,14 @@ static void guard(_cl_mem *m) {
     m->host_dirty = false;
     if (g_elide < 2 || !m->host || m->guarded || m->lazy) return;  // (a parked mirror is inaccessible: tracked anyway)
     m->guarded = true;
-    mprotect(m->host, m->host_bytes, PROT_READ);
+    counted_mprotect(m->host, m->host_bytes, PROT_READ);
 }
 // tracking ends: nothing is known about the mirror's bytes any more (a parked mirror stays parked and tracked)
 static void unguard(_cl_mem *m) {
     if (!m->lazy) m->shadow_valid = false;
     if (!m->guarded) return;
     m->guarded = false;
-    mprotect(m->host, m->host_bytes, PROT_READ | PROT_WRITE);
+    counted_mprotect(m->host, m->host_bytes, PROT_READ | PROT_WRITE);
 }
 
 // ---- lazy downloads (transfer elision, mode "lazy") ------------------------------------------------
@@ -364,9 +564,10 @@ static void unguard(_cl_mem *m) {
 // tracking: a system call handed a pointer into a parked mirror (write(2) of a mapped buffer) gets EFAULT instead
 // of a fault; the reference host only ever touches these buffers with its own loads and stores.
 static void fill_from_shadow(_cl_mem *m) {
-    mprotect(m->host, m->host_bytes, PROT_READ | PROT_WRITE);
-    cudaMemcpyAsync(m->host, m->shadow, m->size, cudaMemcpyDeviceToHost, g_stream);
+    counted_mprotect(m->host, m->host_bytes, PROT_READ | PROT_WRITE);
+    copy_async(m->host, m->shadow, m->size, cudaMemcpyDeviceToHost, g_stream);
     g_d2h_bytes += m->size;
+    WaitTimer wt;
     cudaStreamSynchronize(g_stream);
     m->lazy = false;
 }
@@ -374,7 +575,7 @@ static void materialise_in_handler(_cl_mem *m) {
     fill_from_shadow(m);
     m->guarded = true;  // clean: equals the shadow until the host stores into it
     m->host_dirty = false;
-    mprotect(m->host, m->host_bytes, PROT_READ);
+    counted_mprotect(m->host, m->host_bytes, PROT_READ);
 }
 // the shim itself is about to access the mirror's bytes (or to change part of them)
 static void materialise(_cl_mem *m) {
@@ -390,14 +591,14 @@ static bool park_download(_cl_mem *m, const void *src) {
         m->shadow = nullptr;
         return false;
     }
-    cudaMemcpyAsync(m->shadow, src, m->size, cudaMemcpyDeviceToDevice, g_stream);
+    copy_async(m->shadow, src, m->size, cudaMemcpyDeviceToDevice, g_stream);
     g_elided_bytes += m->size;
     m->shadow_valid = true;
     m->host_dirty = false;
     m->guarded = false;
     if (!m->lazy) {  // (a mirror the host has not touched since the last download is still inaccessible)
         m->lazy = true;
-        mprotect(m->host, m->host_bytes, PROT_NONE);
+        counted_mprotect(m->host, m->host_bytes, PROT_NONE);
     }
     return true;
 }
@@ -406,7 +607,7 @@ static void drop_shadow(_cl_mem *m) { m->shadow_valid = false; }
 static void cancel_lazy(_cl_mem *m) {
     if (!m->lazy) return;
     m->lazy = false;
-    mprotect(m->host, m->host_bytes, PROT_READ | PROT_WRITE);
+    counted_mprotect(m->host, m->host_bytes, PROT_READ | PROT_WRITE);
 }
 
 // ---- buffer coherence ---------------------------------------------------------------------
@@ -455,6 +656,38 @@ static cl_mem mirror_of(const void *ptr, size_t size, size_t *off) {
     }
     return nullptr;
 }
+// ---- pinning of the host program's own source buffers (VP8B200_PIN_HOST=1) -----------------------------------
+// The host uploads the current frame from the same malloc'ed planes every frame (src/vp8enc.cpp:376-378).  From
+// pageable memory the driver stages such a copy through its own pinned buffer with the calling thread doing the
+// memcpy (3 MB per 1080p frame); once a (pointer, size) pair has been seen twice the range is page-locked in place
+// and the upload becomes a plain DMA.  Opt-in: the range stays registered until the process ends, which is only safe
+// for a host that keeps these buffers for its lifetime (the reference host does, src/init.h:1500-1560).  OpenCL
+// already forbids touching the source of a non-blocking write before the queue is finished, and every finish /
+// blocking read of this shim waits for the one stream all copies are issued on.
+struct PinnedRange { const char *base; size_t bytes; int seen; bool tried, pinned; };
+static std::vector<PinnedRange> g_pin_ranges;
+static bool is_pinned_range(const void *ptr, size_t size) {
+    for (const PinnedRange &r : g_pin_ranges)
+        if (r.pinned && (const char *)ptr >= r.base && (const char *)ptr + size <= r.base + r.bytes) return true;
+    return false;
+}
+static void maybe_pin(const void *ptr, size_t size) {
+    if (!g_pin_host || size < (64u << 10)) return;
+    for (PinnedRange &r : g_pin_ranges) {
+        if (r.base == (const char *)ptr && r.bytes == size) {
+            if (!r.tried && ++r.seen >= 2) {
+                const size_t page = (size_t)sysconf(_SC_PAGESIZE);
+                const size_t lo = (size_t)ptr / page * page, hi = ((size_t)ptr + size + page - 1) / page * page;
+                r.tried = true;  // (once, whatever the outcome)
+                if (cudaHostRegister((void *)lo, hi - lo, cudaHostRegisterDefault) == cudaSuccess) r.pinned = true;
+                else cudaGetLastError();
+            }
+            return;
+        }
+    }
+    if (g_pin_ranges.size() < 16) g_pin_ranges.push_back({(const char *)ptr, size, 1, false, false});
+}
+
 // device address that currently holds the same bytes as mirror range [off, off+size) of m, or null
 static const void *device_twin_of_mirror(cl_mem m, size_t off) {
     if (!g_elide || m->host_dirty) return nullptr;
@@ -472,11 +705,11 @@ static void *dev_ptr(cl_mem m, bool will_write) {
         if (src == m->dev) {
             g_elided_bytes += m->size;  // nothing to do: the device copy never stopped being right
         } else if (src) {
-            cudaMemcpyAsync(m->dev, src, m->size, cudaMemcpyDeviceToDevice, g_stream);
+            copy_async(m->dev, src, m->size, cudaMemcpyDeviceToDevice, g_stream);
             g_elided_bytes += m->size;
         } else {
             materialise(m);
-            cudaMemcpyAsync(m->dev, m->host, m->size, cudaMemcpyHostToDevice, g_stream);
+            copy_async(m->dev, m->host, m->size, cudaMemcpyHostToDevice, g_stream);
             g_h2d_bytes += m->size;
         }
         m->dev_valid = true;
@@ -502,7 +735,7 @@ static void *host_ptr(cl_mem m, bool will_write, bool discard = false, bool lazy
         } else if (!(lazy_ok && park_download(m, m->dev))) {
             cancel_lazy(m);
             drop_shadow(m);
-            cudaMemcpyAsync(m->host, m->dev, m->size, cudaMemcpyDeviceToHost, g_stream);
+            copy_async(m->host, m->dev, m->size, cudaMemcpyDeviceToHost, g_stream);
             g_d2h_bytes += m->size;
             stream_sync();
         }
@@ -616,7 +849,7 @@ static bool tokens_on_gpu(cl_kernel k) {
         arg_mem(k, 3)->host_valid = arg_mem(k, 4)->host_valid = arg_mem(k, 5)->host_valid = false;
         return false;
     }
-    cudaMemcpyAsync(g_tok.host_part_info, g_tok.dev_part_info, (2 * P + 1) * 4, cudaMemcpyDeviceToHost, g_stream);
+    copy_async(g_tok.host_part_info, g_tok.dev_part_info, (2 * P + 1) * 4, cudaMemcpyDeviceToHost, g_stream);
     g_tok.MB = MB; g_tok.nz = nz; g_tok.parts = parts; g_tok.ctx = ctx;
     g_tok.mbh = mbh; g_tok.mbw = mbw; g_tok.P = P;
     g_tok.stage = 1;
@@ -650,7 +883,7 @@ static void tokens_fetch() {
                                         (uint32_t *)scratch, (uint32_t *)((char *)scratch + tables),
                                         (uint8_t *)scratch + 2 * tables, g_tok.dev_tokens, (uint32_t)g_tok.capacity,
                                         g_tok.dev_mb_tokens, g_tok.dev_mb_offset, g_tok.dev_part_info, g_tok.dev_tail) == 0;
-            cudaMemcpyAsync(g_tok.host_part_info, g_tok.dev_part_info, (2 * g_tok.P + 1) * 4, cudaMemcpyDeviceToHost, g_stream);
+            copy_async(g_tok.host_part_info, g_tok.dev_part_info, (2 * g_tok.P + 1) * 4, cudaMemcpyDeviceToHost, g_stream);
             stream_sync();
             total = g_tok.host_part_info[2 * g_tok.P];
         }
@@ -662,7 +895,7 @@ static void tokens_fetch() {
         }
     }
     if (total && !g_gpu_boolcoder) {
-        cudaMemcpyAsync(g_tok.host_tokens, g_tok.dev_tokens, (size_t)total * 2, cudaMemcpyDeviceToHost, g_stream);
+        copy_async(g_tok.host_tokens, g_tok.dev_tokens, (size_t)total * 2, cudaMemcpyDeviceToHost, g_stream);
         g_d2h_bytes += (size_t)total * 2;
     }
     g_tok.stage = 2;
@@ -705,7 +938,7 @@ static bool tokens_encode(cl_kernel k) {
         }
         // (fall through to the host threads: the streams have to come over after all)
         if (total) {
-            cudaMemcpyAsync(g_tok.host_tokens, g_tok.dev_tokens, (size_t)total * 2, cudaMemcpyDeviceToHost, g_stream);
+            copy_async(g_tok.host_tokens, g_tok.dev_tokens, (size_t)total * 2, cudaMemcpyDeviceToHost, g_stream);
             g_d2h_bytes += (size_t)total * 2;
         }
     }
@@ -728,7 +961,7 @@ static void stage_partitions(const int32_t *sizes) {
     }
     for (int p = 0; p < g_tok.P; ++p) {
         const size_t at = (size_t)p * g_tok.out_step;
-        cudaMemcpyAsync((char *)parts->host + at, (char *)parts->dev + at, sizes[p], cudaMemcpyDeviceToHost, g_stream);
+        copy_async((char *)parts->host + at, (char *)parts->dev + at, sizes[p], cudaMemcpyDeviceToHost, g_stream);
         g_d2h_bytes += sizes[p];
     }
     stream_sync();
@@ -738,6 +971,7 @@ static void stage_partitions(const int32_t *sizes) {
 // executes one kernel now (GPU kernels: launches on the stream; entropy kernels: runs on host threads)
 static cl_int dispatch_now(cl_kernel k, size_t global) {
     void *s = g_stream;
+    g_stream_pending = true;
     int rc = 0;
     if (k->id >= K_COUNT_PROBS) ++g_host_kernels;
     else ++g_kernel_launches;
@@ -1033,6 +1267,7 @@ static size_t try_lf_planes(size_t i) {
 
 static void run_cmds() {
     // (commands executed here may not enqueue: the list is stable while it runs)
+    g_stream_pending = true;
     for (size_t i = 0; i < g_cmds.size();) {
         size_t used = 0;
         if (g_fuse) {
@@ -1046,11 +1281,11 @@ static void run_cmds() {
             if (c.id == C_COPY_BUFFER) {
                 const char *sp = (const char *)dev_ptr(c.src, false);
                 char *dp = (char *)dev_ptr(c.dst, true);
-                cudaMemcpyAsync(dp + c.a[1], sp + c.a[0], c.a[2], cudaMemcpyDeviceToDevice, g_stream);
+                copy_async(dp + c.a[1], sp + c.a[0], c.a[2], cudaMemcpyDeviceToDevice, g_stream);
             } else if (c.id == C_COPY_IMAGE) {
                 const char *sp = (const char *)dev_ptr(c.src, false) + c.a[1] * c.src->width + c.a[0];
                 char *dp = (char *)dev_ptr(c.dst, true) + c.a[3] * c.dst->width + c.a[2];
-                cudaMemcpy2DAsync(dp, c.dst->width, sp, c.src->width, c.a[4], c.a[5], cudaMemcpyDeviceToDevice, g_stream);
+                copy2d_async(dp, c.dst->width, sp, c.src->width, c.a[4], c.a[5], cudaMemcpyDeviceToDevice, g_stream);
             } else {
                 dispatch_now(&c.k, c.global);
             }
@@ -1165,6 +1400,7 @@ static cl_mem new_mem(size_t size, bool image, int w, int h, bool want_host, cl_
     // nets of never-searched blocks are read before they are first written (Q4, Q9)
     cudaError_t e = cudaMalloc(&m->dev, size ? size : 1);
     if (e == cudaSuccess) e = cudaMemsetAsync(m->dev, 0, size ? size : 1, g_stream);
+    g_stream_pending = true;
     m->dev_valid = true;
     m->host_valid = false;
     if (e == cudaSuccess && want_host) {
@@ -1179,7 +1415,7 @@ static cl_mem new_mem(size_t size, bool image, int w, int h, bool want_host, cl_
 cl_mem clCreateBuffer(cl_context, cl_mem_flags flags, size_t size, void *host_ptr_in, cl_int *err) {
     cl_mem m = new_mem(size, false, 0, 0, (flags & CL_MEM_ALLOC_HOST_PTR) != 0, err);
     if (host_ptr_in && (flags & (CL_MEM_COPY_HOST_PTR | CL_MEM_USE_HOST_PTR)))
-        cudaMemcpyAsync(m->dev, host_ptr_in, size, cudaMemcpyHostToDevice, g_stream);
+        copy_async(m->dev, host_ptr_in, size, cudaMemcpyHostToDevice, g_stream);
     return m;
 }
 
@@ -1201,7 +1437,7 @@ cl_int clReleaseMemObject(cl_mem m) {
     if (m->host) {
         for (int i = 0; i < g_num_guard_slots; ++i)
             if (g_guard_slots[i].mem == m) g_guard_slots[i].mem = nullptr;
-        if (m->guarded || m->lazy) mprotect(m->host, m->host_bytes, PROT_READ | PROT_WRITE);
+        if (m->guarded || m->lazy) counted_mprotect(m->host, m->host_bytes, PROT_READ | PROT_WRITE);
         cudaHostUnregister(m->host);
         munmap(m->host, m->host_bytes);
     }
@@ -1259,6 +1495,7 @@ cl_int clEnqueueNDRangeKernel(cl_command_queue, cl_kernel k, cl_uint dim, const 
     for (int i = 0; i < kKernels[k->id].nargs; ++i)
         if (!k->set[i]) return CL_INVALID_KERNEL_ARGS;
     start_gate(k->id == K_RESET_VECTORS);
+    if (k->id == K_RESET_VECTORS) stats_frame_start();
     ScopedTimer timer(k->id >= K_COUNT_PROBS ? T_HOST_KERNEL : T_LAUNCH);
     return dispatch(k, gsz[0]);
 }
@@ -1297,11 +1534,16 @@ cl_int clEnqueueReadBuffer(cl_command_queue, cl_mem m, cl_bool blocking, size_t 
     if (parked) {
         // nothing to wait for
     } else if (m->dev_valid && !m->host_staged) {
-        cudaError_t e = cudaMemcpyAsync(ptr, (char *)m->dev + off, size, cudaMemcpyDeviceToHost, g_stream);
+        // into pinned memory (a mirror, a page-locked range of the host's) directly; into pageable memory through
+        // the bounce arena, handed over when the covering wait completes
+        size_t poff = 0;
+        char *via = (mirror_of(ptr, size, &poff) || is_pinned_range(ptr, size)) ? nullptr : bounce_alloc(size);
+        cudaError_t e = copy_async(via ? (void *)via : ptr, (char *)m->dev + off, size, cudaMemcpyDeviceToHost, g_stream);
         g_d2h_bytes += size;
         if (e != cudaSuccess) return cuda_rc(e);
+        if (via) g_pending_out.push_back({ptr, via, size});
         if (blocking || g_trace) stream_sync();
-        else note_async_d2h();
+        else note_host_xfer();
         if (m == g_tok.out_sizes && blocking && off == 0 && size >= (size_t)g_tok.P * 4) stage_partitions((const int32_t *)ptr);
     } else {
         materialise(m);
@@ -1346,11 +1588,14 @@ cl_int clEnqueueWriteBuffer(cl_command_queue, cl_mem m, cl_bool blocking, size_t
     cl_mem srcm = g_elide ? mirror_of(ptr, size, &moff) : nullptr;
     const void *dsrc = srcm ? device_twin_of_mirror(srcm, moff) : nullptr;
     if (dsrc) {  // the bytes are on the device already
-        e = cudaMemcpyAsync((char *)m->dev + off, dsrc, size, cudaMemcpyDeviceToDevice, g_stream);
+        e = copy_async((char *)m->dev + off, dsrc, size, cudaMemcpyDeviceToDevice, g_stream);
         g_elided_bytes += size;
     } else {
-        e = cudaMemcpyAsync((char *)m->dev + off, ptr, size, cudaMemcpyHostToDevice, g_stream);
+        if (!srcm) maybe_pin(ptr, size);
+        settle_user_range(ptr, size);
+        e = copy_async((char *)m->dev + off, ptr, size, cudaMemcpyHostToDevice, g_stream);
         g_h2d_bytes += size;
+        note_host_xfer();
     }
     m->host_valid = false;
     m->host_staged = false;
@@ -1386,11 +1631,13 @@ cl_int clEnqueueWriteImage(cl_command_queue, cl_mem img, cl_bool blocking, const
     cl_mem srcm = g_elide ? mirror_of(ptr, pitch * (region[1] - 1) + region[0], &moff) : nullptr;
     const void *dsrc = srcm ? device_twin_of_mirror(srcm, moff) : nullptr;
     if (dsrc) {
-        e = cudaMemcpy2DAsync(dst, img->width, dsrc, pitch, region[0], region[1], cudaMemcpyDeviceToDevice, g_stream);
+        e = copy2d_async(dst, img->width, dsrc, pitch, region[0], region[1], cudaMemcpyDeviceToDevice, g_stream);
         g_elided_bytes += region[0] * region[1];
     } else {
-        e = cudaMemcpy2DAsync(dst, img->width, ptr, pitch, region[0], region[1], cudaMemcpyHostToDevice, g_stream);
+        settle_user_range(ptr, pitch * (region[1] - 1) + region[0]);
+        e = copy2d_async(dst, img->width, ptr, pitch, region[0], region[1], cudaMemcpyHostToDevice, g_stream);
         g_h2d_bytes += region[0] * region[1];
+        note_host_xfer();
     }
     if (pitch == region[0]) trace_rec(4, img->index, 0, region[0] * region[1], ptr);
     if (blocking) stream_sync();
@@ -1427,14 +1674,7 @@ void *clEnqueueMapBuffer(cl_command_queue, cl_mem m, cl_bool, cl_map_flags flags
         return nullptr;
     }
     // in-flight asynchronous reads into other mapped buffers must have landed before the host looks
-    if (g_d2h_pending) {
-        if (g_sync_sleep_us > 0) {
-            stream_sync();
-        } else {
-            cudaEventSynchronize(g_d2h_event);
-            g_d2h_pending = false;
-        }
-    }
+    xfer_sync();
     m->mapped_for_write = writes;
     if (writes) {
         // the host owns the contents until the unmap; until it writes, the device copy still equals
@@ -1469,9 +1709,10 @@ cl_int clEnqueueUnmapMemObject(cl_command_queue, cl_mem m, void *, cl_uint, cons
 cl_int clFlush(cl_command_queue) { return CL_SUCCESS; }
 cl_int clFinish(cl_command_queue) {
     ScopedTimer timer(T_FINISH);
-    // waits for the transfers already issued; deferred kernels stay deferred (see the header comment)
+    // waits for the host-visible transfers already issued; deferred kernels stay deferred (see the header comment)
+    // and kernels already launched need not have finished (see "waiting")
     if (g_trace) fflush(g_trace);
-    return cuda_rc(stream_sync());
+    return cuda_rc(g_trace ? stream_sync() : xfer_sync());
 }
 
 }  // extern "C"
