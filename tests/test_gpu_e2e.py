@@ -238,3 +238,30 @@ def test_host_control_flow_variants(name, args, cut, tmp_path):
     assert a == open(os.path.join(d, "b200.ivf"), "rb").read()
     if cut is not None:
         assert "1 scene changes detected by color change" in out_ref, out_ref[-400:]
+
+
+def test_loop_filter_on_gpu_option_is_refused_cleanly(tmp_path):
+    """-loop-filter-on-gpu (src/init.h:180-183, 285-293; src/loop_filter.h:57-138) cannot work against any runtime:
+    the reference's own GPU_kernels.cl has the three kernels commented out and its host hands them a buffer it never
+    creates (with oracle/_ref the host dies with SIGSEGV before the first frame).  The shim refuses the -DLOOP_FILTER
+    build; the unmodified host then writes the build log to clErrors.txt and ends (src/init.h:188-201) without
+    writing a frame.  Without the option the same clip encodes (every other test of this file)."""
+    import subprocess
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_y4m
+    d = str(tmp_path)
+    y4m = os.path.join(d, "clip.y4m")
+    gen_y4m.write_y4m(y4m, 176, 144, 4)
+    for name, txt in (("GPU_kernels.cl", _trace.GPU_STUB), ("CPU_kernels.cl", _trace.CPU_STUB)):
+        with open(os.path.join(d, name), "w") as f:
+            f.write(txt)
+    env = dict(os.environ, LD_LIBRARY_PATH=SHIM_DIR + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+    p = subprocess.run([_trace.HOST_BIN, "-i", y4m, "-o", os.path.join(d, "out.ivf"), "-qmin", "24", "-qmax", "24", "-g", "12",
+                        "-loop-filter-on-gpu"], cwd=d, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
+    assert p.returncode not in (777 % 256, -11, 139), (p.returncode, p.stdout[-300:])  # neither "encoded" nor a crash
+    assert b"kernel build fail" in p.stdout
+    assert b"-loop-filter-on-gpu" in p.stderr
+    log = open(os.path.join(d, "clErrors.txt")).read()
+    assert "normal_loop_filter_MBH" in log and "Run without -loop-filter-on-gpu" in log
+    assert not os.path.exists(os.path.join(d, "out.ivf")) or os.path.getsize(os.path.join(d, "out.ivf")) == 0

@@ -48,7 +48,7 @@ struct _cl_platform_id { int unused; };
 struct _cl_device_id { cl_device_type type; };
 struct _cl_context { cl_device_id dev; };
 struct _cl_command_queue { cl_context ctx; };
-struct _cl_program { bool gpu_program; };
+struct _cl_program { bool gpu_program; const char *build_log; };
 
 struct _cl_mem {
     unsigned index;
@@ -664,7 +664,7 @@ static cl_mem mirror_of(const void *ptr, size_t size, size_t *off) {
 // for a host that keeps these buffers for its lifetime (the reference host does, src/init.h:1500-1560).  OpenCL
 // already forbids touching the source of a non-blocking write before the queue is finished, and every finish /
 // blocking read of this shim waits for the one stream all copies are issued on.
-struct PinnedRange { const char *base; size_t bytes; int seen; bool tried, pinned; };
+struct PinnedRange { const char *base; size_t bytes; int seen; bool tried, pinned; const char *lo, *hi; };  // [lo, hi): the registered pages
 static std::vector<PinnedRange> g_pin_ranges;
 static bool is_pinned_range(const void *ptr, size_t size) {
     for (const PinnedRange &r : g_pin_ranges)
@@ -679,13 +679,44 @@ static void maybe_pin(const void *ptr, size_t size) {
                 const size_t page = (size_t)sysconf(_SC_PAGESIZE);
                 const size_t lo = (size_t)ptr / page * page, hi = ((size_t)ptr + size + page - 1) / page * page;
                 r.tried = true;  // (once, whatever the outcome)
-                if (cudaHostRegister((void *)lo, hi - lo, cudaHostRegisterDefault) == cudaSuccess) r.pinned = true;
-                else cudaGetLastError();
+                if (cudaHostRegister((void *)lo, hi - lo, cudaHostRegisterDefault) == cudaSuccess) {
+                    r.pinned = true;
+                    r.lo = (const char *)lo;
+                    r.hi = (const char *)hi;
+                } else {
+                    cudaGetLastError();
+                }
             }
             return;
         }
     }
-    if (g_pin_ranges.size() < 16) g_pin_ranges.push_back({(const char *)ptr, size, 1, false, false});
+    if (g_pin_ranges.size() < 16) g_pin_ranges.push_back({(const char *)ptr, size, 1, false, false, nullptr, nullptr});
+}
+
+// A driver copy must not straddle the edge of a page-locked range (the registration is page-rounded, so the bytes
+// next to a pinned plane -- the chroma planes that follow the luma plane in the host's input buffer -- share its
+// first or last page): the CUDA runtime mis-copies a host range that is only partly registered.  Transfers between
+// the host program's own memory and the device are therefore cut at those edges; each piece is either wholly inside
+// one registration (asynchronous DMA) or wholly pageable (staged by the driver).
+static cudaError_t user_copy(void *dst, const void *src, size_t n, cudaMemcpyKind kind) {
+    const bool host_is_src = kind == cudaMemcpyHostToDevice;
+    const char *h = (const char *)(host_is_src ? src : dst), *end = h + n;
+    char *d = (char *)(host_is_src ? dst : const_cast<void *>(src));
+    cudaError_t rc = cudaSuccess;
+    while (h < end) {
+        const char *cut = end;
+        for (const PinnedRange &r : g_pin_ranges) {
+            if (!r.pinned) continue;
+            if (h >= r.lo && h < r.hi) { cut = r.hi < end ? r.hi : end; break; }  // inside this registration
+            if (r.lo > h && r.lo < cut) cut = r.lo;                               // pageable up to the next one
+        }
+        const size_t piece = (size_t)(cut - h);
+        const cudaError_t e = host_is_src ? copy_async(d, h, piece, kind, g_stream) : copy_async(const_cast<char *>(h), d, piece, kind, g_stream);
+        if (e != cudaSuccess) rc = e;
+        h += piece;
+        d += piece;
+    }
+    return rc;
 }
 
 // device address that currently holds the same bytes as mirror range [off, off+size) of m, or null
@@ -1415,7 +1446,7 @@ static cl_mem new_mem(size_t size, bool image, int w, int h, bool want_host, cl_
 cl_mem clCreateBuffer(cl_context, cl_mem_flags flags, size_t size, void *host_ptr_in, cl_int *err) {
     cl_mem m = new_mem(size, false, 0, 0, (flags & CL_MEM_ALLOC_HOST_PTR) != 0, err);
     if (host_ptr_in && (flags & (CL_MEM_COPY_HOST_PTR | CL_MEM_USE_HOST_PTR)))
-        copy_async(m->dev, host_ptr_in, size, cudaMemcpyHostToDevice, g_stream);
+        user_copy(m->dev, host_ptr_in, size, cudaMemcpyHostToDevice);
     return m;
 }
 
@@ -1452,13 +1483,32 @@ cl_int clReleaseMemObject(cl_mem m) {
 cl_program clCreateProgramWithSource(cl_context ctx, cl_uint, const char **, const size_t *, cl_int *err) {
     if (err) *err = CL_SUCCESS;
     // which of the two programs this is follows from the device its context was made for
-    return new _cl_program{ctx->dev->type == CL_DEVICE_TYPE_GPU};
+    return new _cl_program{ctx->dev->type == CL_DEVICE_TYPE_GPU, ""};
 }
-cl_int clBuildProgram(cl_program, cl_uint, const cl_device_id *, const char *, void (*)(cl_program, void *), void *) {
+// -loop-filter-on-gpu (src/init.h:180-183 builds the GPU program with -DLOOP_FILTER, :285-293 asks it for
+// prepare_filter_mask / normal_loop_filter_MBH / normal_loop_filter_MBV, src/loop_filter.h:57-138 drives them stage
+// by stage): the reference's own src/GPU_kernels.cl has these kernels commented out (:2107-2694) and its host hands
+// them a buffer it never creates (transformed_blocks_gpu, src/init.h:1123 "loop filter on gpu is broken now"), so
+// the option cannot work against any runtime.  The build is refused with a log that says so -- the host writes the
+// log to clErrors.txt and ends (src/init.h:188-201) -- instead of letting it encode garbage.  In the default mode
+// the loop filter runs on the GPU anyway (loop_filter_frame_luma/chroma of the "CPU program" are CUDA kernels).
+static const char kLoopFilterOnGpuLog[] =
+    "vp8oclenc_b200: the program was built with -DLOOP_FILTER (option -loop-filter-on-gpu).\n"
+    "That mode needs the kernels prepare_filter_mask (GPU program), normal_loop_filter_MBH and normal_loop_filter_MBV,\n"
+    "which the reference's own GPU_kernels.cl does not define (commented out) and which its host drives with a buffer\n"
+    "it never creates.  Run without -loop-filter-on-gpu: in the default mode this library already runs the normal\n"
+    "loop filter on the GPU (loop_filter_frame_luma / loop_filter_frame_chroma).\n";
+cl_int clBuildProgram(cl_program prog, cl_uint, const cl_device_id *, const char *options, void (*)(cl_program, void *), void *) {
+    if (prog && prog->gpu_program && options && strstr(options, "-DLOOP_FILTER")) {
+        prog->build_log = kLoopFilterOnGpuLog;
+        fputs(kLoopFilterOnGpuLog, stderr);
+        return CL_BUILD_PROGRAM_FAILURE;
+    }
     return CL_SUCCESS;
 }
-cl_int clGetProgramBuildInfo(cl_program, cl_device_id, cl_program_build_info, size_t cap, void *dst, size_t *ret) {
-    return put_info("", 1, cap, dst, ret);
+cl_int clGetProgramBuildInfo(cl_program prog, cl_device_id, cl_program_build_info, size_t cap, void *dst, size_t *ret) {
+    const char *log = prog && prog->build_log ? prog->build_log : "";
+    return put_info(log, strlen(log) + 1, cap, dst, ret);
 }
 cl_int clReleaseProgram(cl_program p) { delete p; return CL_SUCCESS; }
 
@@ -1471,8 +1521,9 @@ cl_kernel clCreateKernel(cl_program prog, const char *name, cl_int *err) {
             if (err) *err = CL_SUCCESS;
             return k;
         }
-    // normal_loop_filter_MBH/MBV and the GPU-program prepare_filter_mask (-loop-filter-on-gpu) are dead
-    // code in the reference's src/GPU_kernels.cl as well: not provided
+    // (normal_loop_filter_MBH/MBV and the GPU-program prepare_filter_mask are never asked for: a -DLOOP_FILTER
+    // build is refused, see clBuildProgram)
+    fprintf(stderr, "vp8oclenc_b200: clCreateKernel: no kernel \"%s\" in the %s program\n", name, prog->gpu_program ? "GPU" : "CPU");
     if (err) *err = CL_INVALID_KERNEL_NAME;
     return nullptr;
 }
@@ -1538,7 +1589,9 @@ cl_int clEnqueueReadBuffer(cl_command_queue, cl_mem m, cl_bool blocking, size_t 
         // the bounce arena, handed over when the covering wait completes
         size_t poff = 0;
         char *via = (mirror_of(ptr, size, &poff) || is_pinned_range(ptr, size)) ? nullptr : bounce_alloc(size);
-        cudaError_t e = copy_async(via ? (void *)via : ptr, (char *)m->dev + off, size, cudaMemcpyDeviceToHost, g_stream);
+        cudaError_t e = via ? copy_async(via, (char *)m->dev + off, size, cudaMemcpyDeviceToHost, g_stream)
+                            : (mirror_of(ptr, size, &poff) ? copy_async(ptr, (char *)m->dev + off, size, cudaMemcpyDeviceToHost, g_stream)
+                                                           : user_copy(ptr, (char *)m->dev + off, size, cudaMemcpyDeviceToHost));
         g_d2h_bytes += size;
         if (e != cudaSuccess) return cuda_rc(e);
         if (via) g_pending_out.push_back({ptr, via, size});
@@ -1593,7 +1646,8 @@ cl_int clEnqueueWriteBuffer(cl_command_queue, cl_mem m, cl_bool blocking, size_t
     } else {
         if (!srcm) maybe_pin(ptr, size);
         settle_user_range(ptr, size);
-        e = copy_async((char *)m->dev + off, ptr, size, cudaMemcpyHostToDevice, g_stream);
+        e = srcm ? copy_async((char *)m->dev + off, ptr, size, cudaMemcpyHostToDevice, g_stream)
+                 : user_copy((char *)m->dev + off, ptr, size, cudaMemcpyHostToDevice);
         g_h2d_bytes += size;
         note_host_xfer();
     }
@@ -1635,7 +1689,13 @@ cl_int clEnqueueWriteImage(cl_command_queue, cl_mem img, cl_bool blocking, const
         g_elided_bytes += region[0] * region[1];
     } else {
         settle_user_range(ptr, pitch * (region[1] - 1) + region[0]);
-        e = copy2d_async(dst, img->width, ptr, pitch, region[0], region[1], cudaMemcpyHostToDevice, g_stream);
+        if (!srcm && pitch == region[0] && (size_t)img->width == region[0])  // contiguous, the host's own memory
+            e = user_copy(dst, ptr, region[0] * region[1], cudaMemcpyHostToDevice);
+        else if (!srcm && !g_pin_ranges.empty())  // (row by row, so that no row's copy straddles a registration edge)
+            for (size_t row = 0; row < region[1] && (row == 0 || e == cudaSuccess); ++row)
+                e = user_copy(dst + row * img->width, (const char *)ptr + row * pitch, region[0], cudaMemcpyHostToDevice);
+        else
+            e = copy2d_async(dst, img->width, ptr, pitch, region[0], region[1], cudaMemcpyHostToDevice, g_stream);
         g_h2d_bytes += region[0] * region[1];
         note_host_xfer();
     }
