@@ -160,6 +160,9 @@ int vp8b200_loop_filter_frame(void *stream, uint8_t *frame, const int32_t *MB_se
 /* the three planes of one frame in a single launch (Y, U, V run concurrently) */
 int vp8b200_loop_filter_planes(void *stream, uint8_t *y, uint8_t *u, uint8_t *v, const int32_t *MB_segment_ids,
                                const int32_t *mb_mask, const vp8b200_segment_data *SD, int width, int height);
+/* The loop filter keeps a ticket counter and a mailbox per stream; whoever owns a stream releases them before
+ * destroying it (vp8b200_engine_destroy does so for its own). */
+void vp8b200_loop_filter_release(void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * Frame-level engine: one object owns every per-frame device buffer the reference creates in

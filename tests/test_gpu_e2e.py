@@ -89,10 +89,12 @@ def test_without_trace_same_bitstream(tmp_path):
                                  {"VP8B200_FUSED": "0"}, {"VP8B200_SYNC": "sleep20"}, {"VP8B200_ENTROPY_THREADS": "3", "VP8B200_GPU_BOOLCODER": "0"},
                                  {"VP8B200_GPU_BOOLCODER": "0"}, {"VP8B200_SYNC": "poll40", "VP8B200_PIN_HOST": "1"},
                                  {"VP8B200_SYNC": "poll5", "VP8B200_SYNC_SPIN_US": "0", "VP8B200_PIN_HOST": "1", "VP8B200_ELIDE": "track"},
-                                 {"VP8B200_SYNC": "yield", "VP8B200_PIN_HOST": "1"}],
+                                 {"VP8B200_SYNC": "yield", "VP8B200_PIN_HOST": "1"}, {"VP8B200_HOST_PROFILE": "reference"},
+                                 {"VP8B200_ELIDE": "lazy"}],
                          ids=["token-scratch-grows", "host-entropy", "no-elision", "eager-downloads", "elision-assumed",
                               "lazy-host-entropy", "kernel-per-kernel", "sleep-sync", "three-entropy-threads", "host-bool-coder",
-                              "poll-sync-pinned-host", "poll-sync-no-spin-eager", "yield-pinned-host"])
+                              "poll-sync-pinned-host", "poll-sync-no-spin-eager", "yield-pinned-host", "reference-host-profile",
+                              "lazy-downloads"])
 def test_shim_modes_same_bitstream(env, tmp_path):
     """every switch of the shim changes HOW the bytes are produced, never the bytes: decision streams that
     outgrow their scratch, the host-only entropy path, no transfer elision, no fused launches, polling sync.

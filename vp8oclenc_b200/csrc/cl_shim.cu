@@ -73,6 +73,7 @@ struct _cl_mem {
     bool shadow_valid;           // the shadow holds exactly what the (clean) mirror holds / would hold
     volatile bool lazy;          // the mirror has not been filled: PROT_NONE, fetch from the shadow on access
     bool host_staged;            // the ranges the host is about to read are in the mirror already (stage_partitions)
+    int guard_slot;              // index into g_guard_slots, -1: none free -- this mirror is never protected (eager transfers)
 };
 
 enum KernelId {
@@ -117,6 +118,14 @@ static unsigned g_next_index = 0;
 static FILE *g_trace = nullptr;
 // statistics, written as JSON to $VP8B200_STATS at exit (bench.py reads them)
 static unsigned long long g_h2d_bytes = 0, g_d2h_bytes = 0, g_kernel_launches = 0, g_host_kernels = 0, g_elided_bytes = 0;
+// entropy-stage work that ran on host threads although the GPU path was asked for (allocation failure, a call
+// sequence the GPU path does not recognise): every event is reported on stderr and counted; bench.py demands zero.
+// (num_div_denom -- 1056 divisions -- always runs on the host and is counted in host_kernels only.)
+static unsigned long long g_entropy_fallbacks = 0;
+static void entropy_fallback(const char *what, const char *why) {
+    if (++g_entropy_fallbacks <= 8)
+        fprintf(stderr, "vp8oclenc_b200: %s runs on HOST threads for this frame: %s\n", what, why);
+}
 // wall-clock time the calling thread spent inside the entry points, by kind
 enum TimedKind { T_LAUNCH, T_HOST_KERNEL, T_READ, T_WRITE, T_MAP, T_FINISH, T_KINDS };
 static const char *const kTimedNames[T_KINDS] = {"launch", "host_kernel", "read", "write", "map", "finish"};
@@ -161,6 +170,7 @@ static int collect_stats(StatItem *out) {
     out[n++] = {"elided_bytes", (double)g_elided_bytes};
     out[n++] = {"kernel_launches", (double)g_kernel_launches};
     out[n++] = {"host_kernels", (double)g_host_kernels};
+    out[n++] = {"entropy_host_fallbacks", (double)g_entropy_fallbacks};
     for (int i = 0; i < T_KINDS; ++i) {
         snprintf(names[i], sizeof(names[i]), "ms_%s", kTimedNames[i]);
         out[n++] = {names[i], g_ns[i] * 1e-6};
@@ -186,7 +196,7 @@ static int collect_stats(StatItem *out) {
     out[n++] = {"ms_total", (now_ns() - g_ns_start) * 1e-6};
     return n;
 }
-constexpr int kMaxStatItems = 48;
+constexpr int kMaxStatItems = 56;
 static StatItem g_stats_base[kMaxStatItems];
 static int g_stats_base_n = 0;
 static long g_stats_from = 0;
@@ -211,7 +221,7 @@ static void write_stats() {
 
 static bool g_gpu_tokens = true;       // coefficient decisions prepared on the GPU (see tokens_on_gpu)
 static bool g_gpu_boolcoder = true;    // ... and bool-coded there as well (VP8B200_GPU_BOOLCODER=0: host threads; see tokens_encode)
-static int g_elide = 3;                // transfer elision: 0 off, 1 assume, 2 track, 3 track + lazy downloads (see "transfer elision" below)
+static int g_elide = 2;                // transfer elision: 0 off, 1 assume, 2 track (default), 3 track + lazy downloads (see "transfer elision" below)
 static std::vector<cl_mem> g_mirrors;  // objects that own a pinned mirror
 static std::vector<Cmd> g_cmds;  // the deferred command list
 static bool g_fuse = true;       // VP8B200_FUSED=0: execute the list kernel by kernel
@@ -233,9 +243,21 @@ static bool cuda_init() {
     }
     const char *dev_env = getenv("VP8B200_DEVICE");
     if (dev_env) cudaSetDevice(atoi(dev_env));
-    // how a waiting host thread waits: spin (default, lowest latency), yield, or block (frees the core for
-    // the other encoder instances when more instances than cores share the machine)
+    // VP8B200_HOST_PROFILE=reference: the caller vouches that the host program is the reference's (it keeps its
+    // frame buffers for its lifetime, touches mapped buffers only with its own loads and stores, never hands them to
+    // a system call): lazy downloads, page-locking of its source planes and polling waits are switched on together.
+    // Without it the defaults are the modes that are safe for any host (track, no pinning, the driver's spin wait);
+    // the individual variables below override either way.
+    if (const char *prof = getenv("VP8B200_HOST_PROFILE")) {
+        if (!strcmp(prof, "reference")) {
+            g_elide = 3;
+            g_pin_host = true;
+            g_sync_sleep_us = 40;
+        }
+    }
+    // how a waiting host thread waits: spin (default, lowest latency), yield, block, or poll (see "waiting")
     if (const char *sync = getenv("VP8B200_SYNC")) {
+        g_sync_sleep_us = 0;
         if (!strcmp(sync, "block")) cudaSetDeviceFlags(cudaDeviceScheduleBlockingSync);
         else if (!strcmp(sync, "yield")) cudaSetDeviceFlags(cudaDeviceScheduleYield);
         else if (!strncmp(sync, "sleep", 5)) g_sync_sleep_us = sync[5] ? atoi(sync + 5) : 20;
@@ -495,7 +517,7 @@ static inline cl_int cuda_rc(cudaError_t e) { return e == cudaSuccess ? CL_SUCCE
 // would fail with EFAULT instead of faulting; the reference host never does that (it stores into
 // these buffers from its intra path only, src/intra_part.h:517-741).
 struct GuardSlot { char *base; size_t bytes; _cl_mem *mem; };
-constexpr int kMaxGuardSlots = 64;
+constexpr int kMaxGuardSlots = 256;
 static GuardSlot g_guard_slots[kMaxGuardSlots];
 static int g_num_guard_slots = 0;
 static struct sigaction g_prev_segv;
@@ -542,6 +564,10 @@ static void install_guard_handler() {
 // the mirror's bytes equal a device copy from now on: watch for host stores
 static void guard(_cl_mem *m) {
     m->host_dirty = false;
+    if (g_elide >= 2 && m->host && m->guard_slot < 0) {
+        m->host_dirty = true;  // cannot be watched: assume the host stores into it (its uploads are real uploads)
+        return;
+    }
     if (g_elide < 2 || !m->host || m->guarded || m->lazy) return;  // (a parked mirror is inaccessible: tracked anyway)
     m->guarded = true;
     counted_mprotect(m->host, m->host_bytes, PROT_READ);
@@ -586,7 +612,7 @@ static void materialise(_cl_mem *m) {
 }
 // parks `size` bytes of device memory `src` as the contents of m's mirror; false: no shadow, download as usual
 static bool park_download(_cl_mem *m, const void *src) {
-    if (g_elide != 3 || !m->host) return false;
+    if (g_elide != 3 || !m->host || m->guard_slot < 0) return false;
     if (!m->shadow && cudaMalloc(&m->shadow, m->size ? m->size : 1) != cudaSuccess) {
         m->shadow = nullptr;
         return false;
@@ -625,11 +651,18 @@ static bool ensure_host_alloc(cl_mem m) {
     m->host = p;
     m->host_valid = false;
     g_mirrors.push_back(m);
-    if (g_num_guard_slots < kMaxGuardSlots) {
-        g_guard_slots[g_num_guard_slots].base = (char *)p;
-        g_guard_slots[g_num_guard_slots].bytes = m->host_bytes;
-        g_guard_slots[g_num_guard_slots].mem = m;
-        __atomic_store_n(&g_num_guard_slots, g_num_guard_slots + 1, __ATOMIC_RELEASE);
+    // a slot of the fault handler's table: a free one (released objects give theirs back), else a new one; with all
+    // kMaxGuardSlots taken the mirror is simply never protected (guard / park_download leave it alone)
+    int slot = -1;
+    for (int i = 0; i < g_num_guard_slots && slot < 0; ++i)
+        if (!g_guard_slots[i].mem) slot = i;
+    if (slot < 0 && g_num_guard_slots < kMaxGuardSlots) slot = g_num_guard_slots;
+    m->guard_slot = slot;
+    if (slot >= 0) {
+        g_guard_slots[slot].base = (char *)p;
+        g_guard_slots[slot].bytes = m->host_bytes;
+        __atomic_store_n(&g_guard_slots[slot].mem, m, __ATOMIC_RELEASE);
+        if (slot == g_num_guard_slots) __atomic_store_n(&g_num_guard_slots, g_num_guard_slots + 1, __ATOMIC_RELEASE);
     }
     return true;
 }
@@ -844,12 +877,17 @@ static bool tokens_on_gpu(cl_kernel k) {
     if (!g_gpu_tokens) return false;
     const int mbh = arg_int(k, 6), mbw = arg_int(k, 7), P = arg_int(k, 8);
     const size_t M = (size_t)mbh * mbw;
-    if (P < 1 || P > 8 || M == 0) return false;
+    if (P < 1 || P > 8 || M == 0) {
+        entropy_fallback("count_probs", "partition count or frame size outside what the GPU kernels take");
+        return false;
+    }
     cl_mem MB = arg_mem(k, 0), nz = arg_mem(k, 1), parts = arg_mem(k, 2), probs = arg_mem(k, 3), den = arg_mem(k, 4),
            ctx = arg_mem(k, 5);
     if (!MB || !nz || !parts || !probs || !den || !ctx || MB->size < M * 800 || nz->size < M * 4 || parts->size < M * 4 ||
-        probs->size < (size_t)P * 1056 * 4 || den->size < (size_t)P * 1056 * 4 || ctx->size < M * 25)
+        probs->size < (size_t)P * 1056 * 4 || den->size < (size_t)P * 1056 * 4 || ctx->size < M * 25) {
+        entropy_fallback("count_probs", "buffer sizes do not fit the frame geometry");
         return false;
+    }
     if (M > g_tok.mbs) {  // scratch for this frame size
         stream_sync();
         cudaFree(g_tok.dev_mb_tokens); cudaFree(g_tok.dev_mb_offset);
@@ -863,8 +901,9 @@ static bool tokens_on_gpu(cl_kernel k) {
                  cudaMalloc((void **)&g_tok.dev_tail, 8 * 68 * 4) == cudaSuccess &&
                  cudaHostAlloc((void **)&g_tok.host_part_info, 32 * 4, cudaHostAllocDefault) == cudaSuccess;
         if (!ok) {
-            g_gpu_tokens = false;
-            g_tok.mbs = 0;
+            cudaGetLastError();
+            g_tok.mbs = 0;  // (tried again for the next frame)
+            entropy_fallback("count_probs", "device memory for the decision streams could not be allocated");
             return false;
         }
         g_tok.mbs = M;
@@ -877,6 +916,7 @@ static bool tokens_on_gpu(cl_kernel k) {
     if (rc != 0) {  // nothing usable was produced: redo on the host
         stream_sync();
         cudaGetLastError();
+        entropy_fallback("count_probs", "the token kernels failed to launch");
         arg_mem(k, 3)->host_valid = arg_mem(k, 4)->host_valid = arg_mem(k, 5)->host_valid = false;
         return false;
     }
@@ -922,6 +962,7 @@ static void tokens_fetch() {
         if (!ok || total > g_tok.capacity) {
             g_tok.stage = 0;  // out of memory: encode_coefficients runs on the host from the coefficients
             if (!ok) g_tok.mbs = 0;
+            entropy_fallback("encode_coefficients", "the decision streams of this frame outgrew the device memory available");
             return;
         }
     }
@@ -935,8 +976,12 @@ static bool tokens_encode(cl_kernel k) {
     const bool usable = g_tok.stage == 2 && arg_mem(k, 0) == g_tok.MB && arg_mem(k, 1) == g_tok.nz &&
                         arg_mem(k, 2) == g_tok.parts && arg_mem(k, 5) == g_tok.ctx && arg_int(k, 7) == g_tok.mbh &&
                         arg_int(k, 8) == g_tok.mbw && arg_int(k, 9) == g_tok.P;
+    const bool was_prepared = g_tok.stage != 0;
     g_tok.stage = 0;
-    if (!usable) return false;
+    if (!usable) {
+        if (g_gpu_tokens && was_prepared) entropy_fallback("encode_coefficients", "its arguments differ from the count_probs call before it");
+        return false;
+    }
     if (g_gpu_boolcoder) {
         // The bool coder runs on the stream as well (parallel formulation, entropy_kernels.cu): the streams never
         // leave the device, the host thread goes on to code the frame header and meets the partitions in
@@ -951,21 +996,27 @@ static bool tokens_encode(cl_kernel k) {
             g_tok.bool_scratch_bytes = 0;
             if (cudaMalloc(&g_tok.bool_scratch, need + need / 4) != cudaSuccess) {
                 cudaGetLastError();
-                g_gpu_boolcoder = false;  // out of memory: the host threads code this and all later frames
+                g_tok.bool_scratch = nullptr;
+                entropy_fallback("the bool coder", "device memory for its working set could not be allocated");
             } else {
                 g_tok.bool_scratch_bytes = need + need / 4;
             }
         }
-        if (g_gpu_boolcoder) {
+        if (g_tok.bool_scratch_bytes >= need) {
             cl_mem parts_out = arg_mem(k, 3), sizes = arg_mem(k, 4);
             parts_out->dev_valid = sizes->dev_valid = true;  // (both are only ever read as far as the kernels write them)
             g_kernel_launches += 4;
             g_tok.out_parts = parts_out;
             g_tok.out_sizes = sizes;
             g_tok.out_step = step;
-            return vp8b200_entropy_boolcode(g_stream, g_tok.dev_tokens, g_tok.dev_part_info, in<uint32_t>(k, 6),
-                                            out<uint8_t>(k, 3), out<int32_t>(k, 4), g_tok.P, step, total,
-                                            g_tok.bool_scratch) == 0;
+            const bool launched = vp8b200_entropy_boolcode(g_stream, g_tok.dev_tokens, g_tok.dev_part_info, in<uint32_t>(k, 6),
+                                                           out<uint8_t>(k, 3), out<int32_t>(k, 4), g_tok.P, step, total,
+                                                           g_tok.bool_scratch) == 0;
+            if (!launched) {
+                cudaGetLastError();
+                entropy_fallback("encode_coefficients", "the bool-coder kernels failed to launch");
+            }
+            return launched;
         }
         // (fall through to the host threads: the streams have to come over after all)
         if (total) {
@@ -974,6 +1025,7 @@ static bool tokens_encode(cl_kernel k) {
         }
     }
     stream_sync();
+    ++g_host_kernels;
     vp8host::encode_token_streams(g_tok.host_tokens, g_tok.host_part_info, hin<uint32_t>(k, 6), hout<uint8_t>(k, 3),
                                   hout<int32_t>(k, 4), g_tok.P, arg_int(k, 10));
     return true;
@@ -999,13 +1051,15 @@ static void stage_partitions(const int32_t *sizes) {
     parts->host_staged = true;
 }
 
+static cl_mem g_packed_ssim = nullptr;  // MB_SSIM buffer pack_8x8_into_16x16 last reset to -2 ...
+static unsigned long g_packed_ssim_version = 0;  // ... at this version of its device copy, for this many macroblocks
+static size_t g_packed_count = 0;
 // executes one kernel now (GPU kernels: launches on the stream; entropy kernels: runs on host threads)
 static cl_int dispatch_now(cl_kernel k, size_t global) {
     void *s = g_stream;
     g_stream_pending = true;
     int rc = 0;
-    if (k->id >= K_COUNT_PROBS) ++g_host_kernels;
-    else ++g_kernel_launches;
+    if (k->id < K_COUNT_PROBS) ++g_kernel_launches;
     switch (k->id) {
         case K_RESET_VECTORS:
             rc = vp8b200_reset_vectors(s, out<int16_t>(k, 0), out<int16_t>(k, 1), out<int16_t>(k, 2), out<int16_t>(k, 3),
@@ -1041,6 +1095,10 @@ static cl_int dispatch_now(cl_kernel k, size_t global) {
         }
         case K_PACK:
             rc = vp8b200_pack_8x8_into_16x16(s, in<int16_t>(k, 0), out<int32_t>(k, 1), out<float>(k, 2), (int)global);
+            // (the fused tail starts its SSIM ladder from the -2 this kernel writes, see try_fused_tail)
+            g_packed_ssim = arg_mem(k, 2);
+            g_packed_ssim_version = g_packed_ssim ? g_packed_ssim->dev_version : 0;
+            g_packed_count = global;
             break;
         case K_DCT: {
             const int width = arg_int(k, 5);
@@ -1086,17 +1144,20 @@ static cl_int dispatch_now(cl_kernel k, size_t global) {
             break;
         case K_COUNT_PROBS:
             if (tokens_on_gpu(k)) break;
+            ++g_host_kernels;
             vp8host::count_probs(hin<int16_t>(k, 0), hin<int32_t>(k, 1), hin<int32_t>(k, 2), hout<uint32_t>(k, 3),
                                  hout<uint32_t>(k, 4), hout<uint8_t>(k, 5), arg_int(k, 6), arg_int(k, 7), arg_int(k, 8));
             break;
         case K_NUM_DIV_DENOM: {
             uint32_t *probs = hout<uint32_t>(k, 0);  // (downloads the statistics and waits when the GPU made them)
+            ++g_host_kernels;
             vp8host::num_div_denom(probs, hin<uint32_t>(k, 1), arg_int(k, 2));
             tokens_fetch();
             break;
         }
         case K_ENCODE_COEFFS:
             if (tokens_encode(k)) break;
+            ++g_host_kernels;
             vp8host::encode_coefficients(hin<int16_t>(k, 0), hin<int32_t>(k, 1), hin<int32_t>(k, 2), hout<uint8_t>(k, 3),
                                          hout<int32_t>(k, 4), hin<uint8_t>(k, 5), hin<uint32_t>(k, 6), arg_int(k, 7),
                                          arg_int(k, 8), arg_int(k, 9), arg_int(k, 10));
@@ -1264,6 +1325,9 @@ static size_t try_fused_tail(size_t i) {
     }
     if (!(target >= -2.0f) || !recon[0] || !recon[1] || !recon[2] || !MB || !seg_id || !parts || !ssim || !SD) return 0;
     if (recon[0]->size < (size_t)width * height || MB->size < mbs * 800) return 0;
+    // k_mb_fused starts every macroblock's ladder at MB_SSIM = -2: only valid when pack_8x8_into_16x16 reset this very
+    // buffer for the whole frame and nothing has written it since (otherwise kernel by kernel, which reads MB_SSIM)
+    if (ssim != g_packed_ssim || ssim->dev_version != g_packed_ssim_version || !ssim->dev_valid || g_packed_count != mbs) return 0;
     const uint8_t *imgp[9];
     for (int q = 0; q < 9; ++q) imgp[q] = img[q] ? (const uint8_t *)dev_ptr(img[q], false) : nullptr;
     ++g_kernel_launches;
@@ -1427,6 +1491,7 @@ static cl_mem new_mem(size_t size, bool image, int w, int h, bool want_host, cl_
     m->shadow_valid = false;
     m->lazy = false;
     m->host_staged = false;
+    m->guard_slot = -1;
     // zero-filled like the reference runtime's calloc: block 24 of never-16x16 macroblocks and the
     // nets of never-searched blocks are read before they are first written (Q4, Q9)
     cudaError_t e = cudaMalloc(&m->dev, size ? size : 1);

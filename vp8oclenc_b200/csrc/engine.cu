@@ -94,6 +94,7 @@ extern "C" vp8b200_engine *vp8b200_engine_create(int width, int height, void *st
 extern "C" void vp8b200_engine_destroy(vp8b200_engine *e) {
     if (!e) return;
     cudaStreamSynchronize(e->stream);
+    vp8b200_loop_filter_release(e->stream);
     for (int k = 0; k < 5; ++k) {
         cudaFree(e->cur_pyr[k]); cudaFree(e->last_pyr[k]); cudaFree(e->gold_pyr[k]); cudaFree(e->alt_pyr[k]);
     }

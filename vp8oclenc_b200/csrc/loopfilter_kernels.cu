@@ -443,26 +443,42 @@ using namespace vp8;
 // ticket counter and mailbox of the launches of one stream (launches on the same stream are ordered, launches
 // on different streams may overlap and must not share them)
 struct LFContext {
+    bool used;
     cudaStream_t stream;
     int *ctrl;
     uint32_t *mail;
     size_t mail_words;
     unsigned tag;
+    size_t smem_configured;  // dynamic shared memory the kernel has been allowed on this stream's device
 };
-static LFContext g_lf_ctx[64];
-static int g_lf_ctx_count = 0;
+static LFContext g_lf_ctx[256];
 static std::mutex g_lf_mutex;
 
 static LFContext *lf_context(cudaStream_t st) {
     std::lock_guard<std::mutex> lock(g_lf_mutex);
-    for (int i = 0; i < g_lf_ctx_count; ++i)
-        if (g_lf_ctx[i].stream == st) return &g_lf_ctx[i];
-    if (g_lf_ctx_count == 64) return nullptr;
-    LFContext *c = &g_lf_ctx[g_lf_ctx_count];
-    *c = LFContext{st, nullptr, nullptr, 0, 0};
-    if (cudaMalloc((void **)&c->ctrl, sizeof(int) * 4) != cudaSuccess) return nullptr;
-    ++g_lf_ctx_count;
-    return c;
+    LFContext *free_slot = nullptr;
+    for (LFContext &c : g_lf_ctx) {
+        if (c.used && c.stream == st) return &c;
+        if (!c.used && !free_slot) free_slot = &c;
+    }
+    if (!free_slot) return nullptr;
+    *free_slot = LFContext{false, st, nullptr, nullptr, 0, 0, 0};
+    if (cudaMalloc((void **)&free_slot->ctrl, sizeof(int) * 4) != cudaSuccess) return nullptr;
+    free_slot->used = true;
+    return free_slot;
+}
+
+// the owner of a stream (vp8b200_engine_destroy) gives the stream's ticket counter and mailbox back; a stream handle
+// the driver hands out again later starts from a clean state
+extern "C" void vp8b200_loop_filter_release(void *stream) {
+    std::lock_guard<std::mutex> lock(g_lf_mutex);
+    for (LFContext &c : g_lf_ctx)
+        if (c.used && c.stream == (cudaStream_t)stream) {
+            cudaStreamSynchronize(c.stream);
+            cudaFree(c.ctrl);
+            if (c.mail) cudaFree(c.mail);
+            c = LFContext{false, nullptr, nullptr, nullptr, 0, 0, 0};
+        }
 }
 
 static int launch_loop_filter(void *stream, LFPlanes p, int first_plane, int num_planes, const int32_t *seg,
@@ -492,11 +508,10 @@ static int launch_loop_filter(void *stream, LFPlanes p, int first_plane, int num
         const int plane = first_plane + ps;
         smem += lf_slot_bytes(plane == 0 ? 16 : 8, plane == 0 ? luma_w : luma_w / 2);
     }
-    static size_t configured = 0;
-    if (smem > configured) {
+    if (smem > c->smem_configured) {  // (the attribute is per device: remembered per stream, not per process)
         if (cudaFuncSetAttribute(k_loop_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return -(int)cudaGetLastError();
-        configured = smem;
+        c->smem_configured = smem;
     }
     k_loop_filter<<<mbh, LF_THREADS, smem, st>>>(p, first_plane, num_planes, seg, mb_mask, SD, luma_w, luma_h, c->ctrl,
                                                  c->mail, c->tag);

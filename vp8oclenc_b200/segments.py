@@ -1,9 +1,18 @@
 """Segment-parallel encoding: the only way the path shards.
 
 Frames depend on their references, so one stream cannot be split inside a group of pictures.
-It can be cut at multiples of the GOP size: the serial encoder places a forced key frame exactly
-there (frames_until_key reloads to -g at every key, src/intra_part.h:1091) and every piece of
-host state is reset or re-sent at a key frame.  Each segment is encoded by its own instance of
+It can be cut where the serial encoder places its key frames: every piece of host state is reset
+or re-sent at a key frame.  Where those are follows from the input alone as long as only the GOP
+counter and the colour-difference scene detector force them: frames_until_key reloads to -g at
+EVERY key frame, forced ones included (src/intra_part.h:1091), so after a scene cut at frame 70
+with -g 150 the next key is frame 220, not 150.  plan_key_frames() replays that logic on the
+chroma planes of the input (src/vp8enc.cpp:265-311, 364-412) and split_y4m_at() cuts there; the
+concatenation then equals the serial encode byte for byte.  Key frames the serial encoder forces
+AFTER an inter pass (bad SSIM / too many intra-replaced macroblocks, src/vp8enc.cpp:443-453)
+depend on the encode itself and cannot be planned: with such content the concatenation is a valid
+stream with the same frames but other key positions than the serial encode.  Plain cuts at
+multiples of -g (split_y4m) are exact only when no key frame is forced at all.
+Each segment is encoded by its own instance of
 the UNMODIFIED reference host against our OpenCL shim, pinned to one GPU with VP8B200_DEVICE;
 several instances share a GPU to hide the host's serial work.  There is no collective: the
 "gather" is host-side concatenation of the IVF files --
@@ -80,6 +89,95 @@ def split_y4m(path, seg_frames, out_dir, prefix="seg"):
     return paths
 
 
+def _y4m_geometry(header):
+    toks = header.split()
+    w = int([t for t in toks if t[:1] == b"W"][0][1:])
+    h = int([t for t in toks if t[:1] == b"H"][0][1:])
+    return w, h
+
+
+def plan_key_frames(path, gop):
+    """-> (sorted key frame indices of the serial encode of `path` with -g `gop`, exact)
+
+    Replays main()'s key-frame logic on the input: the GOP counter (src/vp8enc.cpp:364-368, reloaded by
+    intra_transform(), src/intra_part.h:1091-1093) and scene_change() (src/vp8enc.cpp:265-311: mean absolute
+    difference of the padded chroma planes against the previous input frame, with its hold-over for detections
+    less than four frames after a key).  `exact` is False when a cut would not reproduce the detector's state
+    (a key frame placed while a hold-over is pending); such a key is not reported as a cut."""
+    import numpy as np
+    with open(path, "rb") as f:
+        w, h = _y4m_geometry(f.readline())
+        cw, ch = w // 2, h // 2
+        wrk_cw, wrk_ch = ((w + 15) // 16 * 16) // 2, ((h + 15) // 16 * 16) // 2
+        fsz = w * h + 2 * cw * ch
+
+        def padded(plane, right_fill):
+            out = np.zeros((wrk_ch, wrk_cw), np.int32)
+            out[:ch, :cw] = plane
+            if wrk_cw > cw:  # copy_with_padding() (src/encIO.h:140-200) extends U to the right; V's padding is never written
+                out[:ch, cw:] = plane[:, -1:] if right_fill else 0
+            out[ch:, :] = out[ch - 1, :]
+            return out
+
+        keys, exact = [], True
+        until_key, last_key_detect, holdover = 1, 0, 0
+        last_u = last_v = None
+        n = 0
+        while True:
+            tag = f.read(6)
+            if len(tag) < 6:
+                break
+            blob = f.read(fsz)
+            if len(blob) < fsz:
+                break
+            u = padded(np.frombuffer(blob, np.uint8, cw * ch, w * h).reshape(ch, cw), True)
+            v = padded(np.frombuffer(blob, np.uint8, cw * ch, w * h + cw * ch).reshape(ch, cw), False)
+            until_key -= 1
+            key = until_key < 1
+            if not key:
+                size = wrk_cw * wrk_ch
+                ud = int(np.abs(last_u - u).sum()) // size
+                vd = int(np.abs(last_v - v).sum()) // size
+                detect = ud > 7 or vd > 7 or ud + vd > 10
+                since = n - last_key_detect
+                if detect and since < 4:
+                    last_key_detect, holdover = n, 1
+                elif detect:
+                    key = True
+                elif holdover and since >= 4:
+                    holdover, key = 0, True
+            if key:
+                if holdover and n > 0:
+                    exact = False  # a fresh instance would start without the pending hold-over: do not cut here
+                else:
+                    keys.append(n)
+                until_key, last_key_detect = gop, n
+            last_u, last_v = u, v
+            n += 1
+    return keys, exact
+
+
+def split_y4m_at(path, cuts, out_dir, prefix="seg"):
+    """cuts a Y4M file at the given frame indices (cuts[0] must be 0); returns the paths of the pieces"""
+    assert cuts and cuts[0] == 0
+    with open(path, "rb") as f:
+        header = f.readline()
+        w, h = _y4m_geometry(header)
+        fsz = 6 + w * h * 3 // 2
+        paths = []
+        for i, start in enumerate(cuts):
+            count = (cuts[i + 1] - start) if i + 1 < len(cuts) else None
+            blob = f.read(fsz * count) if count is not None else f.read()
+            if not blob:
+                break
+            p = os.path.join(out_dir, "%s%03d.y4m" % (prefix, i))
+            with open(p, "wb") as g:
+                g.write(header)
+                g.write(blob)
+            paths.append(p)
+    return paths
+
+
 class MpsDaemon:
     """CUDA Multi-Process Service for the encoder instances that share a GPU.
 
@@ -141,6 +239,9 @@ class EncoderProcess:
                 f.write(txt)
         env = dict(os.environ)
         env["LD_LIBRARY_PATH"] = lib_dir + os.pathsep + env.get("LD_LIBRARY_PATH", "")
+        # the binary started here IS the reference host (build_host.py): the shim may use the modes that rely on its
+        # habits (csrc/cl_shim.cu, VP8B200_HOST_PROFILE); env_extra can still override every single one of them
+        env.setdefault("VP8B200_HOST_PROFILE", "reference")
         if device is not None:
             env["VP8B200_DEVICE"] = str(device)
         env.update(env_extra or {})
@@ -177,6 +278,41 @@ class EncoderProcess:
         return self.stamps
 
 
+def assign_segments(n_segments, world, rank):
+    """which segments rank `rank` of `world` encodes: round-robin, so that every rank gets early and late
+    (possibly shorter) segments alike.  The ranks share nothing but this rule and the input."""
+    return list(range(rank, n_segments, world))
+
+
+def encode_clip_segment_parallel(y4m, args, gop, work_dir, rank=0, world=1, device=0, per_device=1, lib_dir=SHIM_DIR,
+                                 host_bin=HOST_BIN, mps_env=None, plan=None):
+    """One rank's share of a segment-parallel encode of `y4m` (config 4/5 of BASELINE.json): plans the cuts
+    (plan_key_frames, the same on every rank), writes and encodes the segments assign_segments() gives this rank,
+    `per_device` at a time on `device`.  Returns (n_segments, {segment index: ivf path}, exact, [EncoderProcess]).
+    The gather is concat_ivf() over all ranks' paths in segment order on one rank (files on a shared directory;
+    the only communication the caller needs is a barrier)."""
+    keys, exact = plan if plan is not None else plan_key_frames(y4m, gop)
+    mine = assign_segments(len(keys), world, rank)
+    os.makedirs(work_dir, exist_ok=True)
+    with open(y4m, "rb") as f:
+        header = f.readline()
+        w, h = _y4m_geometry(header)
+        fsz = 6 + w * h * 3 // 2
+        base = f.tell()
+        seg_paths = {}
+        for i in mine:
+            f.seek(base + fsz * keys[i])
+            blob = f.read(fsz * (keys[i + 1] - keys[i])) if i + 1 < len(keys) else f.read()
+            seg_paths[i] = os.path.join(work_dir, "seg%04d.y4m" % i)
+            with open(seg_paths[i], "wb") as g:
+                g.write(header)
+                g.write(blob)
+    order = sorted(seg_paths)
+    ivfs, procs = _encode_segments([seg_paths[i] for i in order], work_dir, args, (device,), per_device, lib_dir, host_bin,
+                                   mps_env or {}, names=["seg%04d" % i for i in order])
+    return len(keys), dict(zip(order, ivfs)), exact, procs
+
+
 def encode_segments(seg_paths, out_dir, args, devices=(0,), per_device=1, lib_dir=SHIM_DIR, host_bin=HOST_BIN, mps=True):
     """encodes every segment, at most len(devices)*per_device at a time, round-robin over the
     devices; returns (list of ivf paths, list of EncoderProcess).  With several instances per
@@ -187,16 +323,17 @@ def encode_segments(seg_paths, out_dir, args, devices=(0,), per_device=1, lib_di
     return _encode_segments(seg_paths, out_dir, args, devices, per_device, lib_dir, host_bin, {})
 
 
-def _encode_segments(seg_paths, out_dir, args, devices, per_device, lib_dir, host_bin, env_extra):
+def _encode_segments(seg_paths, out_dir, args, devices, per_device, lib_dir, host_bin, env_extra, names=None):
     slots = [d for d in devices for _ in range(per_device)]
-    ivfs = [os.path.join(out_dir, "seg%03d.ivf" % i) for i in range(len(seg_paths))]
+    names = names or ["seg%03d" % i for i in range(len(seg_paths))]
+    ivfs = [os.path.join(out_dir, n + ".ivf") for n in names]
     procs, running = [None] * len(seg_paths), {}
     nxt = 0
     free = list(range(len(slots)))
     while nxt < len(seg_paths) or running:
         while free and nxt < len(seg_paths):
             s = free.pop(0)
-            procs[nxt] = EncoderProcess(seg_paths[nxt], ivfs[nxt], args, os.path.join(out_dir, "run%03d" % nxt), lib_dir,
+            procs[nxt] = EncoderProcess(seg_paths[nxt], ivfs[nxt], args, os.path.join(out_dir, "run_" + names[nxt]), lib_dir,
                                         host_bin, device=slots[s], env_extra=env_extra)
             running[nxt] = s
             nxt += 1
