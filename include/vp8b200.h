@@ -220,6 +220,20 @@ void *vp8b200_engine_buffer(vp8b200_engine *e, int which);
 /* number of kernels the last inter_frame + loop_filter launched */
 int vp8b200_engine_last_launch_count(vp8b200_engine *e);
 
+/* Measurement aid (bench.py's per-kernel roofline lines): with stage timing on, the engine records a CUDA event
+ * on its stream at every stage boundary of a frame; vp8b200_engine_stage_times() waits for the stream and returns
+ * the duration in milliseconds of every stage of the LAST frame (-1 for a stage that did not run).  The stages
+ * follow the reference's enqueue sequence: buffer preparation (copies, reset_vectors, pyramid), the five
+ * luma_search_1step levels, luma_search_2step, select_reference + pack, the predict / transform / SSIM ladder,
+ * prepare_filter_mask, the loop filter. */
+enum {
+    VP8B200_STAGE_SETUP = 0, VP8B200_STAGE_SEARCH_16X, VP8B200_STAGE_SEARCH_8X, VP8B200_STAGE_SEARCH_4X,
+    VP8B200_STAGE_SEARCH_2X, VP8B200_STAGE_SEARCH_1X, VP8B200_STAGE_SEARCH_QPEL, VP8B200_STAGE_SELECT,
+    VP8B200_STAGE_TRANSFORM, VP8B200_STAGE_FILTER_MASK, VP8B200_STAGE_LOOP_FILTER, VP8B200_NUM_STAGES
+};
+int vp8b200_engine_stage_timing(vp8b200_engine *e, int on);
+int vp8b200_engine_stage_times(vp8b200_engine *e, float *ms, int cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,6 +28,10 @@ struct vp8b200_engine {
     int sd_next;
     int launches;
     bool fused;  // VP8B200_FUSED=0 selects the kernel-per-kernel sequence
+    // stage timing (vp8b200_engine_stage_timing): events at the stage boundaries of a frame on the engine's stream
+    bool timing;
+    cudaEvent_t stage_ev[VP8B200_NUM_STAGES + 1];
+    bool stage_seen[VP8B200_NUM_STAGES + 1];
 };
 
 namespace {
@@ -43,7 +47,33 @@ bool dalloc(T *&p, size_t bytes) {
         ++e->launches;    \
     } while (0)
 inline int cu(cudaError_t err) { return err == cudaSuccess ? 0 : -(int)err; }
+// start of stage i (= end of stage i - 1)
+inline void stage(vp8b200_engine *e, int i) {
+    if (!e->timing) return;
+    cudaEventRecord(e->stage_ev[i], e->stream);
+    e->stage_seen[i] = true;
+}
 }  // namespace
+
+extern "C" int vp8b200_engine_stage_timing(vp8b200_engine *e, int on) {
+    if (!e) return -1;
+    if (on && !e->stage_ev[0])
+        for (int i = 0; i <= VP8B200_NUM_STAGES; ++i)
+            if (cudaEventCreate(&e->stage_ev[i]) != cudaSuccess) return -(int)cudaGetLastError();
+    e->timing = on != 0;
+    for (int i = 0; i <= VP8B200_NUM_STAGES; ++i) e->stage_seen[i] = false;
+    return 0;
+}
+
+extern "C" int vp8b200_engine_stage_times(vp8b200_engine *e, float *ms, int cap) {
+    if (!e || !e->timing) return -1;
+    if (cudaStreamSynchronize(e->stream) != cudaSuccess) return -(int)cudaGetLastError();
+    for (int i = 0; i < VP8B200_NUM_STAGES && i < cap; ++i) {
+        ms[i] = -1.0f;
+        if (e->stage_seen[i] && e->stage_seen[i + 1]) cudaEventElapsedTime(&ms[i], e->stage_ev[i], e->stage_ev[i + 1]);
+    }
+    return 0;
+}
 
 extern "C" vp8b200_engine *vp8b200_engine_create(int width, int height, void *stream) {
     if (width < 16 || height < 16 || (width & 15) || (height & 15)) return nullptr;
@@ -107,6 +137,8 @@ extern "C" void vp8b200_engine_destroy(vp8b200_engine *e) {
     for (int p = 0; p < 3; ++p) { cudaFree(e->pred[p]); cudaFree(e->res[p]); }
     cudaFree(e->coeffs); cudaFree(e->vectors); cudaFree(e->parts); cudaFree(e->ref_frame); cudaFree(e->seg_id);
     cudaFree(e->nz); cudaFree(e->mask); cudaFree(e->ssim); cudaFree(e->sd_dev);
+    for (int i = 0; i <= VP8B200_NUM_STAGES; ++i)
+        if (e->stage_ev[i]) cudaEventDestroy(e->stage_ev[i]);
     if (e->sd_pinned) cudaFreeHost(e->sd_pinned);
     for (int i = 0; i < 8; ++i)
         if (e->sd_event[i]) cudaEventDestroy(e->sd_event[i]);
@@ -167,6 +199,7 @@ static int inter_frame_body(vp8b200_engine *e, const uint8_t *cur_y, const uint8
     const uint8_t *cur[3] = {cur_y, cur_u, cur_v};
     uint8_t *recon[3] = {e->last_pyr[0], e->recon_u, e->recon_v};
     e->launches = 0;
+    stage(e, VP8B200_STAGE_SETUP);
 
     // the host's uploads of the previous (loop-filtered) reconstruction into the image objects
     // (src/vp8enc.cpp:399-401) are device-to-device copies here
@@ -215,6 +248,7 @@ static int inter_frame_body(vp8b200_engine *e, const uint8_t *cur_y, const uint8
                 sn[i] = e->net[rid[i]][src];
                 dn[i] = e->net[rid[i]][src ^ 1];
             }
+            stage(e, VP8B200_STAGE_SEARCH_16X + (4 - k));
             TRY(vp8b200_luma_search_1step_multi(s, cpyr[k], nrefs, rp, sn, dn, (w / 16) * 2, w >> k, h >> k, 1 << k));
         }
         for (int i = 0; i < nrefs; ++i) {
@@ -223,23 +257,28 @@ static int inter_frame_body(vp8b200_engine *e, const uint8_t *cur_y, const uint8
             dn[i] = e->net[rid[i]][0];
             met[i] = e->metrics[rid[i]];
         }
+        stage(e, VP8B200_STAGE_SEARCH_QPEL);
         TRY(vp8b200_luma_search_2step_multi(s, cur_y, nrefs, rp, sn, dn, met, w, h));
     } else {
         for (int k = 4; k >= 0; --k) {
             const int src = (k & 1) ? 1 : 0;
+            stage(e, VP8B200_STAGE_SEARCH_16X + (4 - k));
             for (int r = 0; r < 3; ++r)
                 if (use[r])
                     TRY(vp8b200_luma_search_1step(s, cpyr[k], pyr[r][k], e->net[r][src], e->net[r][src ^ 1], (w / 16) * 2,
                                                   w >> k, h >> k, 1 << k));
         }
+        stage(e, VP8B200_STAGE_SEARCH_QPEL);
         for (int r = 0; r < 3; ++r)
             if (use[r])
                 TRY(vp8b200_luma_search_2step(s, cur_y, e->img[r][0], e->net[r][1], e->net[r][0], e->metrics[r], w, h));
     }
 
+    stage(e, VP8B200_STAGE_SELECT);
     TRY(vp8b200_select_reference(s, e->net[0][0], e->net[1][0], e->net[2][0], e->metrics[0], e->metrics[1], e->metrics[2],
                                  e->ref_frame, e->vectors, w, h, use_golden, use_altref));
     TRY(vp8b200_pack_8x8_into_16x16(s, e->vectors, e->parts, e->ssim, M));
+    stage(e, VP8B200_STAGE_TRANSFORM);
 
     if (e->fused && SSIM_target >= -2.0f) {
         const uint8_t *img[9];
@@ -248,6 +287,7 @@ static int inter_frame_body(vp8b200_engine *e, const uint8_t *cur_y, const uint8
         TRY(vp8b200_mb_predict_transform_fused(s, cur_y, cur_u, cur_v, img, e->ref_frame, e->vectors, e->parts, e->coeffs,
                                                e->seg_id, e->ssim, recon[0], recon[1], recon[2], e->sd_dev, SSIM_target,
                                                w, h));
+        stage(e, VP8B200_STAGE_FILTER_MASK);
         return 0;
     }
     for (int p = 0; p < 3; ++p)
@@ -270,6 +310,7 @@ static int inter_frame_body(vp8b200_engine *e, const uint8_t *cur_y, const uint8
                                    seg, p ? 8 : 16));
         TRY(vp8b200_gather_SSIM(s, (float *)e->metrics[0], (float *)e->metrics[1], (float *)e->metrics[2], e->ssim, M));
     }
+    stage(e, VP8B200_STAGE_FILTER_MASK);
     return 0;
 }
 
@@ -287,9 +328,12 @@ extern "C" int vp8b200_engine_loop_filter(vp8b200_engine *e, const vp8b200_segme
         if (rc) return rc;
     }
     e->launches = 0;
+    stage(e, VP8B200_STAGE_FILTER_MASK);
     TRY(vp8b200_prepare_filter_mask(e->stream, e->coeffs, e->nz, e->parts, e->mask, e->w, e->h));
+    stage(e, VP8B200_STAGE_LOOP_FILTER);
     TRY(vp8b200_loop_filter_planes(e->stream, e->last_pyr[0], e->recon_u, e->recon_v, e->seg_id, e->mask, e->sd_dev, e->w,
                                    e->h));
+    stage(e, VP8B200_NUM_STAGES);
     return 0;
 }
 

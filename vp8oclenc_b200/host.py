@@ -251,6 +251,18 @@ class Engine:
     def last_launch_count(self):
         return lib().vp8b200_engine_last_launch_count(self._h)
 
+    STAGES = ("setup", "search_16x", "search_8x", "search_4x", "search_2x", "search_1x", "search_qpel", "select",
+              "transform", "filter_mask", "loop_filter")
+
+    def stage_timing(self, on=True):
+        _check(lib().vp8b200_engine_stage_timing(self._h, int(on)), "engine_stage_timing")
+
+    def stage_times(self):
+        """{stage name: milliseconds} of the last frame (waits for the stream); stages that did not run are left out"""
+        buf = (ctypes.c_float * len(self.STAGES))()
+        _check(lib().vp8b200_engine_stage_times(self._h, buf, len(self.STAGES)), "engine_stage_times")
+        return {n: float(buf[i]) for i, n in enumerate(self.STAGES) if buf[i] >= 0.0}
+
 
 _cudart_lib = None
 
