@@ -81,6 +81,64 @@ __device__ __forceinline__ void filter_b_edge(int p3, int p2, int &p1, int &p0, 
     p1 += a;
 }
 
+// Inner edges 8 and 12 of a line depend on the edge before them only through two terms of the filter mask (their
+// p3, p2 are the q0, q1 the edge before has just rewritten; p1, p0 and the q side are still untouched).  So the
+// filter is evaluated from the untouched pixels while the edges before it are still in flight (the lanes of a
+// filter warp are latency-bound: one dependent chain per lane) and only the mask is resolved afterwards: a masked-off
+// edge leaves all four pixels as they were (a = 0 gives b = 0 and (a + 1) >> 1 = 0).
+struct SpecEdge {
+    int p1, p0, q0, q1;  // what the four pixels become if the edge is filtered
+    int off;             // mask terms that do not involve p3, p2
+};
+__device__ __forceinline__ SpecEdge spec_b_edge(int p1, int p0, int q0, int q1, int q2, int q3, int b_lim, int int_lim,
+                                                int hev_thr) {
+    SpecEdge s;
+    s.off = lf_over(p1, p0, int_lim) | lf_over(q1, q0, int_lim) | lf_over(q2, q1, int_lim) | lf_over(q3, q2, int_lim) |
+            ((abs(p0 - q0) * 2 + (abs(p1 - q1) >> 1)) > b_lim);
+    const int hev = lf_over(p1, p0, hev_thr) | lf_over(q1, q0, hev_thr);
+    int a = hev ? c128(p1 - q1) : 0;
+    a = c128(a + 3 * (q0 - p0));
+    const int b = c128(a + 3) >> 3;
+    a = c128(a + 4) >> 3;
+    s.q0 = q0 - a;
+    s.p0 = p0 + b;
+    a = (a + 1) >> 1;
+    a = hev ? 0 : a;
+    s.q1 = q1 - a;
+    s.p1 = p1 + a;
+    return s;
+}
+__device__ __forceinline__ void resolve_b_edge(const SpecEdge &s, int p3, int p2, int &p1, int &p0, int &q0, int &q1,
+                                               int int_lim) {
+    const int off = s.off | lf_over(p3, p2, int_lim) | lf_over(p2, p1, int_lim);
+    p1 = off ? p1 : s.p1;
+    p0 = off ? p0 : s.p0;
+    q0 = off ? q0 : s.q0;
+    q1 = off ? q1 : s.q1;
+}
+
+// The edges of one line of N pixels of a macroblock, v[0..3] = the four pixels before it, v[4..4+N) the line, all as
+// pixel - 128; results stay UNCLAMPED in v (within one macroblock the reference hands the unclamped q0..q3 of an edge
+// on as p3..p0 of the next, Q7; memory gets the clamped values).  Same results as the edge-after-edge walk
+// (filter_mb_edge, then filter_b_edge at 4, 8, 12), shorter dependent chain: see SpecEdge.
+template <int N>
+__device__ __forceinline__ void filter_line_spec(int (&v)[N + 4], bool mb_edge, bool inner, int mb_lim, int b_lim,
+                                                 int int_lim, int hev_thr) {
+    SpecEdge s8, s12;
+    if (N == 16 && inner) {
+        s8 = spec_b_edge(v[10], v[11], v[12], v[13], v[14], v[15], b_lim, int_lim, hev_thr);
+        s12 = spec_b_edge(v[14], v[15], v[16], v[17], v[18], v[19], b_lim, int_lim, hev_thr);
+    }
+    if (mb_edge) filter_mb_edge(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], mb_lim, int_lim, hev_thr);
+    if (inner) {
+        filter_b_edge(v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11], b_lim, int_lim, hev_thr);
+        if (N == 16) {
+            resolve_b_edge(s8, v[8], v[9], v[10], v[11], v[12], v[13], int_lim);
+            resolve_b_edge(s12, v[12], v[13], v[14], v[15], v[16], v[17], int_lim);
+        }
+    }
+}
+
 // All edges that cross one line of N pixels (v[4..4+N)) plus the 4 pixels before it (v[0..4)).
 // v holds pixel-128 and keeps the UNCLAMPED results: within one macroblock the reference
 // hands the unclamped q0..q3 of an edge on as p3..p0 of the next (Q7); memory gets clamped.
@@ -105,7 +163,12 @@ __device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d) {
     return r ^ 0x80808080u;
 }
 // byte k of a word of pixels -> pixel-128 (flip the sign bit, sign-extend)
-__device__ __forceinline__ int unpack1(uint32_t w_flipped, int k) { return (int)(signed char)(w_flipped >> (8 * k)); }
+// (one PRMT: selector nibble k takes byte k, nibbles 8|k replicate its sign bit)
+__device__ __forceinline__ int unpack1(uint32_t w_flipped, int k) {
+    int v;
+    asm("prmt.b32 %0, %1, 0, %2;" : "=r"(v) : "r"(w_flipped), "r"(0x8880 + 0x1111 * k));
+    return v;
+}
 
 __device__ __forceinline__ int ld_acquire(const int *p) {
     int v;
@@ -119,6 +182,17 @@ __device__ __forceinline__ void st_release(int *p, int v) {
 __device__ __forceinline__ uint32_t ld_cg_u8(const uint8_t *p) {
     uint32_t v;
     asm volatile("ld.global.cg.u8 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// progress flags between the warps of a CTA (shared memory): release store / acquire load at CTA scope -- the
+// sequentially consistent fence __threadfence_block() compiles to (MEMBAR.SC.CTA) is not needed for a hand-off
+__device__ __forceinline__ void flag_release(volatile int *p, int v) {
+    asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(const_cast<int *>(p))), "r"(v) : "memory");
+}
+__device__ __forceinline__ int flag_acquire(volatile int *p) {
+    int v;
+    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(const_cast<int *>(p))) : "memory");
     return v;
 }
 
@@ -160,6 +234,14 @@ __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p) {
     return v;
 }
 
+// VP8_LF_SPECULATIVE selects filter_line_spec (measured on B200, 1080p, three planes: 242 us against 227 us for the
+// edge-after-edge walk: the filter warp is bound by the number of instructions it has to issue on its own, about 700
+// per macroblock at an IPC of 0.3, not by the depth of the dependent chain, and speculation adds instructions)
+#if defined(VP8_LF_SPECULATIVE)
+#define LF_FILTER_LINE filter_line_spec
+#else
+#define LF_FILTER_LINE filter_line
+#endif
 template <int N>
 __device__ void lf_plane_roles(uint8_t *__restrict__ frame, int width, int r, int ncols, bool row_below_exists,
                                int stop_below_cols, LFSlot sl, uint32_t *mail_row, const uint32_t *mail_above,
@@ -180,77 +262,60 @@ __device__ void lf_plane_roles(uint8_t *__restrict__ frame, int width, int r, in
             const int x0 = c * N;
             // Both passes walk the N/4 four-pixel groups of a line with a sliding window p3..p0 | q0..q3
             // kept in registers: the unclamped q's of one edge are the p's of the next (Q7).
-            if (lane < N) {  // pass 1: one lane per pixel row
+            if (lane < N) {  // pass 1: one lane per pixel row, the whole line in registers
                 uint32_t *row = reinterpret_cast<uint32_t *>(strip + lane * S + 4 + x0);
-                int p3, p2, p1, p0, q0, q1, q2, q3;
-                uint32_t w = row[0] ^ 0x80808080u;
-                q0 = unpack1(w, 0); q1 = unpack1(w, 1); q2 = unpack1(w, 2); q3 = unpack1(w, 3);
-                if (c > 0) {
-                    w = row[-1] ^ 0x80808080u;
-                    p3 = unpack1(w, 0); p2 = unpack1(w, 1); p1 = unpack1(w, 2); p0 = unpack1(w, 3);
-                    filter_mb_edge(p3, p2, p1, p0, q0, q1, q2, q3, mb_lim, int_lim, hev_thr);
-                    row[-1] = pack4(p3, p2, p1, p0);
-                }
+                int v[N + 4];
+                uint32_t w = c > 0 ? row[-1] ^ 0x80808080u : 0u;
+                v[0] = unpack1(w, 0); v[1] = unpack1(w, 1); v[2] = unpack1(w, 2); v[3] = unpack1(w, 3);
 #pragma unroll
-                for (int e = 1; e < N / 4; ++e) {
-                    p3 = q0; p2 = q1; p1 = q2; p0 = q3;
+                for (int e = 0; e < N / 4; ++e) {
                     w = row[e] ^ 0x80808080u;
-                    q0 = unpack1(w, 0); q1 = unpack1(w, 1); q2 = unpack1(w, 2); q3 = unpack1(w, 3);
-                    if (inner) filter_b_edge(p3, p2, p1, p0, q0, q1, q2, q3, b_lim, int_lim, hev_thr);
-                    row[e - 1] = pack4(p3, p2, p1, p0);
+                    v[4 + 4 * e] = unpack1(w, 0); v[5 + 4 * e] = unpack1(w, 1); v[6 + 4 * e] = unpack1(w, 2); v[7 + 4 * e] = unpack1(w, 3);
                 }
-                row[N / 4 - 1] = pack4(q0, q1, q2, q3);
+                LF_FILTER_LINE<N>(v, c > 0, inner, mb_lim, b_lim, int_lim, hev_thr);
+                if (c > 0) row[-1] = pack4(v[0], v[1], v[2], v[3]);
+#pragma unroll
+                for (int e = 0; e < N / 4; ++e) row[e] = pack4(v[4 + 4 * e], v[5 + 4 * e], v[6 + 4 * e], v[7 + 4 * e]);
             }
             __syncwarp();
-            if (lane == 0) {
-                __threadfence_block();
-                flags[0] = c + 1;  // h_done: macroblock c-1 is final now
-            }
+            if (lane == 0) flag_release(&flags[0], c + 1);  // h_done: macroblock c-1 is final now
             if (r > 0) {
-                while (flags[2] < c + 1) {}  // the lines above macroblock c are in the ring
-                __threadfence_block();
+                while (flag_acquire(&flags[2]) < c + 1) {}  // the lines above macroblock c are in the ring
             }
-            if (lane < N) {  // pass 2: one lane per pixel column
+            if (lane < N) {  // pass 2: one lane per pixel column, the whole column in registers
                 uint8_t *scol = strip + 4 + x0 + lane;
-                int p3, p2, p1, p0, q0, q1, q2, q3;
-                q0 = (int)scol[0] - 128; q1 = (int)scol[S] - 128; q2 = (int)scol[2 * S] - 128; q3 = (int)scol[3 * S] - 128;
+                int v[N + 4];
+#pragma unroll
+                for (int j = 0; j < N; ++j) v[4 + j] = (int)scol[j * S] - 128;
+                v[0] = v[1] = v[2] = v[3] = 0;
                 if (r > 0) {
                     const uint8_t *tq = reinterpret_cast<const uint8_t *>(topq + (c % TOPQ) * N) + lane;
-                    p3 = (int)tq[0] - 128; p2 = (int)tq[N] - 128; p1 = (int)tq[2 * N] - 128; p0 = (int)tq[3 * N] - 128;
-                    filter_mb_edge(p3, p2, p1, p0, q0, q1, q2, q3, mb_lim, int_lim, hev_thr);
+                    v[0] = (int)tq[0] - 128; v[1] = (int)tq[N] - 128; v[2] = (int)tq[2 * N] - 128; v[3] = (int)tq[3 * N] - 128;
+                }
+                LF_FILTER_LINE<N>(v, r > 0, inner, mb_lim, b_lim, int_lim, hev_thr);
+                if (r > 0) {
                     // the three lines above now belong to this row: straight to the frame
                     uint8_t *gcol = frame + (size_t)y0 * width + x0 + lane;
-                    const uint32_t t = pack4(p3, p2, p1, p0);
+                    const uint32_t t = pack4(v[0], v[1], v[2], v[3]);
                     gcol[-3 * (ptrdiff_t)width] = (uint8_t)(t >> 8);
                     gcol[-2 * (ptrdiff_t)width] = (uint8_t)(t >> 16);
                     gcol[-1 * (ptrdiff_t)width] = (uint8_t)(t >> 24);
                 }
 #pragma unroll
-                for (int e = 1; e < N / 4; ++e) {
-                    p3 = q0; p2 = q1; p1 = q2; p0 = q3;
+                for (int e = 0; e < N / 4; ++e) {
                     uint8_t *g = scol + 4 * e * S;
-                    q0 = (int)g[0] - 128; q1 = (int)g[S] - 128; q2 = (int)g[2 * S] - 128; q3 = (int)g[3 * S] - 128;
-                    if (inner) filter_b_edge(p3, p2, p1, p0, q0, q1, q2, q3, b_lim, int_lim, hev_thr);
-                    const uint32_t t = pack4(p3, p2, p1, p0);
-                    g[-4 * S] = (uint8_t)t; g[-3 * S] = (uint8_t)(t >> 8); g[-2 * S] = (uint8_t)(t >> 16); g[-S] = (uint8_t)(t >> 24);
-                }
-                {
-                    uint8_t *g = scol + (N - 4) * S;
-                    const uint32_t t = pack4(q0, q1, q2, q3);
+                    const uint32_t t = pack4(v[4 + 4 * e], v[5 + 4 * e], v[6 + 4 * e], v[7 + 4 * e]);
                     g[0] = (uint8_t)t; g[S] = (uint8_t)(t >> 8); g[2 * S] = (uint8_t)(t >> 16); g[3 * S] = (uint8_t)(t >> 24);
                 }
             }
             __syncwarp();
-            if (lane == 0) {
-                __threadfence_block();
-                flags[1] = c + 1;  // v_done
-            }
+            if (lane == 0) flag_release(&flags[1], c + 1);  // v_done
         }
     } else if (role == 1) {
         // ---- receiver warp: the four lines above each macroblock, from the mailbox of the row above ----
         if (r > 0) {
             for (int c = 0; c < ncols; ++c) {
-                while (c - flags[1] >= TOPQ) {}  // ring slot free again
+                while (c - flag_acquire(&flags[1]) >= TOPQ) {}  // ring slot free again
                 const uint32_t *m = mail_above + (size_t)c * 32 + lane;
                 uint32_t w;
                 do {
@@ -265,10 +330,7 @@ __device__ void lf_plane_roles(uint8_t *__restrict__ frame, int width, int r, in
                     if ((lane & 1) == 0 && lane < 16) topq[(c % TOPQ) * N + (lane >> 1)] = (w & 0xffffu) | (other << 16);
                 }
                 __syncwarp();
-                if (lane == 0) {
-                    __threadfence_block();
-                    flags[2] = c + 1;  // top_ready
-                }
+                if (lane == 0) flag_release(&flags[2], c + 1);  // top_ready
             }
         }
     } else {
@@ -276,11 +338,10 @@ __device__ void lf_plane_roles(uint8_t *__restrict__ frame, int width, int r, in
         for (int c = 0; c < ncols; ++c) {
             // macroblock c is final once pass 1 of macroblock c+1 ran, the last one after its own pass 2
             if (c + 1 < ncols) {
-                while (flags[0] < c + 2) {}
+                while (flag_acquire(&flags[0]) < c + 2) {}
             } else {
-                while (flags[1] < ncols) {}
+                while (flag_acquire(&flags[1]) < ncols) {}
             }
-            __threadfence_block();
             const bool consumer = row_below_exists && c < stop_below_cols;
             if (consumer) {
                 // 4 lines x N/4 words, split in halves: word k -> lanes 2k, 2k+1 (N=8 uses lanes 0..15)

@@ -12,7 +12,7 @@ import os
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_PKG, "lib", "libvp8b200.so")
+_LIB_PATH = os.environ.get("VP8B200_ENGINE_LIB") or os.path.join(_PKG, "lib", "libvp8b200.so")  # (the variable: kernel-tuning variants, tools/)
 _lib = None
 
 
