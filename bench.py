@@ -442,9 +442,10 @@ def end_to_end(args, w, h, Ke, W, rank, world, local_rank, dist, tmp, ref_ivf, d
     cores = os.cpu_count() or 2
     big = padded(w, h)[0] * padded(w, h)[1] > 1920 * 1088
     if daemon.active:
-        # one and a half instances per host core (the instances sleep while they wait for the GPU: a second one fills the
-        # gap), at most 32 per GPU (24 above 1080p) and 128 on the node
-        P = args.e2e_procs or max(1, min(24 if big else 32, (3 * cores) // (2 * world), max(4, 128 // world)))
+        # one and a half instances per host core on one or two GPUs, two per core beyond (the instances sleep while they
+        # wait for the GPU: the others fill the gap), at most 32 per GPU (24 above 1080p) and 128 on the node
+        per_core = 3 if world <= 2 else 4
+        P = args.e2e_procs or max(1, min(24 if big else 32, (per_core * cores) // (2 * world), max(4, 128 // world)))
     else:
         P = args.e2e_procs or max(1, min(8, cores // max(2, 2 * world)))
     err_text, fps1, fpsP, per, check, cpu = None, 0.0, 0.0, None, None, None
@@ -513,17 +514,18 @@ def segment_parallel_config(args, which, rank, world, local_rank, dist, tmp):
         gen_y4m.write_y4m(y4m, w, h, frames)
     if dist:
         dist.barrier()
+    plan = segments.plan_key_frames(y4m, gop)
+    nseg = len(plan[0])
+    per_rank = (nseg + world - 1) // world
+    P = args.e2e_procs or max(1, min(per_rank, 16, (3 * (os.cpu_count() or 2)) // (2 * world)))
+    # (two contexts on a GPU time-slice well enough; bringing the MPS server up costs more than it saves then)
     daemon = segments.MpsDaemon(os.path.join(tempfile.gettempdir(), "vp8b200_mps_%s" % os.environ.get("MASTER_PORT", os.getpid())))
-    if local_rank == 0 and not args.no_mps:
+    if local_rank == 0 and not args.no_mps and P > 2:
         daemon.__enter__()
     if dist:
         dist.barrier()
         daemon.active = os.path.exists(os.path.join(daemon.pipe, "control"))
     try:
-        plan = segments.plan_key_frames(y4m, gop)
-        nseg = len(plan[0])
-        per_rank = (nseg + world - 1) // world
-        P = args.e2e_procs or max(1, min(per_rank, 16, (3 * (os.cpu_count() or 2)) // (2 * world)))
         if dist:
             dist.barrier()
         torch.cuda.synchronize()
@@ -533,6 +535,9 @@ def segment_parallel_config(args, which, rank, world, local_rank, dist, tmp):
                                                                       mps_env=daemon.env(), plan=plan)
         t_mine = time.perf_counter() - t0
         steady = [(len(pr.stamps) - 2) / (pr.stamps[-1] - pr.stamps[1]) for pr in procs if len(pr.stamps) > 2]
+        # where an instance's wall time goes: start-up until its key frame is coded, the inter frames, shutdown
+        phases = [(pr.stamps[0] - pr.t_start, pr.stamps[-1] - pr.stamps[0], pr.t_end - pr.stamps[-1]) for pr in procs if pr.stamps]
+        phase_avg = [sum(p[k] for p in phases) / max(1, len(phases)) for k in range(3)]
         if dist:
             tt = torch.tensor([t_mine], device="cuda", dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -563,6 +568,9 @@ def segment_parallel_config(args, which, rank, world, local_rank, dist, tmp):
                     "seconds_segment_parallel": t_all, "seconds_serial_one_instance": t_serial, "speedup_vs_serial_instance": t_serial / t_all,
                     "includes": "process start-up, CUDA context creation and the host-coded key frame of every segment",
                     "steady_frames_per_s_per_instance": sum(steady) / max(1, len(steady)),
+                    "instance_seconds": {"start_to_key_frame_coded": phase_avg[0], "inter_frames": phase_avg[1], "shutdown": phase_avg[2],
+                                         "note": "rank 0's instances, averaged"},
+                    "mps": bool(daemon.active),
                     "frames_in_concatenation": total, "identical_to_serial_encode": a == b,
                     "md5": hashlib.md5(b).hexdigest(), "bytes": len(b)}
             print(json.dumps(line))

@@ -71,6 +71,14 @@ int vp8b200_luma_search_2step_multi(void *stream, const uint8_t *current_frame, 
                                     const uint8_t *const *ref_frame, const int16_t *const *net, int16_t *const *ref_net,
                                     int32_t *const *ref_Bdiff, int width, int height);
 
+/* Experiment (not used by the frame pipeline): the same search with its reference windows staged by TMA 2-D box
+ * copies out of a replicate-padded copy of the plane instead of word loads + funnel shifts.  `padded` is scratch of
+ * (width + 32) * (height + 32) bytes; pad_only != 0 only builds the padded plane (to time the two parts apart).
+ * Bit-identical results; the A/B numbers are in DESIGN.md section 4. */
+int vp8b200_experiment_search_2step_tma(void *stream, const uint8_t *current_frame, const uint8_t *ref_frame, uint8_t *padded,
+                                        const int16_t *net, int16_t *ref_net, int32_t *ref_Bdiff, int width, int height,
+                                        int pad_only);
+
 /* replaces select_reference, src/GPU_kernels.cl:1205-1283 (src/inter_part.h:250-255) */
 int vp8b200_select_reference(void *stream, const int16_t *last_net, const int16_t *golden_net,
                              const int16_t *altref_net, const int32_t *last_Bdiff, const int32_t *golden_Bdiff,
@@ -163,6 +171,17 @@ int vp8b200_loop_filter_planes(void *stream, uint8_t *y, uint8_t *u, uint8_t *v,
 /* The loop filter keeps a ticket counter and a mailbox per stream; whoever owns a stream releases them before
  * destroying it (vp8b200_engine_destroy does so for its own). */
 void vp8b200_loop_filter_release(void *stream);
+
+/* the two O(N) reductions the reference host runs on every frame in plain C --
+ * get_loopfilter_strength() (src/vp8enc.cpp:96-127: out4[0] = "reductor" from the mean luma, out4[1] = sharpness from
+ * the mean squared difference of every interior pixel to the average of its eight neighbours) and the two chroma
+ * differences scene_change() thresholds (src/vp8enc.cpp:265-285: out4[2] = mean |last_U - current_U|, out4[3] the same
+ * for V, over the padded planes).  Same `int` arithmetic as the reference, wrap-around of its accumulators included.
+ * cur_y may be NULL (chroma only) and so may the four chroma planes (luma only).  scratch4: four 64-bit words of
+ * device memory, out4: four int32 of device memory.  Not reachable from the unmodified host. */
+int vp8b200_frame_statistics(void *stream, const uint8_t *cur_y, int width, int height, const uint8_t *last_u,
+                             const uint8_t *cur_u, const uint8_t *last_v, const uint8_t *cur_v,
+                             unsigned long long *scratch4, int32_t *out4);
 
 /* ------------------------------------------------------------------------------------------
  * Frame-level engine: one object owns every per-frame device buffer the reference creates in

@@ -674,6 +674,46 @@ void vp8o_loop_filter_frame(uint8_t *frame, const int32_t *MB_segment_ids, const
     }
 }
 
+/* ---- the host's per-frame reductions ------------------------------------------------------------
+ * get_loopfilter_strength(), src/vp8enc.cpp:96-127, and the chroma differences of scene_change(),
+ * src/vp8enc.cpp:265-285.  The reference accumulates in `int`; at the largest frame sizes those sums pass 2^31.
+ * They are formed here in unsigned 32-bit arithmetic (what the compiled reference does) and read back as signed.
+ * out4 = { reductor, sharpness, Udiff, Vdiff }. */
+void vp8o_frame_statistics(const uint8_t *cur_y, int width, int height, const uint8_t *last_u, const uint8_t *cur_u,
+                           const uint8_t *last_v, const uint8_t *cur_v, int32_t *out4) {
+    if (cur_y) {
+        const int n = width * height;
+        uint32_t acc = 0;
+        for (int i = 0; i < n; ++i) acc += cur_y[i];
+        int avg = (int)(acc + (uint32_t)(n / 2));
+        avg /= n;
+        out4[0] = avg * 5 / 255 + 3;
+        uint32_t div = 0;
+        for (int i = 1; i < height - 1; ++i)
+            for (int j = 1; j < width - 1; ++j) {
+                const int p = i * width + j;
+                int a = cur_y[p - width - 1] + cur_y[p - width] + cur_y[p - width + 1] + cur_y[p - 1] + cur_y[p + 1] +
+                        cur_y[p + width - 1] + cur_y[p + width] + cur_y[p + width + 1];
+                a /= 8;
+                div += (uint32_t)((cur_y[p] - a) * (cur_y[p] - a));
+            }
+        int d = (int)(div + (uint32_t)((height - 1) * (width - 1) / 2));
+        d /= (height - 1) * (width - 1);
+        const int sh = d / 8;
+        out4[1] = sh > 7 ? 7 : sh;
+    }
+    if (last_u && cur_u && last_v && cur_v) {
+        const int n = (width / 2) * (height / 2);
+        uint32_t du = 0, dv = 0;
+        for (int i = 0; i < n; ++i) {
+            du += (uint32_t)abs((int)last_u[i] - (int)cur_u[i]);
+            dv += (uint32_t)abs((int)last_v[i] - (int)cur_v[i]);
+        }
+        out4[2] = (int)du / n;
+        out4[3] = (int)dv / n;
+    }
+}
+
 /* ---------------------------------------------------------------------------------------- */
 struct vp8o_frame_ctx {
     int w, h, mb_count;

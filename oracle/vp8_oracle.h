@@ -121,6 +121,11 @@ void vp8o_loop_filter_planes(uint8_t *y, uint8_t *u, uint8_t *v, const int16_t *
                              const int32_t *MB_parts, const int32_t *MB_segment_id, const vp8o_segment_data *SD,
                              int32_t *MB_non_zero_coeffs, int width, int height);
 
+/* src/vp8enc.cpp:96-127 (get_loopfilter_strength) and :265-285 (the differences scene_change() thresholds);
+ * out4 = { reductor, sharpness, Udiff, Vdiff }; either the luma plane or the chroma planes may be NULL */
+void vp8o_frame_statistics(const uint8_t *cur_y, int width, int height, const uint8_t *last_u, const uint8_t *cur_u,
+                           const uint8_t *last_v, const uint8_t *cur_v, int32_t *out4);
+
 /* test aid (tests/test_decoder_pin.py): which = 0 -> blocks whose predictor Q5 changed (x, y, plane), which = 1 ->
  * loop-filter edges that chained an unclamped value, Q7 (x, y, macroblock size).  Returns the number of events
  * since the last reset; at most `cap` positions are copied. */

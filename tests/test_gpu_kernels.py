@@ -8,7 +8,9 @@ import ctypes
 import numpy as np
 import pytest
 
-from _libs import P, make_segment_data, oracle
+import os
+
+from _libs import P, ROOT, make_segment_data, oracle
 
 torch = pytest.importorskip("torch")
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a CUDA device")]
@@ -318,3 +320,15 @@ def test_loop_filter_three_planes_1080p(eng):
     dy, du, dv = dev(y), dev(u), dev(v)
     eng.loop_filter_planes(dy, du, dv, dev(seg), dev(mask), dev(sd), W, H)
     assert np.array_equal(ya, host(dy)) and np.array_equal(ua, host(du)) and np.array_equal(va, host(dv))
+
+
+@pytest.mark.parametrize("w,h", [(352, 288), (208, 176), (1920, 1088)])
+def test_luma_search_2step_tma_variant_identical(w, h):
+    """the TMA-staged experiment kernel (vp8b200_experiment_search_2step_tma: box copies out of a replicate-padded
+    plane) finds the same vectors and metrics as the production kernel, frame edges included"""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import me_tma_ab
+    r = me_tma_ab.ab(w, h, reps=1)
+    assert r["identical"], r
+    assert r["nonzero_vectors"] > 0

@@ -15,6 +15,8 @@
 //   * in the quarter-pel kernel the horizontal six-tap pass is computed once per x-phase
 //     (5 variants) and shared by the 5 y-phases, instead of once per candidate; a thread owns one
 //     x-phase of one 4x4 sub-block and walks its five y-phases with the lines held in registers.
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace vp8 {
@@ -296,14 +298,32 @@ __device__ __forceinline__ void s2_residual(const uint32_t (&tl)[4][3], int firs
         }
 }
 
-__global__ void __launch_bounds__(S2_THREADS, VP8_S2_MINCTAS)
-k_luma_search_2step(const uint8_t *__restrict__ cur, Search2Refs refs, int width, int height, int nblocks) {
+// Staging of the reference windows, two ways (the north star names the second, so it is measured):
+//   WindowsByLoads   one window line per thread: five aligned word loads + funnel shifts (the production path)
+//   WindowsByTMA     one 2-D box copy (cp.async.bulk.tensor, 32 x 14 bytes from the 16-byte boundary below the window:
+//                    a box cannot start at an arbitrary byte) per block out of a replicate-padded copy of the
+//                    reference plane, completion through an mbarrier
+struct WindowsByLoads {};
+struct WindowsByTMA {
+    CUtensorMap map;  // the padded plane, uint8, box 32 x 14
+    int pad;          // replicated border on every side
+};
+template <class Staging>
+__device__ __forceinline__ void luma_search_2step_body(const uint8_t *__restrict__ cur, const Search2Refs &refs, int width,
+                                                       int height, int nblocks, const Staging &staging) {
+    constexpr bool kTMA = sizeof(Staging) > 1;
+    // words per window line.  A TMA box has to start on a 16-byte boundary of the plane, so the 14 bytes a window line
+    // needs arrive somewhere inside a dense 32-byte box line and the horizontal pass shifts them out itself
+    constexpr int WIN_PITCH = kTMA ? 8 : 5;
     const int ri = blockIdx.y;
     const uint8_t *__restrict__ ref = ri == 0 ? refs.ref[0] : ri == 1 ? refs.ref[1] : refs.ref[2];
     const short2 *__restrict__ net = ri == 0 ? refs.net[0] : ri == 1 ? refs.net[1] : refs.net[2];
     short2 *__restrict__ ref_net = ri == 0 ? refs.ref_net[0] : ri == 1 ? refs.ref_net[1] : refs.ref_net[2];
     int *__restrict__ ref_Bdiff = ri == 0 ? refs.ref_Bdiff[0] : ri == 1 ? refs.ref_Bdiff[1] : refs.ref_Bdiff[2];
-    __shared__ uint32_t s_win[S2_BLOCKS][14][5];   // ref pixels rows/cols [base-3, base+11), clamp-to-edge; 20-byte lines
+    // ref pixels rows/cols [base-3, base+11), clamp-to-edge; 20-byte lines (TMA: 32-byte box lines, 512 bytes per block)
+    __shared__ __align__(128) uint32_t s_win[S2_BLOCKS][kTMA ? 16 : 14][WIN_PITCH];
+    __shared__ __align__(8) unsigned long long s_mbar;
+    __shared__ int s_off[S2_BLOCKS];  // TMA: byte offset of the window inside its box lines (0..15)
     // horizontally filtered + saturated lines, TRANSPOSED: [x-phase][column][line], 16 lines (14 used) per column
     __shared__ __align__(4) uint8_t s_h[S2_BLOCKS][5][8][16];
     __shared__ uint32_t s_cur[S2_BLOCKS][8][2];
@@ -329,26 +349,60 @@ k_luma_search_2step(const uint8_t *__restrict__ cur, Search2Refs refs, int width
     };
     if (tid < S2_BLOCKS) s_key[tid] = 0xffffffffu;
 
+    if constexpr (kTMA) {
+        // one thread per block: geometry, then the box copy; everybody waits on the mbarrier below
+        const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&s_mbar);
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(1));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (tid < 32) {
+            // lanes 0..7 work out where their block's window lies; ONE lane issues the copies (the TMA instruction
+            // takes its operands from uniform registers: a warp cannot issue eight different ones at once)
+            int x0 = 0, y0 = 0;
+            if (tid < S2_BLOCKS) {
+                const int4 g = block_geometry(tid);
+                s_geo[tid] = g;
+                x0 = g.x + (g.z >> 2) - 3 + staging.pad;
+                y0 = g.y + (g.w >> 2) - 3 + staging.pad;
+                s_off[tid] = x0 & 15;
+                x0 &= ~15;
+            }
+            if (tid == 0)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(S2_BLOCKS * 14 * 32) : "memory");
+#pragma unroll 1
+            for (int b = 0; b < S2_BLOCKS; ++b) {
+                const int bx0 = __shfl_sync(0xffffffffu, x0, b), by0 = __shfl_sync(0xffffffffu, y0, b);
+                if (tid == 0) {
+                    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&s_win[b][0][0]);
+                    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                                 ::"r"(dst), "l"(&staging.map), "r"(bx0), "r"(by0), "r"(mbar) : "memory");
+                }
+            }
+        }
+    } else {
     // one window line per thread: five aligned words cover its 14 pixels wherever they start; lines that
-    // touch the left/right frame edge (or an unaligned plane) take the clamped byte path
-    for (int i = tid; i < S2_BLOCKS * 14; i += S2_THREADS) {
-        const int b = i / 14, r = i % 14;
-        const int4 g = block_geometry(b);
-        if (r == 0) s_geo[b] = g;
-        const int x0 = g.x + (g.z >> 2) - 3, y = clampi(g.y + (g.w >> 2) - 3 + r, 0, height - 1);
-        const uint8_t *line = ref + (size_t)y * width;
-        const int xa = x0 & ~3;
-        if (x0 >= 0 && xa + 20 <= width && ((reinterpret_cast<uintptr_t>(ref) | (unsigned)width) & 3) == 0) {
-            const uint32_t *wp = reinterpret_cast<const uint32_t *>(line + xa);
-            const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2), w3 = __ldg(wp + 3), w4 = __ldg(wp + 4);
-            const int sh = 8 * (x0 & 3);
-            s_win[b][r][0] = __funnelshift_r(w0, w1, sh);
-            s_win[b][r][1] = __funnelshift_r(w1, w2, sh);
-            s_win[b][r][2] = __funnelshift_r(w2, w3, sh);
-            s_win[b][r][3] = __funnelshift_r(w3, w4, sh);
-        } else {
-            uint8_t *dst = reinterpret_cast<uint8_t *>(&s_win[b][r][0]);
-            for (int c = 0; c < 14; ++c) dst[c] = __ldg(line + clampi(x0 + c, 0, width - 1));
+        // touch the left/right frame edge (or an unaligned plane) take the clamped byte path
+        for (int i = tid; i < S2_BLOCKS * 14; i += S2_THREADS) {
+            const int b = i / 14, r = i % 14;
+            const int4 g = block_geometry(b);
+            if (r == 0) s_geo[b] = g;
+            const int x0 = g.x + (g.z >> 2) - 3, y = clampi(g.y + (g.w >> 2) - 3 + r, 0, height - 1);
+            const uint8_t *line = ref + (size_t)y * width;
+            const int xa = x0 & ~3;
+            if (x0 >= 0 && xa + 20 <= width && ((reinterpret_cast<uintptr_t>(ref) | (unsigned)width) & 3) == 0) {
+                const uint32_t *wp = reinterpret_cast<const uint32_t *>(line + xa);
+                const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2), w3 = __ldg(wp + 3), w4 = __ldg(wp + 4);
+                const int sh = 8 * (x0 & 3);
+                s_win[b][r][0] = __funnelshift_r(w0, w1, sh);
+                s_win[b][r][1] = __funnelshift_r(w1, w2, sh);
+                s_win[b][r][2] = __funnelshift_r(w2, w3, sh);
+                s_win[b][r][3] = __funnelshift_r(w3, w4, sh);
+            } else {
+                uint8_t *dst = reinterpret_cast<uint8_t *>(&s_win[b][r][0]);
+                for (int c = 0; c < 14; ++c) dst[c] = __ldg(line + clampi(x0 + c, 0, width - 1));
+            }
         }
     }
     // (S2_THREADS - S2_BLOCKS * 16 = 32 < 112: going backwards spreads the two jobs over the threads)
@@ -360,6 +414,13 @@ k_luma_search_2step(const uint8_t *__restrict__ cur, Search2Refs refs, int width
         s_cur[b][r][h] = __ldg(reinterpret_cast<const uint32_t *>(cur + (size_t)(gy + r) * width + gx) + h);
         s_zero[b][r][h] = __ldg(reinterpret_cast<const uint32_t *>(ref + (size_t)(gy + r) * width + gx) + h);
     }
+    if constexpr (kTMA) {
+        const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&s_mbar);
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(mbar) : "memory");
+    }
     __syncthreads();
 
     // horizontal pass: 5 x-variants x 14 rows x 8 columns per block.  An item is (block, row, half line): its
@@ -370,7 +431,18 @@ k_luma_search_2step(const uint8_t *__restrict__ cur, Search2Refs refs, int width
     // -128<s<0, both give 0.
     for (int i = tid; i < S2_BLOCKS * 28; i += S2_THREADS) {
         const int b = i / 28, q = i % 28, r = q >> 1, h = q & 1;
-        const uint32_t wa = s_win[b][r][h], wb = s_win[b][r][h + 1], wc = s_win[b][r][h + 2];
+        uint32_t wa, wb, wc;
+        if constexpr (kTMA) {
+            const int o = s_off[b], q = (o >> 2) + h, sh = 8 * (o & 3);
+            const uint32_t t0 = s_win[b][r][q], t1 = s_win[b][r][q + 1], t2 = s_win[b][r][q + 2], t3 = s_win[b][r][q + 3];
+            wa = __funnelshift_r(t0, t1, sh);
+            wb = __funnelshift_r(t1, t2, sh);
+            wc = __funnelshift_r(t2, t3, sh);
+        } else {
+            wa = s_win[b][r][h];
+            wb = s_win[b][r][h + 1];
+            wc = s_win[b][r][h + 2];
+        }
         const uint32_t lo[5] = {wa, __funnelshift_r(wa, wb, 8), __funnelshift_r(wa, wb, 16), __funnelshift_r(wa, wb, 24), wb};
         const uint32_t hi[5] = {wb, __funnelshift_r(wb, wc, 8), __funnelshift_r(wb, wc, 16), __funnelshift_r(wb, wc, 24), wc};
         uint8_t *dst = &s_h[b][0][4 * h][r];  // + 128 per variant, + 16 per column
@@ -477,6 +549,29 @@ k_luma_search_2step(const uint8_t *__restrict__ cur, Search2Refs refs, int width
     }
 }
 
+__global__ void __launch_bounds__(S2_THREADS, VP8_S2_MINCTAS)
+k_luma_search_2step(const uint8_t *__restrict__ cur, Search2Refs refs, int width, int height, int nblocks) {
+    luma_search_2step_body(cur, refs, width, height, nblocks, WindowsByLoads());
+}
+__global__ void __launch_bounds__(S2_THREADS, VP8_S2_MINCTAS)
+k_luma_search_2step_tma(const uint8_t *__restrict__ cur, Search2Refs refs, int width, int height, int nblocks,
+                        const __grid_constant__ WindowsByTMA staging) {
+    luma_search_2step_body(cur, refs, width, height, nblocks, staging);
+}
+
+// replicate-padded copy of a plane (the TMA variant reads its windows from it: a box copy fills what lies outside the
+// tensor with zeros, the search wants the edge pixel; `pad` >= 4 covers every candidate that can win)
+__global__ void k_pad_replicate(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int width, int height, int pad) {
+    const int pw = width + 2 * pad, ph = height + 2 * pad;
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
+    if (x4 >= pw || y >= ph) return;
+    const uint8_t *line = src + (size_t)clampi(y - pad, 0, height - 1) * width;
+    uint32_t w = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w |= (uint32_t)line[clampi(x4 + k - pad, 0, width - 1)] << (8 * k);
+    *reinterpret_cast<uint32_t *>(dst + (size_t)y * pw + x4) = w;
+}
+
 // ------------------------------------------------------------------------------------------
 __global__ void k_select_reference(const short2 *__restrict__ last_net, const short2 *__restrict__ gold_net,
                                    const short2 *__restrict__ alt_net, const int *__restrict__ last_d,
@@ -574,6 +669,46 @@ extern "C" int vp8b200_luma_search_2step_multi(void *stream, const uint8_t *cur,
     }
     dim3 grid((nblocks + S2_BLOCKS - 1) / S2_BLOCKS, nrefs);
     k_luma_search_2step<<<grid, S2_THREADS, 0, (cudaStream_t)stream>>>(cur, r, width, height, nblocks);
+    VP8_LAUNCH_CHECK();
+}
+
+// ---- experiment: luma_search_2step with TMA-staged windows (see WindowsByTMA) ---------------------------------
+// Pads `ref` (replicated border of 16 pixels) into `padded` (caller-provided, (width+32)*(height+32) bytes), builds
+// the tensor map and runs the search.  Results are bit-identical to vp8b200_luma_search_2step (tested); the point is
+// the A/B timing of the two staging methods (tools/me_tma_ab.py).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+extern "C" int vp8b200_experiment_search_2step_tma(void *stream, const uint8_t *cur, const uint8_t *ref, uint8_t *padded,
+                                                   const int16_t *net, int16_t *ref_net, int32_t *ref_Bdiff, int width,
+                                                   int height, int pad_only) {
+    const int pad = 16;
+    const int nblocks = width * height / 64;
+    if (nblocks <= 0 || (width & 15)) return -(int)cudaErrorInvalidValue;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int pw = width + 2 * pad, ph = height + 2 * pad;
+    k_pad_replicate<<<dim3((pw / 4 + 127) / 128, ph), 128, 0, st>>>(ref, padded, width, height, pad);
+    if (pad_only) VP8_LAUNCH_CHECK();
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        cudaDriverEntryPointQueryResult q;
+        void *fn = nullptr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return -1;
+        encode = (EncodeTiledFn)fn;
+    }
+    WindowsByTMA staging;
+    staging.pad = pad;
+    const cuuint64_t dims[2] = {(cuuint64_t)pw, (cuuint64_t)ph}, strides[1] = {(cuuint64_t)pw};
+    const cuuint32_t box[2] = {32, 14}, estr[2] = {1, 1};
+    if (encode(&staging.map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, padded, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return -2;
+    Search2Refs r = {};
+    r.ref[0] = ref;  // (the co-located block of the zero-vector candidate still comes from the plane itself)
+    r.net[0] = (const short2 *)net;
+    r.ref_net[0] = (short2 *)ref_net;
+    r.ref_Bdiff[0] = ref_Bdiff;
+    k_luma_search_2step_tma<<<dim3((nblocks + S2_BLOCKS - 1) / S2_BLOCKS, 1), S2_THREADS, 0, st>>>(cur, r, width, height, nblocks, staging);
     VP8_LAUNCH_CHECK();
 }
 

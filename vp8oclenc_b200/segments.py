@@ -243,7 +243,11 @@ class EncoderProcess:
         # habits (csrc/cl_shim.cu, VP8B200_HOST_PROFILE); env_extra can still override every single one of them
         env.setdefault("VP8B200_HOST_PROFILE", "reference")
         if device is not None:
-            env["VP8B200_DEVICE"] = str(device)
+            # one visible GPU per instance: a CUDA process that sees all eight of a node spends seconds initialising the
+            # seven it will never use.  `device` counts within what this process may see.
+            vis = [v for v in env.get("CUDA_VISIBLE_DEVICES", "").split(",") if v != ""]
+            env["CUDA_VISIBLE_DEVICES"] = vis[device] if device < len(vis) else str(device)
+            env["VP8B200_DEVICE"] = "0"
         env.update(env_extra or {})
         cmd = [host_bin, "-i", y4m, "-o", ivf] + [str(a) for a in args] + (["-print-info"] if print_info else [])
         import shutil
@@ -299,14 +303,37 @@ def encode_clip_segment_parallel(y4m, args, gop, work_dir, rank=0, world=1, devi
         w, h = _y4m_geometry(header)
         fsz = 6 + w * h * 3 // 2
         base = f.tell()
-        seg_paths = {}
-        for i in mine:
-            f.seek(base + fsz * keys[i])
-            blob = f.read(fsz * (keys[i + 1] - keys[i])) if i + 1 < len(keys) else f.read()
-            seg_paths[i] = os.path.join(work_dir, "seg%04d.y4m" % i)
-            with open(seg_paths[i], "wb") as g:
-                g.write(header)
-                g.write(blob)
+    total_frames = (os.path.getsize(y4m) - base) // fsz
+    seg_paths = {i: os.path.join(work_dir, "seg%04d.y4m" % i) for i in mine}
+
+    def cut(i):  # (in-kernel copy where the file system offers it; the pieces are written concurrently)
+        start = base + fsz * keys[i]
+        count = fsz * ((keys[i + 1] if i + 1 < len(keys) else total_frames) - keys[i])
+        with open(y4m, "rb") as src, open(seg_paths[i], "wb") as dst:
+            dst.write(header)
+            dst.flush()
+            done = 0
+            try:
+                while done < count:
+                    n = os.copy_file_range(src.fileno(), dst.fileno(), min(count - done, 1 << 30), start + done, len(header) + done)
+                    if n <= 0:
+                        break
+                    done += n
+            except (OSError, AttributeError):
+                pass
+            if done < count:
+                src.seek(start + done)
+                dst.seek(len(header) + done)
+                while done < count:
+                    blob = src.read(min(count - done, 64 << 20))
+                    if not blob:
+                        break
+                    dst.write(blob)
+                    done += len(blob)
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=max(1, min(16, len(mine)))) as pool:
+        list(pool.map(cut, mine))
     order = sorted(seg_paths)
     ivfs, procs = _encode_segments([seg_paths[i] for i in order], work_dir, args, (device,), per_device, lib_dir, host_bin,
                                    mps_env or {}, names=["seg%04d" % i for i in order])
