@@ -172,6 +172,21 @@ int vp8b200_loop_filter_planes(void *stream, uint8_t *y, uint8_t *u, uint8_t *v,
  * destroying it (vp8b200_engine_destroy does so for its own). */
 void vp8b200_loop_filter_release(void *stream);
 
+/* the intra (key-frame) path the reference host runs in plain C on one thread -- intra_transform() /
+ * predict_and_transform_mb(), src/intra_part.h:37-741, 1089-1128 -- for a whole frame: every macroblock B_PRED (the
+ * best of the ten 4x4 sub-block modes by the reference's weight()), chroma TM_PRED, forward DCT, quantise, dequantise,
+ * inverse DCT, reconstruction, in the reference's raster dependency order (a wavefront over macroblocks on the GPU).
+ * Planes are macroblock-padded (width, height multiples of 16).  Outputs as intra_transform() leaves them: rec_* the
+ * unfiltered reconstruction, MB 25 x 16 int16 per macroblock in zig-zag order (block 24 untouched), modes 16 int32
+ * per macroblock (frames.e_data[].mode), MB_parts = are4x4, MB_segment_id = intra_segment.  The four quantisers are
+ * frames.y_dc_q / y_ac_q / uv_dc_q / uv_ac_q of the intra segment (src/vp8enc.cpp:160-181).  scratch: device memory
+ * of vp8b200_intra_frame_scratch_bytes().  Not reachable from the unmodified host. */
+size_t vp8b200_intra_frame_scratch_bytes(int width, int height);
+int vp8b200_intra_frame(void *stream, const uint8_t *cur_y, const uint8_t *cur_u, const uint8_t *cur_v, uint8_t *rec_y,
+                        uint8_t *rec_u, uint8_t *rec_v, int16_t *MB, int32_t *modes, int32_t *MB_parts,
+                        int32_t *MB_segment_id, int width, int height, int y_dc_q, int y_ac_q, int uv_dc_q, int uv_ac_q,
+                        void *scratch);
+
 /* the two O(N) reductions the reference host runs on every frame in plain C --
  * get_loopfilter_strength() (src/vp8enc.cpp:96-127: out4[0] = "reductor" from the mean luma, out4[1] = sharpness from
  * the mean squared difference of every interior pixel to the average of its eight neighbours) and the two chroma

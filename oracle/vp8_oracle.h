@@ -126,6 +126,12 @@ void vp8o_loop_filter_planes(uint8_t *y, uint8_t *u, uint8_t *v, const int16_t *
 void vp8o_frame_statistics(const uint8_t *cur_y, int width, int height, const uint8_t *last_u, const uint8_t *cur_u,
                            const uint8_t *last_v, const uint8_t *cur_v, int32_t *out4);
 
+/* the intra (key-frame) path of the reference host, src/intra_part.h:37-741, 1089-1128 (vp8_oracle_intra.c):
+ * quants = { y_dc_q, y_ac_q, uv_dc_q, uv_ac_q }; MB 25 x 16 int16 per macroblock (zig-zag), modes 16 per macroblock */
+void vp8o_intra_frame(int width, int height, const uint8_t *cur_y, const uint8_t *cur_u, const uint8_t *cur_v,
+                      uint8_t *rec_y, uint8_t *rec_u, uint8_t *rec_v, int16_t *MB, int32_t *modes, int32_t *parts,
+                      int32_t *segment_id, const int32_t *quants);
+
 /* test aid (tests/test_decoder_pin.py): which = 0 -> blocks whose predictor Q5 changed (x, y, plane), which = 1 ->
  * loop-filter edges that chained an unclamped value, Q7 (x, y, macroblock size).  Returns the number of events
  * since the last reset; at most `cap` positions are copied. */

@@ -68,11 +68,20 @@ def oracle():
     if _oracle is None:
         so = os.path.join(ORACLE_DIR, "liboracle.so")
         src = os.path.join(ORACLE_DIR, "vp8_oracle.c")
-        if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        srcs = [src, os.path.join(ORACLE_DIR, "vp8_oracle_intra.c"), os.path.join(ORACLE_DIR, "vp8_oracle.h")]
+        if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(x) for x in srcs):
             subprocess.check_call(["make", "-C", ORACLE_DIR, "liboracle.so"], stdout=subprocess.DEVNULL)
         _oracle = ctypes.CDLL(so)
         _oracle.vp8o_ctx_create.restype = ctypes.c_void_p
     return _oracle
+
+
+def ref_intra():
+    """ctypes handle of oracle/_ref/libref_intra.so (the reference's own intra path, oracle/ref_intra.cpp) or None"""
+    so = os.path.join(ORACLE_DIR, "_ref", "libref_intra.so")
+    if not os.path.exists(so) and os.path.isdir("/root/reference/src"):
+        subprocess.call(["make", "-C", ORACLE_DIR, "ref"], stdout=subprocess.DEVNULL)
+    return ctypes.CDLL(so) if os.path.exists(so) else None
 
 
 def ref():

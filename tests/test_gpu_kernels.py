@@ -332,3 +332,49 @@ def test_luma_search_2step_tma_variant_identical(w, h):
     r = me_tma_ab.ab(w, h, reps=1)
     assert r["identical"], r
     assert r["nonzero_vectors"] > 0
+
+
+@pytest.mark.parametrize("w,h,q,seed", [(176, 144, (19, 24, 7, 10), 0), (352, 288, (8, 6, 4, 4), 0), (64, 48, (157, 284, 132, 284), 0),
+                                        (208, 176, (4, 4, 4, 4), 0), (1920, 1088, (19, 24, 7, 10), 0), (96, 80, (7, 6, 6, 9), 5),
+                                        (16, 16, (12, 12, 12, 12), 6), (32, 160, (5, 9, 9, 5), 7)])
+def test_intra_frame_vs_oracle(w, h, q, seed):
+    """the key-frame path (B_PRED mode decision, TM chroma, transform, quantise, reconstruct) as a
+    wavefront kernel against the oracle's restatement of src/intra_part.h (itself pinned against the reference's own
+    code, tests/test_intra_oracle.py): modes, coefficients, all three reconstructed planes"""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_y4m
+    from vp8oclenc_b200 import host as eng
+    if seed == 0:
+        y, u, v = (np.ascontiguousarray(p).reshape(-1) for p in gen_y4m.Clip(max(w, 128), max(h, 128)).frame(3))
+        if w < 128 or h < 128:
+            full = gen_y4m.Clip(max(w, 128), max(h, 128)).frame(3)
+            y = np.ascontiguousarray(full[0][:h, :w]).reshape(-1)
+            u = np.ascontiguousarray(full[1][:h // 2, :w // 2]).reshape(-1)
+            v = np.ascontiguousarray(full[2][:h // 2, :w // 2]).reshape(-1)
+    else:
+        r = rng(seed)
+        yy = r.integers(0, 256, size=(h, w), dtype=np.uint8)
+        yy[: h // 2, : w // 2] = np.where(r.integers(0, 2, size=(h // 2, w // 2)) > 0, 255, 0)
+        y = np.ascontiguousarray(yy).reshape(-1)
+        u = r.integers(0, 256, size=w * h // 4, dtype=np.uint8)
+        v = np.where(r.integers(0, 2, size=w * h // 4) > 0, 250, 3).astype(np.uint8)
+    M = (w // 16) * (h // 16)
+    qa = np.asarray(q, np.int32)
+    ry, ru, rv = np.zeros(w * h, np.uint8), np.zeros(w * h // 4, np.uint8), np.zeros(w * h // 4, np.uint8)
+    mb = np.zeros(M * 400, np.int16)
+    modes, parts, seg = np.zeros(M * 16, np.int32), np.full(M, -1, np.int32), np.full(M, -1, np.int32)
+    oracle().vp8o_intra_frame(w, h, P(y), P(u), P(v), P(ry), P(ru), P(rv), P(mb), P(modes), P(parts), P(seg), P(qa))
+    d = {k: torch.from_numpy(a).cuda() for k, a in dict(y=y, u=u, v=v).items()}
+    g = dict(ry=torch.zeros(w * h, dtype=torch.uint8, device="cuda"), ru=torch.zeros(w * h // 4, dtype=torch.uint8, device="cuda"),
+             rv=torch.zeros(w * h // 4, dtype=torch.uint8, device="cuda"), mb=torch.zeros(M * 400, dtype=torch.int16, device="cuda"),
+             modes=torch.zeros(M * 16, dtype=torch.int32, device="cuda"), parts=torch.full((M,), -1, dtype=torch.int32, device="cuda"),
+             seg=torch.full((M,), -1, dtype=torch.int32, device="cuda"))
+    keep = eng.intra_frame(d["y"], d["u"], d["v"], g["ry"], g["ru"], g["rv"], g["mb"], g["modes"], g["parts"], g["seg"], w, h, q)
+    torch.cuda.synchronize()
+    del keep
+    assert np.array_equal(g["modes"].cpu().numpy(), modes), "sub-block modes"
+    assert np.array_equal(g["mb"].cpu().numpy().reshape(M, 25, 16)[:, :24], mb.reshape(M, 25, 16)[:, :24]), "coefficients"
+    assert np.array_equal(g["ry"].cpu().numpy(), ry), "luma reconstruction"
+    assert np.array_equal(g["ru"].cpu().numpy(), ru) and np.array_equal(g["rv"].cpu().numpy(), rv), "chroma reconstruction"
+    assert np.array_equal(g["parts"].cpu().numpy(), parts) and np.array_equal(g["seg"].cpu().numpy(), seg)

@@ -23,7 +23,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-ccbin", HOST_CXX, "-I", INC, "-I", CSRC]
 
 ENGINE_SRCS = ["me_kernels.cu", "transform_kernels.cu", "loopfilter_kernels.cu", "capi_misc.cu", "engine.cu", "mb_fused_kernel.cu",
-               "entropy_kernels.cu", "host_reductions.cu"]
+               "entropy_kernels.cu", "host_reductions.cu", "intra_kernels.cu"]
 # the float SSIM must not be contracted into FMAs the reference source does not have
 EXTRA = {"transform_kernels.cu": ["-fmad=false"], "mb_fused_kernel.cu": ["-fmad=false"]}
 SHIM_SRCS = ["cl_shim.cu", "entropy_host.cpp"]

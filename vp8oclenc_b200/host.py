@@ -164,6 +164,19 @@ def entropy_boolcode(tokens, part_info, coeff_probs, output, partition_sizes, nu
     return scratch  # (keep it alive until the stream has run)
 
 
+def intra_frame(cur_y, cur_u, cur_v, rec_y, rec_u, rec_v, MB, modes, MB_parts, MB_segment_id, width, height, quants):
+    """intra_transform() / predict_and_transform_mb() of the reference host for a whole frame (src/intra_part.h:37-741,
+    1089-1128): B_PRED luma, TM_PRED chroma, transform, quantise, reconstruct.  quants = (y_dc_q, y_ac_q, uv_dc_q, uv_ac_q)"""
+    import torch
+    L = lib()
+    L.vp8b200_intra_frame_scratch_bytes.restype = ctypes.c_size_t
+    scratch = torch.empty(L.vp8b200_intra_frame_scratch_bytes(width, height), dtype=torch.uint8, device=cur_y.device)
+    _check(L.vp8b200_intra_frame(_stream(), _p(cur_y), _p(cur_u), _p(cur_v), _p(rec_y), _p(rec_u), _p(rec_v), _p(MB), _p(modes),
+                                 _p(MB_parts), _p(MB_segment_id), width, height, int(quants[0]), int(quants[1]), int(quants[2]),
+                                 int(quants[3]), _p(scratch)), "intra_frame")
+    return scratch  # (keep it alive until the stream has run)
+
+
 # ---------------------------------------------------------------------------------------------
 class Engine:
     """Frame-level engine (vp8b200_engine_* of include/vp8b200.h): the sequence of
