@@ -317,7 +317,61 @@ def kernel_lines(w, h, pipe, units):
                                      "us_per_dependent_stage": 1000.0 * t["loop_filter"] / stages,
                                      "note": "dependency-bound wavefront of mb_w+2(mb_h-1) macroblock stages, not bandwidth-bound"}
     out["frame_stage_ms"] = t
+    out["key_frame"] = key_frame_line(w, h, pipe)
     return out, int_peak
+
+
+def key_frame_line(w, h, pipe):
+    """one key frame -- intra_transform() + loop filter -- on the engine (vp8b200_engine_key_frame, CUDA
+    events on the engine's stream) next to the reference's own intra code (src/intra_part.h compiled in place,
+    oracle/_ref/libref_intra.so: the cpu_baseline of this stage, one host thread as in the reference)"""
+    import numpy as np
+    import torch
+    from vp8oclenc_b200.hostlogic import intra_quants, make_segment_data
+    ww, wh = padded(w, h)
+    e = pipe["engines"][0]
+    ext = torch.cuda.ExternalStream(e.stream)
+    y, u, v = pipe["frames"][0]
+    sdk = make_segment_data(QI, key=True)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    reps, t_intra, t_lf = 5, 0.0, 0.0
+    for i in range(reps + 1):
+        with torch.cuda.stream(ext):
+            pipe["flush"].fill_(4)
+            ev[0].record(ext)
+        e.key_frame(y, u, v, sdk)
+        with torch.cuda.stream(ext):
+            ev[1].record(ext)
+        e.loop_filter(sdk)
+        with torch.cuda.stream(ext):
+            ev[2].record(ext)
+        e.synchronize()
+        if i:  # (first pass: warm-up)
+            t_intra += ev[0].elapsed_time(ev[1])
+            t_lf += ev[1].elapsed_time(ev[2])
+    line = {"gpu_intra_ms": t_intra / reps, "gpu_loop_filter_ms": t_lf / reps, "dependent_stages": ww // 16 + 2 * (wh // 16 - 1),
+            "us_per_dependent_stage": 1000.0 * t_intra / reps / (ww // 16 + 2 * (wh // 16 - 1)),
+            "what": "vp8b200_engine_key_frame + vp8b200_engine_loop_filter: B_PRED mode decision over the ten sub-block modes, TM chroma, "
+                    "transform, quantise, reconstruct for every macroblock (wavefront over macroblocks), then the normal loop filter"}
+    so = os.path.join(ROOT, "oracle", "_ref", "libref_intra.so")
+    if os.path.exists(so):
+        lib = ctypes.CDLL(so)
+        M = (ww // 16) * (wh // 16)
+        hy, hu, hv = (np.ascontiguousarray(t.cpu().numpy()) for t in (y, u, v))
+        ry, ru, rv = np.zeros(ww * wh, np.uint8), np.zeros(ww * wh // 4, np.uint8), np.zeros(ww * wh // 4, np.uint8)
+        mb, modes = np.zeros(M * 400, np.int16), np.zeros(M * 16, np.int32)
+        parts, seg = np.zeros(M, np.int32), np.zeros(M, np.int32)
+        q = np.asarray(intra_quants(sdk), np.int32)
+        P = lambda a: ctypes.c_void_p(a.ctypes.data)  # noqa: E731
+        best = None
+        for _ in range(2):
+            t0 = time.perf_counter()
+            lib.vp8ref_intra_frame(ww, wh, P(hy), P(hu), P(hv), P(ry), P(ru), P(rv), P(mb), P(modes), P(parts), P(seg), P(q))
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        line["reference_host_intra_ms"] = 1000.0 * best
+        line["reference_kind"] = "reference (src/intra_part.h compiled in place, one host thread as in the reference)"
+    return line
 
 
 # ------------------------------------------------------------------------------------------------

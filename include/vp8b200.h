@@ -228,6 +228,13 @@ int vp8b200_engine_inter_frame(vp8b200_engine *e, const uint8_t *cur_y, const ui
                                const vp8b200_segment_data *SD_host, float SSIM_target, int prev_is_golden,
                                int prev_is_altref, int altref_differs_from_golden);
 
+/* One key frame with the current frame resident in device memory: intra_transform() (src/intra_part.h:1089-1128) on
+ * the GPU (vp8b200_intra_frame) into the engine's coefficient, mode (VP8B200_BUF_INTRA_MODES), parts, segment-id and
+ * reconstruction buffers; the quantisers are those of segment 0 of SD_host as prepare_segments_data() derives them on
+ * the host (src/vp8enc.cpp:160-181).  Follow with vp8b200_engine_loop_filter(e, SD_host). */
+int vp8b200_engine_key_frame(vp8b200_engine *e, const uint8_t *cur_y, const uint8_t *cur_u, const uint8_t *cur_v,
+                             const vp8b200_segment_data *SD_host);
+
 /* Filter mask + normal loop filter of the three reconstruction planes in place (they then are
  * the next frame's LAST). */
 int vp8b200_engine_loop_filter(vp8b200_engine *e, const vp8b200_segment_data *SD_host);
@@ -248,7 +255,7 @@ int vp8b200_engine_encode_frame_host(vp8b200_engine *e, const uint8_t *cur_y, co
 enum {
     VP8B200_BUF_COEFFS = 0, VP8B200_BUF_VECTORS, VP8B200_BUF_PARTS, VP8B200_BUF_REFERENCE_FRAME,
     VP8B200_BUF_SEGMENT_ID, VP8B200_BUF_SSIM, VP8B200_BUF_NON_ZERO, VP8B200_BUF_RECON_Y, VP8B200_BUF_RECON_U,
-    VP8B200_BUF_RECON_V, VP8B200_BUF_COUNT
+    VP8B200_BUF_RECON_V, VP8B200_BUF_INTRA_MODES, VP8B200_BUF_COUNT
 };
 void *vp8b200_engine_buffer(vp8b200_engine *e, int which);
 /* number of kernels the last inter_frame + loop_filter launched */

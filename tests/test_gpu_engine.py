@@ -18,7 +18,7 @@ pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not torch.cuda.is_available(),
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 
-def run_sequence(w, h, nframes, altref_range, ssim_target, qi, host_api, fused=True):
+def run_sequence(w, h, nframes, altref_range, ssim_target, qi, host_api, fused=True, real_key=False):
     import gen_y4m
     from vp8oclenc_b200 import host as eng
     o = oracle()
@@ -31,9 +31,29 @@ def run_sequence(w, h, nframes, altref_range, ssim_target, qi, host_api, fused=T
     state = _trace.HostState(10 ** 6, altref_range)
     sd = make_segment_data(qi)
     y0, u0, v0 = clip.frame(0)
-    state.next_frame()  # frame 0 is the key frame; its (pretend) reconstruction seeds LAST
-    rec = [y0.copy().reshape(-1), u0.copy().reshape(-1), v0.copy().reshape(-1)]
-    e.set_reconstruction(torch.from_numpy(rec[0]).cuda(), torch.from_numpy(rec[1]).cuda(), torch.from_numpy(rec[2]).cuda())
+    state.next_frame()  # frame 0 is the key frame
+    if real_key:
+        # coded for real: intra_transform() + loop filter with the key frame's segment data, oracle against engine
+        from vp8oclenc_b200.hostlogic import intra_quants
+        sdk = make_segment_data(qi, key=True)
+        src = [np.ascontiguousarray(p).reshape(-1) for p in (y0, u0, v0)]
+        rec = [np.zeros_like(p) for p in src]
+        coef, modes = np.zeros(M * 400, np.int16), np.zeros(M * 16, np.int32)
+        parts, seg, nz = np.zeros(M, np.int32), np.zeros(M, np.int32), np.zeros(M, np.int32)
+        qk = np.asarray(intra_quants(sdk), np.int32)
+        o.vp8o_intra_frame(w, h, P(src[0]), P(src[1]), P(src[2]), P(rec[0]), P(rec[1]), P(rec[2]), P(coef), P(modes), P(parts), P(seg), P(qk))
+        o.vp8o_loop_filter_planes(P(rec[0]), P(rec[1]), P(rec[2]), P(coef), P(parts), P(seg), P(sdk), P(nz), w, h)
+        e.key_frame(*[torch.from_numpy(p).cuda() for p in src], sdk)
+        assert np.array_equal(e.read("intra_modes"), modes), "key frame: sub-block modes"
+        assert np.array_equal(e.read("coeffs").reshape(M, 25, 16)[:, :24], coef.reshape(M, 25, 16)[:, :24]), "key frame: coefficients"
+        e.loop_filter(sdk)
+        assert np.array_equal(e.read("non_zero"), nz), "key frame: non-zero counts"
+        for k, p in zip(("recon_y", "recon_u", "recon_v"), rec):
+            assert np.array_equal(e.read(k), p), "key frame: loop-filtered %s" % k
+    else:
+        # its (pretend) reconstruction seeds LAST
+        rec = [y0.copy().reshape(-1), u0.copy().reshape(-1), v0.copy().reshape(-1)]
+        e.set_reconstruction(torch.from_numpy(rec[0]).cuda(), torch.from_numpy(rec[1]).cuda(), torch.from_numpy(rec[2]).cuda())
     refs_seen = set()
     for i in range(1, nframes):
         st = state.next_frame()
@@ -101,6 +121,17 @@ def test_engine_kernel_per_kernel_sequence(target):
 def test_engine_odd_macroblock_counts():
     """sizes whose macroblock count is not a multiple of the fused kernel's CTA size"""
     run_sequence(208, 176, 4, 3, 0.9, (10, 24, 40, 60), host_api=False)
+
+
+def test_engine_key_frame_then_inter_frames():
+    """a real key frame on the GPU (vp8b200_engine_key_frame: intra + loop filter with the key frame's filter table),
+    then inter frames that reference it -- every array against the oracle"""
+    refs = run_sequence(352, 288, 7, 3, -1.0, (24, 24, 24, 24), host_api=False, real_key=True)
+    assert 0 in refs
+
+
+def test_engine_key_frame_1080p():
+    run_sequence(1920, 1088, 3, 5, -1.0, (24, 24, 24, 24), host_api=False, real_key=True)
 
 
 def test_engine_host_buffers_api():

@@ -21,6 +21,8 @@ struct vp8b200_engine {
     int16_t *res[3];
     int16_t *coeffs, *vectors;
     int32_t *parts, *ref_frame, *seg_id, *nz, *mask;
+    int32_t *modes;       // key frames: the sixteen sub-block modes of every macroblock
+    void *intra_scratch;  // row progress counters of the intra kernel
     float *ssim;
     vp8b200_segment_data *sd_dev;
     vp8b200_segment_data *sd_pinned;  // 8 slots of 4 segments
@@ -111,6 +113,7 @@ extern "C" vp8b200_engine *vp8b200_engine_create(int width, int height, void *st
     ok = ok && dalloc(e->coeffs, (size_t)e->M * 800) && dalloc(e->vectors, (size_t)e->M * 16) &&
          dalloc(e->parts, (size_t)e->M * 4) && dalloc(e->ref_frame, (size_t)e->M * 4) &&
          dalloc(e->seg_id, (size_t)e->M * 4) && dalloc(e->nz, (size_t)e->M * 4) && dalloc(e->mask, (size_t)e->M * 4) &&
+         dalloc(e->modes, (size_t)e->M * 64) && dalloc(e->intra_scratch, vp8b200_intra_frame_scratch_bytes(e->w, e->h)) &&
          dalloc(e->ssim, (size_t)e->M * 4) && dalloc(e->sd_dev, sizeof(vp8b200_segment_data) * 4);
     ok = ok && cudaHostAlloc((void **)&e->sd_pinned, sizeof(vp8b200_segment_data) * 4 * 8, cudaHostAllocDefault) == cudaSuccess;
     for (int i = 0; i < 8 && ok; ++i) ok = cudaEventCreateWithFlags(&e->sd_event[i], cudaEventDisableTiming) == cudaSuccess;
@@ -136,7 +139,7 @@ extern "C" void vp8b200_engine_destroy(vp8b200_engine *e) {
     }
     for (int p = 0; p < 3; ++p) { cudaFree(e->pred[p]); cudaFree(e->res[p]); }
     cudaFree(e->coeffs); cudaFree(e->vectors); cudaFree(e->parts); cudaFree(e->ref_frame); cudaFree(e->seg_id);
-    cudaFree(e->nz); cudaFree(e->mask); cudaFree(e->ssim); cudaFree(e->sd_dev);
+    cudaFree(e->nz); cudaFree(e->mask); cudaFree(e->ssim); cudaFree(e->sd_dev); cudaFree(e->modes); cudaFree(e->intra_scratch);
     for (int i = 0; i <= VP8B200_NUM_STAGES; ++i)
         if (e->stage_ev[i]) cudaEventDestroy(e->stage_ev[i]);
     if (e->sd_pinned) cudaFreeHost(e->sd_pinned);
@@ -162,6 +165,7 @@ extern "C" void *vp8b200_engine_buffer(vp8b200_engine *e, int which) {
         case VP8B200_BUF_RECON_Y: return e->last_pyr[0];
         case VP8B200_BUF_RECON_U: return e->recon_u;
         case VP8B200_BUF_RECON_V: return e->recon_v;
+        case VP8B200_BUF_INTRA_MODES: return e->modes;
         default: return nullptr;
     }
 }
@@ -320,6 +324,43 @@ extern "C" int vp8b200_engine_inter_frame(vp8b200_engine *e, const uint8_t *cur_
     int rc = upload_sd(e, SD_host, 0);
     if (rc) return rc;
     return inter_frame_body(e, cur_y, cur_u, cur_v, SSIM_target, prev_is_golden, prev_is_altref, altref_differs);
+}
+
+// A key frame (intra_transform(), src/intra_part.h:1089-1128, as the host runs it for frame 0, at every GOP boundary and
+// for forced keys): the current frame is coded intra into the engine's coefficient / reconstruction buffers, with the
+// quantisers of segment 0 derived from SD_host the way prepare_segments_data() derives frames.y_dc_q ...
+// (src/vp8enc.cpp:160-181: the host-side table, where uv_dc is capped at 132 but y2 plays no role).  The loop filter
+// (vp8b200_engine_loop_filter with the same SD) then makes the reconstruction the LAST reference; GOLDEN and ALTREF
+// follow on the next inter frame through its prev_is_golden / prev_is_altref flags, as in the reference.
+extern "C" int vp8b200_engine_key_frame(vp8b200_engine *e, const uint8_t *cur_y, const uint8_t *cur_u, const uint8_t *cur_v,
+                                        const vp8b200_segment_data *SD_host) {
+    if (!e || !SD_host) return -(int)cudaErrorInvalidValue;
+    int rc = upload_sd(e, SD_host, 0);
+    if (rc) return rc;
+    static const short dcq[128] = {
+        4,   5,   6,   7,   8,   9,   10,  10,  11,  12,  13,  14,  15,  16,  17,  17,  18,  19,  20,  20,  21,  21,
+        22,  22,  23,  23,  24,  25,  25,  26,  27,  28,  29,  30,  31,  32,  33,  34,  35,  36,  37,  37,  38,  39,
+        40,  41,  42,  43,  44,  45,  46,  46,  47,  48,  49,  50,  51,  52,  53,  54,  55,  56,  57,  58,  59,  60,
+        61,  62,  63,  64,  65,  66,  67,  68,  69,  70,  71,  72,  73,  74,  75,  76,  76,  77,  78,  79,  80,  81,
+        82,  83,  84,  85,  86,  87,  88,  89,  91,  93,  95,  96,  98,  100, 101, 102, 104, 106, 108, 110, 112, 114,
+        116, 118, 122, 124, 126, 128, 130, 132, 134, 136, 138, 140, 143, 145, 148, 151, 154, 157};
+    static const short acq[128] = {
+        4,   5,   6,   7,   8,   9,   10,  11,  12,  13,  14,  15,  16,  17,  18,  19,  20,  21,  22,  23,  24,  25,
+        26,  27,  28,  29,  30,  31,  32,  33,  34,  35,  36,  37,  38,  39,  40,  41,  42,  43,  44,  45,  46,  47,
+        48,  49,  50,  51,  52,  53,  54,  55,  56,  57,  58,  60,  62,  64,  66,  68,  70,  72,  74,  76,  78,  80,
+        82,  84,  86,  88,  90,  92,  94,  96,  98,  100, 102, 104, 106, 108, 110, 112, 114, 116, 119, 122, 125, 128,
+        131, 134, 137, 140, 143, 146, 149, 152, 155, 158, 161, 164, 167, 170, 173, 177, 181, 185, 189, 193, 197, 201,
+        205, 209, 213, 217, 221, 225, 229, 234, 239, 245, 249, 254, 259, 264, 269, 274, 279, 284};
+    auto cl = [](int v) { return v < 0 ? 0 : (v > 127 ? 127 : v); };
+    const int i = SD_host[0].y_ac_i;
+    const int y_ac = acq[cl(i)], y_dc = dcq[cl(i + SD_host[0].y_dc_idelta)];
+    int uv_dc = dcq[cl(i + SD_host[0].uv_dc_idelta)];
+    const int uv_ac = acq[cl(i + SD_host[0].uv_ac_idelta)];
+    if (uv_dc > 132) uv_dc = 132;
+    e->launches = 0;
+    TRY(vp8b200_intra_frame(e->stream, cur_y, cur_u, cur_v, e->last_pyr[0], e->recon_u, e->recon_v, e->coeffs, e->modes, e->parts,
+                            e->seg_id, e->w, e->h, y_dc, y_ac, uv_dc, uv_ac, e->intra_scratch));
+    return 0;
 }
 
 extern "C" int vp8b200_engine_loop_filter(vp8b200_engine *e, const vp8b200_segment_data *SD_host) {

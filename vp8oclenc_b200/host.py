@@ -184,7 +184,7 @@ class Engine:
     (src/inter_part.h, src/loop_filter.h) on one CUDA stream."""
 
     BUF = dict(coeffs=0, vectors=1, parts=2, reference_frame=3, segment_id=4, ssim=5, non_zero=6, recon_y=7,
-               recon_u=8, recon_v=9)
+               recon_u=8, recon_v=9, intra_modes=10)
 
     def __init__(self, width, height, stream=None):
         L = lib()
@@ -223,6 +223,11 @@ class Engine:
                                                 int(prev_is_golden), int(prev_is_altref), int(altref_differs)),
                "engine_inter_frame")
 
+    def key_frame(self, cur_y, cur_u, cur_v, sd_np):
+        """intra_transform() for the current frame (device tensors); follow with loop_filter(sd_np)"""
+        _check(lib().vp8b200_engine_key_frame(self._h, _p(cur_y), _p(cur_u), _p(cur_v), ctypes.c_void_p(sd_np.ctypes.data)),
+               "engine_key_frame")
+
     def loop_filter(self, sd_np=None):
         p = ctypes.c_void_p(sd_np.ctypes.data) if sd_np is not None else ctypes.c_void_p(0)
         _check(lib().vp8b200_engine_loop_filter(self._h, p), "engine_loop_filter")
@@ -250,7 +255,7 @@ class Engine:
         shapes = dict(coeffs=(np.int16, M * 400), vectors=(np.int16, M * 8), parts=(np.int32, M),
                       reference_frame=(np.int32, M), segment_id=(np.int32, M), ssim=(np.float32, M),
                       non_zero=(np.int32, M), recon_y=(np.uint8, w * h), recon_u=(np.uint8, w * h // 4),
-                      recon_v=(np.uint8, w * h // 4))
+                      recon_v=(np.uint8, w * h // 4), intra_modes=(np.int32, M * 16))
         dt, n = shapes[name]
         out = np.empty(n, dt)
         self.synchronize()

@@ -11,6 +11,22 @@ _DC_Q = [4, 5, 6, 7, 8, 9, 10, 10, 11, 12, 13, 14, 15, 16, 17, 17, 18, 19, 20, 2
          154, 157]
 
 
+_AC_Q = [4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33,
+         34, 35, 36, 37, 38, 39, 40, 41, 42, 43, 44, 45, 46, 47, 48, 49, 50, 51, 52, 53, 54, 55, 56, 57, 58, 60, 62, 64,
+         66, 68, 70, 72, 74, 76, 78, 80, 82, 84, 86, 88, 90, 92, 94, 96, 98, 100, 102, 104, 106, 108, 110, 112, 114,
+         116, 119, 122, 125, 128, 131, 134, 137, 140, 143, 146, 149, 152, 155, 158, 161, 164, 167, 170, 173, 177, 181,
+         185, 189, 193, 197, 201, 205, 209, 213, 217, 221, 225, 229, 234, 239, 245, 249, 254, 259, 264, 269, 274, 279,
+         284]
+
+
+def intra_quants(sd):
+    """(y_dc_q, y_ac_q, uv_dc_q, uv_ac_q) of segment 0 as prepare_segments_data() derives frames.y_dc_q ... from the
+    segment table (src/vp8enc.cpp:160-181); what intra_transform() quantises a key frame with"""
+    cl = lambda v: max(0, min(127, int(v)))  # noqa: E731
+    i = int(sd[0, 0])
+    return (_DC_Q[cl(i + sd[0, 1])], _AC_Q[cl(i)], min(_DC_Q[cl(i + sd[0, 4])], 132), _AC_Q[cl(i + sd[0, 5])])
+
+
 def make_segment_data(qi=(24, 24, 24, 24), key=False, lf_level=None, sharpness=0, reductor=4):
     """int32 [4][11] segment_data (src/vp8enc.h:80-92) filled like prepare_segments_data()
     (src/vp8enc.cpp:129-221) does for an inter frame; the loop-filter level is
