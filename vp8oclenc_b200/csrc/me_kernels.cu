@@ -284,18 +284,47 @@ __device__ __forceinline__ constexpr uint32_t taps_lo(int ph) {
 }
 __device__ __forceinline__ constexpr uint32_t taps_hi(int ph) { return pack_taps(six_tap(ph, 4), six_tap(ph, 5), 0, 0); }
 
-__device__ __forceinline__ void s2_residual(const uint32_t (&tl)[4][3], int first, uint32_t lo, uint32_t hi,
-                                            const uint32_t (&cur)[4], int (&r)[16]) {
+// Vertical six taps without aligning the data: the twelve lines of a column sit in three words (line = byte), an
+// output whose first line is byte k of word a multiplies the words a, a+1 (and a+2 when k = 3) by tap words that carry
+// the taps at byte k onwards -- two or three dp4a, no funnel shift.  vtap_word(ph, k, j): the part of phase ph's taps
+// that falls into word j when tap 0 sits at byte k.  All arguments are literals after unrolling.
+__device__ __forceinline__ constexpr uint32_t vtap_word(int ph, int k, int j) {
+    uint32_t w = 0;
+    for (int i = 0; i < 6; ++i)
+        if (((k + i) >> 2) == j) w |= (uint32_t)(six_tap(ph, i) & 255) << (8 * ((k + i) & 3));
+    return w;
+}
+// four values -> four saturated bytes (a in byte 0): the six-tap's ">> 7 then clamp to 0..255" is the saturation
+__device__ __forceinline__ uint32_t pack4_sat_u8(int a, int b, int c, int d) {
+    uint32_t hi, r;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(d), "r"(c), "r"(0));
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(b), "r"(a), "r"(hi));
+    return r;
+}
+// the four predicted pixels (output rows 0..3, packed) of one column for y-phase ph; c = lines 0..11 of the column,
+// first = line of tap 0 of output row 0
+__device__ __forceinline__ uint32_t s2_pred_column(const uint32_t (&c)[3], int ph, int first) {
+    int s[4];
 #pragma unroll
-    for (int y = 0; y < 4; ++y)
-#pragma unroll
-        for (int x = 0; x < 4; ++x) {
-            const int s0 = first + y, a = s0 >> 2, sh = 8 * (s0 & 3);
-            const uint32_t w_lo = sh ? __funnelshift_r(tl[x][a], tl[x][a + 1], sh) : tl[x][a];
-            const uint32_t w_hi = sh ? __funnelshift_r(tl[x][a + 1], tl[x][(a + 2) % 3], sh) : tl[x][a + 1];
-            const int s = dp4a_u8s8(w_hi, hi, dp4a_u8s8(w_lo, lo, 64));
-            r[4 * y + x] = (int)__byte_perm(cur[y], 0, 0x4440 + x) - sat8(s >> 7);
-        }
+    for (int y = 0; y < 4; ++y) {
+        const int s0 = first + y, a = s0 >> 2, k = s0 & 3;
+        s[y] = dp4a_u8s8(c[a + 1], vtap_word(ph, k, 1), dp4a_u8s8(c[a], vtap_word(ph, k, 0), 64));
+        if (k == 3) s[y] = dp4a_u8s8(c[a + 2], vtap_word(ph, k, 2), s[y]);
+    }
+    return pack4_sat_u8(s[0] >> 7, s[1] >> 7, s[2] >> 7, s[3] >> 7);
+}
+// Pass 1 of the cost transform for one column from its packed predicted pixels and the features of the current
+// sub-block's column (col_features, common.cuh): the transform is linear before its shifts, so it never sees a
+// residual.  The four sums of the predicted column are dp4a with +-1 weights.
+__device__ __forceinline__ void s2_column_pass1(uint32_t pred, const int4 cf, int &o0, int &o4, int &o8, int &o12) {
+    const int e0 = dp4a_u8s8(pred, 0x01ff0101u, 0);  // p0 + p1 - p2 + p3   (s + u)
+    const int e8 = dp4a_u8s8(pred, 0x0101ff01u, 0);  // p0 - p1 + p2 + p3   (s - u)
+    const int t = dp4a_u8s8(pred, 0xff000001u, 0);   // p0 - p3
+    const int x = (int)__byte_perm(pred, 0, 0x4442); // p2
+    o0 = cf.x - e0;
+    o8 = cf.y - e8;
+    o4 = (cf.z - x * 2217 - t * 42816) >> 12;
+    o12 = (cf.w - t * 17736 + x * 5352) >> 12;
 }
 
 // Staging of the reference windows, two ways (the north star names the second, so it is measured):
@@ -329,6 +358,7 @@ __device__ __forceinline__ void luma_search_2step_body(const uint8_t *__restrict
     __shared__ uint32_t s_cur[S2_BLOCKS][8][2];
     __shared__ uint32_t s_zero[S2_BLOCKS][8][2];   // co-located reference block (candidate #25)
     __shared__ unsigned s_key[S2_BLOCKS];
+    __shared__ int4 s_cf[S2_BLOCKS][4][4];         // pass-1 features of the current block: [sub-block][column]
 
     const int tid = threadIdx.x;
     const int bw = width >> 3;
@@ -455,6 +485,15 @@ __device__ __forceinline__ void luma_search_2step_body(const uint8_t *__restrict
             dst[4 * 128 + 16 * c] = (uint8_t)sat8(dp4a_u8s8(hi[c + 1], taps_hi(4), dp4a_u8s8(lo[c + 1], taps_lo(4), 64)) >> 7);
         }
     }
+    // pass-1 features of every column of the current sub-blocks (the candidates only subtract theirs)
+    for (int i = tid; i < S2_BLOCKS * 16; i += S2_THREADS) {
+        const int b = i >> 4, j = (i >> 2) & 3, k = i & 3, sx = j >> 1, sy = (j & 1) * 4;
+        const uint32_t sel = 0x4440 + k;
+        const ColFeat f = col_features((int)__byte_perm(s_cur[b][sy][sx], 0, sel), (int)__byte_perm(s_cur[b][sy + 1][sx], 0, sel),
+                                       (int)__byte_perm(s_cur[b][sy + 2][sx], 0, sel), (int)__byte_perm(s_cur[b][sy + 3][sx], 0, sel),
+                                       14500, 7500);
+        s_cf[b][j][k] = make_int4(f.e0, f.e8, f.a4, f.a12);
+    }
     // candidate #25, the zero vector (full-pel, no penalty), on the last warp, which has no item in round 2:
     // four threads per block, one 4x4 sub-block each
     if (tid >= S2_THREADS - 32) {
@@ -481,11 +520,7 @@ __device__ __forceinline__ void luma_search_2step_body(const uint8_t *__restrict
         const bool live = n0 + b < nblocks;
         int bx, by, v0x, v0y;
         geometry(b, bx, by, v0x, v0y);
-        uint32_t cu[4];  // the current sub-block stays packed: one PRMT per use is cheaper than 12 more registers
-#pragma unroll
-        for (int y = 0; y < 4; ++y) cu[y] = s_cur[b][sy + y][sx];
         unsigned best = 0xffffffffu;
-        int r[16];
         uint32_t tl[4][3];  // lines sy .. sy+11 of the four columns of this x-phase (lines >= 14 are never used)
 #pragma unroll
         for (int x = 0; x < 4; ++x) {
@@ -501,19 +536,18 @@ __device__ __forceinline__ void luma_search_2step_body(const uint8_t *__restrict
 #pragma unroll 1
 #endif
         for (int yi = 0; yi < 5; ++yi) {
-            if (yi < 2) {
-                s2_residual(tl, 0, yi == 0 ? taps_lo(4) : taps_lo(6), yi == 0 ? taps_hi(4) : taps_hi(6), cu, r);
-            } else if (yi == 2) {
+            int o[16];
 #pragma unroll
-                for (int y = 0; y < 4; ++y)
-#pragma unroll
-                    for (int x = 0; x < 4; ++x)  // full-pel phase: line 1+2+y itself
-                        r[4 * y + x] = (int)__byte_perm(cu[y], 0, 0x4440 + x) -
-                                       (int)__byte_perm(tl[x][(3 + y) >> 2], 0, 0x4440 + ((3 + y) & 3));
-            } else {
-                s2_residual(tl, 1, yi == 3 ? taps_lo(2) : taps_lo(4), yi == 3 ? taps_hi(2) : taps_hi(4), cu, r);
+            for (int x = 0; x < 4; ++x) {
+                uint32_t pred;
+                if (yi == 0) pred = s2_pred_column(tl[x], 4, 0);
+                else if (yi == 1) pred = s2_pred_column(tl[x], 6, 0);
+                else if (yi == 2) pred = __funnelshift_r(tl[x][0], tl[x][1], 24);  // full-pel phase: lines 3..6 themselves
+                else if (yi == 3) pred = s2_pred_column(tl[x], 2, 1);
+                else pred = s2_pred_column(tl[x], 4, 1);
+                s2_column_pass1(pred, s_cf[b][j][x], o[x], o[4 + x], o[8 + x], o[12 + x]);
             }
-            int cost = weight4x4(r);
+            int cost = weight4x4_rows(o);
             cost += __shfl_xor_sync(0xffffffffu, cost, 1);
             cost += __shfl_xor_sync(0xffffffffu, cost, 2);
             cost += (abs(xi - 2) + abs(yi - 2)) * 32;
