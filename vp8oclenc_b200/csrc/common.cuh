@@ -120,6 +120,15 @@ __device__ __forceinline__ int weight4x4_rows(const int (&o)[16]) {
     return sum;
 }
 
+// Truncating x / q through m = magic(q): |x| * m >> 32 with the sign put back.  m * q = 2^32 + e with 0 <= e < q,
+// so the quotient is exact while |x| * e < 2^32; quantisers are <= 440 and the dividends below 2^18.
+// q == 1 (m would be 2^32) is encoded as m == 0.
+__device__ __forceinline__ uint32_t magic(int q) { return q == 1 ? 0u : 0xffffffffu / (uint32_t)q + 1u; }
+__device__ __forceinline__ int div_magic(int x, uint32_t m) {
+    const int r = (int)__umulhi((uint32_t)abs(x), m);
+    return m == 0u ? x : (x < 0 ? -r : r);
+}
+
 // quantisers of one segment, derived exactly as the device code of the reference does it
 // in three places (Q11; src/GPU_kernels.cl:1394-1408, 1515-1524, 1568-1582)
 struct Quants {

@@ -83,7 +83,8 @@ __device__ __forceinline__ void intra_fdct(const int (&r)[16], int (&f)[16]) {
 }
 
 // quantise (:212-250), then dequantise + inverse DCT + predictor (:40-122); f becomes the quantised block
-__device__ __forceinline__ void intra_quant_recon(int (&f)[16], const int (&pred)[16], int (&out)[16], int dc_q, int ac_q) {
+__device__ __forceinline__ void intra_quant_recon(int (&f)[16], const int (&pred)[16], int (&out)[16], int dc_q, int ac_q,
+                                                  uint32_t m_dc, uint32_t m_ac) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         const int q = i == 0 ? dc_q : ac_q;
@@ -91,7 +92,7 @@ __device__ __forceinline__ void intra_quant_recon(int (&f)[16], const int (&pred
         f[i] = s16(f[i] + (sign_of < 0 ? -q / 2 : q / 2));
     }
 #pragma unroll
-    for (int i = 0; i < 16; ++i) f[i] = s16(f[i] / (i == 0 ? dc_q : ac_q));
+    for (int i = 0; i < 16; ++i) f[i] = div_magic(f[i], i == 0 ? m_dc : m_ac);  // (exact: |f| < 2^15, see common.cuh)
     int t[16];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -145,6 +146,10 @@ __device__ __forceinline__ uint32_t ld_cg_u8(const uint8_t *p) {
 struct IntraQuants { int y_dc, y_ac, uv_dc, uv_ac; };
 
 // ctrl[0] = ticket, ctrl[1 + r] = luma macroblocks finished in row r, ctrl[1 + mbh + r] = chroma macroblocks finished
+#if defined(INTRA_EXP_TIMELINE)
+__device__ unsigned long long g_timeline[4][128][16];
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#endif
 __global__ void __launch_bounds__(64)
 k_intra_frame(const uint8_t *__restrict__ cur_y, const uint8_t *__restrict__ cur_u, const uint8_t *__restrict__ cur_v,
               uint8_t *rec_y, uint8_t *rec_u, uint8_t *rec_v, int16_t *__restrict__ MB, int *__restrict__ modes,
@@ -159,25 +164,40 @@ k_intra_frame(const uint8_t *__restrict__ cur_y, const uint8_t *__restrict__ cur
     __shared__ __align__(16) uint8_t ty[17][28];
     __shared__ __align__(16) uint8_t sy[16][16];  // source luma
     __shared__ int s_edge[2][16];      // per half-warp: L3 L2 L1 L0 P A0..A7, DC value
+    // the tap table, transposed ([pixel][mode]): the ten lanes of a half-warp read ten neighbouring entries (from
+    // constant memory their ten different addresses would be served one after the other)
+    __shared__ unsigned short s_taps[16][16];
     __shared__ uint8_t tc[2][9][12];   // chroma tiles with border, per plane
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) s_row = atomicAdd(&ctrl[0], 1);
+    for (int i = tid; i < 160; i += 64) s_taps[i & 15][i >> 4] = c_intra_taps.t[i >> 4][i & 15];
     __syncthreads();
     const int r = s_row;
     if (r >= mbh) return;
     int *done_y = ctrl + 1, *done_c = ctrl + 1 + mbh;
+    const uint32_t m_y_dc = magic(q.y_dc), m_y_ac = magic(q.y_ac), m_uv_dc = magic(q.uv_dc), m_uv_ac = magic(q.uv_ac);
 
     if (warp == 0) {
         // ------------------------------------------------ luma ------------------------------------------------
         const int h = lane >> 4, m = lane & 15;  // half-warp, sub-block mode evaluated by this lane
+        // source pixels, 8 bytes per lane, fetched one macroblock ahead (the walk along the row is latency-bound)
+        const uint8_t *src_lane = cur_y + (size_t)(16 * r + (lane >> 1)) * width + 8 * (lane & 1);
+        uint2 src_next = *reinterpret_cast<const uint2 *>(src_lane);
         for (int c = 0; c < mbw; ++c) {
             const int mb = r * mbw + c;
+#if defined(INTRA_EXP_TIMELINE)
+            if (lane == 0 && r < 4 && c < 128) g_timeline[r][c][0] = gtime();
+#endif
             if (r > 0) {
                 const int need = min(c + 2, mbw);
-                if (lane == 0)
-                    while (ld_acquire_gpu(&done_y[r - 1]) < need) {}
+                // every lane polls (one broadcast load): a single polling lane leaves the warp split for the rest of the
+                // macroblock and every instruction issues twice
+                while (ld_acquire_gpu(&done_y[r - 1]) < need) {}
                 __syncwarp();
             }
+#if defined(INTRA_EXP_TIMELINE)
+            if (lane == 0 && r < 4 && c < 128) g_timeline[r][c][1] = gtime();
+#endif
             // left column: the previous macroblock's last column (still in the tile), 129 at the frame edge
             if (lane < 16) ty[1 + lane][XO - 1] = c == 0 ? (uint8_t)129 : ty[1 + lane][XO + 15];
             __syncwarp();
@@ -194,14 +214,14 @@ k_intra_frame(const uint8_t *__restrict__ cur_y, const uint8_t *__restrict__ cur
                 }
                 ty[0][XO - 1 + lane] = (uint8_t)v;
             }
-            {   // source pixels: 8 bytes per lane
-                const int row = lane >> 1, half = lane & 1;
-                const uint2 v = *reinterpret_cast<const uint2 *>(cur_y + (size_t)(16 * r + row) * width + 16 * c + 8 * half);
-                *reinterpret_cast<uint2 *>(&sy[row][8 * half]) = v;
-            }
+            *reinterpret_cast<uint2 *>(&sy[lane >> 1][8 * (lane & 1)]) = src_next;
+            if (c + 1 < mbw) src_next = *reinterpret_cast<const uint2 *>(src_lane + 16 * (c + 1));
             __syncwarp();
             if (lane < 12) ty[4 + 4 * (lane >> 2)][XO + 16 + (lane & 3)] = ty[0][XO + 16 + (lane & 3)];
             __syncwarp();
+#if defined(INTRA_EXP_TIMELINE)
+            if (lane == 0 && r < 4 && c < 128) g_timeline[r][c][2] = gtime();
+#endif
 
 #pragma unroll 1
             for (int t = 0; t < 10; ++t) {
@@ -238,7 +258,7 @@ k_intra_frame(const uint8_t *__restrict__ cur_y, const uint8_t *__restrict__ cur
                     } else {
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
-                            const int tp = c_intra_taps.t[m][i];
+                            const int tp = s_taps[i][m];
                             pred[i] = (s_edge[h][tp & 15] + 2 * s_edge[h][(tp >> 4) & 15] + s_edge[h][tp >> 8] + 2) >> 2;
                         }
                     }
@@ -255,7 +275,7 @@ k_intra_frame(const uint8_t *__restrict__ cur_y, const uint8_t *__restrict__ cur
                 for (int o = 8; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
                 if (valid && key == best) {  // exactly one lane of the half-warp
                     int out[16];
-                    intra_quant_recon(f, pred, out, q.y_dc, q.y_ac);
+                    intra_quant_recon(f, pred, out, q.y_dc, q.y_ac, m_y_dc, m_y_ac);
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
                         *reinterpret_cast<uint32_t *>(&ty[1 + y0 + i][XO + x0]) =
@@ -264,6 +284,9 @@ k_intra_frame(const uint8_t *__restrict__ cur_y, const uint8_t *__restrict__ cur
                     modes[16 * mb + 4 * br + bc] = m;
                 }
                 __syncwarp();
+#if defined(INTRA_EXP_TIMELINE)
+                if (lane == 0 && r < 4 && c < 128) g_timeline[r][c][3 + t] = gtime();
+#endif
             }
             // the macroblock's reconstruction to the frame; then tell the row below
             {
@@ -276,8 +299,14 @@ k_intra_frame(const uint8_t *__restrict__ cur_y, const uint8_t *__restrict__ cur
                 segment_id[mb] = 0;
             }
             __syncwarp();
-            __threadfence();
+#if defined(INTRA_EXP_TIMELINE)
+            if (lane == 0 && r < 4 && c < 128) g_timeline[r][c][13] = gtime();
+#endif
+            // (the release below is cumulative over the lanes the __syncwarp ordered before it: no separate fence)
             if (lane == 0) st_release_gpu(&done_y[r], c + 1);
+#if defined(INTRA_EXP_TIMELINE)
+            if (lane == 0 && r < 4 && c < 128) g_timeline[r][c][14] = gtime();
+#endif
         }
     } else {
         // ------------------------------------------------ chroma: TM_PRED, eight blocks on eight lanes ------------------------------------------------
@@ -285,8 +314,7 @@ k_intra_frame(const uint8_t *__restrict__ cur_y, const uint8_t *__restrict__ cur
             const int mb = r * mbw + c;
             if (r > 0) {
                 const int need = min(c + 1, mbw);
-                if (lane == 0)
-                    while (ld_acquire_gpu(&done_c[r - 1]) < need) {}
+                while (ld_acquire_gpu(&done_c[r - 1]) < need) {}
                 __syncwarp();
             }
             const int pl = lane >> 4, l = lane & 15;
@@ -312,7 +340,7 @@ k_intra_frame(const uint8_t *__restrict__ cur_y, const uint8_t *__restrict__ cur
                     res[i] = (int)cp[(size_t)(8 * r + y0 + (i >> 2)) * cw + 8 * c + x0 + (i & 3)] - pred[i];
                 }
                 intra_fdct(res, f);
-                intra_quant_recon(f, pred, out, q.uv_dc, q.uv_ac);
+                intra_quant_recon(f, pred, out, q.uv_dc, q.uv_ac, m_uv_dc, m_uv_ac);
                 // (the blocks of a plane only read the border: the tile's interior can be overwritten right away, except
                 // column 8, which the next macroblock needs and which block column 1 writes last)
 #pragma unroll
@@ -324,7 +352,7 @@ k_intra_frame(const uint8_t *__restrict__ cur_y, const uint8_t *__restrict__ cur
                 store_zigzag(MB + (size_t)mb * 400 + 16 * (16 + 4 * pl + l), f);
             }
             __syncwarp();
-            __threadfence();
+            // (cumulative release, as above)
             if (lane == 0) st_release_gpu(&done_c[r], c + 1);
         }
     }
@@ -334,6 +362,11 @@ k_intra_frame(const uint8_t *__restrict__ cur_y, const uint8_t *__restrict__ cur
 
 using namespace vp8;
 
+#if defined(INTRA_EXP_TIMELINE)
+extern "C" int vp8b200_intra_debug_timeline(unsigned long long *out) {
+    return (int)cudaMemcpyFromSymbol(out, g_timeline, sizeof(g_timeline));
+}
+#endif
 extern "C" size_t vp8b200_intra_frame_scratch_bytes(int width, int height) {
     return (size_t)(1 + 2 * (height / 16)) * sizeof(int);
 }

@@ -33,14 +33,6 @@ __device__ __forceinline__ int wht_pick(int a0, int a1, int a2, int a3, int r) {
     const int p = (r & 1) ? d : a, q = (r & 1) ? c : b;
     return (r & 2) ? p - q : p + q;
 }
-// Truncating x / q through m = magic(q): |x| * m >> 32 with the sign put back.  m * q = 2^32 + e with 0 <= e < q,
-// so the quotient is exact while |x| * e < 2^32; quantisers are <= 440 and the dividends below 2^18.
-// q == 1 (m would be 2^32) is encoded as m == 0.
-__device__ __forceinline__ uint32_t magic(int q) { return q == 1 ? 0u : 0xffffffffu / (uint32_t)q + 1u; }
-__device__ __forceinline__ int div_magic(int x, uint32_t m) {
-    const int r = (int)__umulhi((uint32_t)abs(x), m);
-    return m == 0u ? x : (x < 0 ? -r : r);
-}
 __device__ __forceinline__ void idct1d(int i0, int i1, int i2, int i3, int &o0, int &o1, int &o2, int &o3) {
     const int a1 = i0 + i2, b1 = i0 - i2;
     const int c1 = ((i1 * 35468) >> 16) - (i3 + ((i3 * 20091) >> 16));
