@@ -131,13 +131,46 @@ def reference_encode(tmp, w, h, frames, tag, threads=None):
     gen_y4m.write_y4m(y4m, w, h, frames)
     ivf = os.path.join(tmp, "ref_%s.ivf" % tag)
     # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1 to its workers)
+    stage_file = os.path.join(tmp, "ref_stages_%s.txt" % tag)
     pr = segments.EncoderProcess(y4m, ivf, ENC_ARGS, os.path.join(tmp, "ref_run_%s" % tag), lib_dir=ref_dir, host_bin=host_bin,
-                                 env_extra={"OMP_NUM_THREADS": str(threads or os.cpu_count() or 1)})
+                                 env_extra={"OMP_NUM_THREADS": str(threads or os.cpu_count() or 1), "VP8CL_STAGES": stage_file})
     stamps = pr.wait(timeout=1500)
     os.remove(y4m)
     if len(stamps) != frames:
         raise RuntimeError("reference encoder finished %d of %d frames" % (len(stamps), frames))
+    reference_encode.stages = reference_stages(stage_file, stamps)
     return stamps, ivf
+
+
+REF_STAGES = {  # BASELINE.md's per-stage split: the reference's kernels by name
+    "motion_search": ("reset_vectors", "downsample_x2", "luma_search_1step", "luma_search_2step", "select_reference", "pack_8x8_into_16x16"),
+    "predict_transform": ("prepare_predictors_and_residual", "dct4x4", "wht4x4_iwht4x4", "idct4x4", "count_SSIM_luma", "count_SSIM_chroma",
+                          "gather_SSIM"),
+    "loop_filter": ("prepare_filter_mask", "loop_filter_frame_luma", "loop_filter_frame_chroma"),
+    "entropy": ("count_probs", "num_div_denom", "encode_coefficients"),
+}
+
+
+def reference_stages(stage_file, stamps):
+    """ms per inter frame of the reference's stages on the CPU, from the runtime's per-kernel wall times
+    (oracle/cl_host_runtime.cpp, VP8CL_STAGES).  Search and transform only run in inter frames; loop filter and entropy
+    run in every frame and are averaged over all of them; host = the inter frames' wall time minus the four."""
+    if not os.path.exists(stage_file) or len(stamps) < 2:
+        return None
+    ms = {}
+    for ln in open(stage_file):
+        f = ln.split()
+        if len(f) == 3:
+            ms[f[0]] = float(f[2])
+    frames, inter = len(stamps), len(stamps) - 1
+    out = {}
+    for stage, names in REF_STAGES.items():
+        tot = sum(ms.get(n, 0.0) for n in names)
+        out[stage] = tot / (inter if stage in ("motion_search", "predict_transform") else frames)
+    per_inter = 1000.0 * (stamps[-1] - stamps[0]) / inter
+    out["host_rest"] = per_inter - sum(out.values())
+    out["frame"] = per_inter
+    return {k: round(v, 3) for k, v in out.items()}
 
 
 def reference_arm(args, tmp, w, h):
@@ -152,7 +185,8 @@ def reference_arm(args, tmp, w, h):
             "sample": "%d inter frames of the %s clip after 1 key + %d warm-up frames; unmodified reference host with its own "
                       ".cl kernels compiled for the CPU (oracle/_ref), OpenMP over work-items, all host cores"
                       % (steps, size_name(w, h), warm),
-            "ms_per_step": 1000.0 * dt / steps, "steps": steps, "warmup": warm, "ivf": ivf}
+            "ms_per_step": 1000.0 * dt / steps, "steps": steps, "warmup": warm, "ivf": ivf,
+            "stages_ms_per_frame": getattr(reference_encode, "stages", None)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -684,7 +718,7 @@ def main():
                     "steps": r["steps"], "warmup": r["warmup"], "ms_per_step": r["ms_per_step"], "higher_is_better": True,
                     "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32", "data": "synthetic", "config": config,
                     "step_is": "one encoded inter frame (the CPU reference encodes one stream)",
-                    "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                    "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "stages_ms_per_frame")},
                     "e2e": {"value": r["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
             print(json.dumps(line))
             return 0
@@ -743,7 +777,7 @@ def b200_arm(args, w, h, S, F, rank, world, local_rank, tmp, config, metric):
             if world == 1:
                 r = reference_arm(argparse.Namespace(steps=min(K, 12), warmup=2), tmp, w, h)
                 if r:
-                    cpu_baseline = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+                    cpu_baseline = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "stages_ms_per_frame")}
                     ref_ivf = r["ivf"]
             else:
                 r = reference_encode(tmp, w, h, 3, "check")

@@ -104,6 +104,43 @@ static void gaps_init() {
     if (getenv("VP8CL_GAPS")) { g_gaps_on = true; g_gap_t = gap_now(); atexit(gaps_write); }
 }
 
+// ---- per-stage profiler (VP8CL_STAGES=<file>): wall time of the reference's kernels by name --------------------
+// Written at exit as "name calls wall_ms" lines plus the process' total wall time; bench.py groups them into the
+// stages of BASELINE.md (motion search, predict + transform, loop filter, entropy; host = the rest).
+static bool g_stages_on = false;
+static unsigned long long g_stage_t0 = 0;
+static std::map<std::string, std::pair<unsigned long long, unsigned long long>> g_stage_ns;
+static unsigned long long wall_now() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (unsigned long long)ts.tv_sec * 1000000000ull + ts.tv_nsec;
+}
+static void stages_write() {
+    const char *p = getenv("VP8CL_STAGES");
+    FILE *f = p ? fopen(p, "w") : nullptr;
+    if (!f) return;
+    fprintf(f, "total_wall %.3f\n", (wall_now() - g_stage_t0) * 1e-6);
+    for (auto &kv : g_stage_ns) fprintf(f, "%s %llu %.3f\n", kv.first.c_str(), kv.second.second, kv.second.first * 1e-6);
+    fclose(f);
+}
+static void stages_init() {
+    static bool done = false;
+    if (done) return;
+    done = true;
+    if (getenv("VP8CL_STAGES")) { g_stages_on = true; g_stage_t0 = wall_now(); atexit(stages_write); }
+}
+struct StageScope {
+    const char *name;
+    unsigned long long t;
+    explicit StageScope(const char *n) : name(n), t(g_stages_on ? wall_now() : 0) {}
+    ~StageScope() {
+        if (!g_stages_on) return;
+        auto &e = g_stage_ns[name];
+        e.first += wall_now() - t;
+        e.second += 1;
+    }
+};
+
 extern "C" const clc::kernel_desc vp8ref_gpu_kernels[];
 extern "C" const clc::kernel_desc vp8ref_cpu_kernels[];
 
@@ -142,6 +179,7 @@ extern "C" {
 
 cl_int clGetPlatformIDs(cl_uint num_entries, cl_platform_id *platforms, cl_uint *num_platforms) {
     gaps_init();
+    stages_init();
     if (num_platforms) *num_platforms = 1;
     if (platforms && num_entries >= 1) platforms[0] = &g_platform;
     return CL_SUCCESS;
@@ -277,6 +315,7 @@ cl_int clEnqueueNDRangeKernel(cl_command_queue, cl_kernel k, cl_uint dim, const 
     GapScope gs("kernel", k ? k->desc->name : "?", -1); if (g_gaps_on && k && !strcmp(k->desc->name, "reset_vectors")) ++g_gap_frames;
     if (!k) return CL_INVALID_KERNEL;
     if (dim != 1) return CL_INVALID_WORK_DIMENSION;
+    StageScope stage_scope(k->desc->name);
     const int n = k->desc->nargs;
     void *resolved[24];
     void *argv[24];
