@@ -206,7 +206,9 @@ static void stats_frame_start() {  // called at the start of every inter frame (
     if (g_account_cpu && g_stats_from > 0 && (long)g_frames == g_stats_from) g_stats_base_n = collect_stats(g_stats_base);
     ++g_frames;
 }
+static void startup_mark(const char *what);
 static void write_stats() {
+    startup_mark("exit");
     const char *p = getenv("VP8B200_STATS");
     if (!p || !*p) return;
     StatItem now[kMaxStatItems];
@@ -233,14 +235,28 @@ static cudaEvent_t g_sync_event = nullptr;
 
 static void install_guard_handler();
 
+// VP8B200_STARTUP=1: where an instance's start-up goes (milliseconds since this library was loaded, on stderr)
+static unsigned long long startup_clock() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (unsigned long long)ts.tv_sec * 1000000000ull + ts.tv_nsec;
+}
+static const unsigned long long g_t_loaded = startup_clock();
+static void startup_mark(const char *what) {
+    static const bool on = getenv("VP8B200_STARTUP") != nullptr;
+    if (on) fprintf(stderr, "vp8oclenc_b200 startup %8.1f ms  %s\n", (startup_clock() - g_t_loaded) * 1e-6, what);
+}
+
 static bool cuda_init() {
     if (g_cuda_tried) return g_cuda_ok;
     g_cuda_tried = true;
     int n = 0;
+    startup_mark("first OpenCL call");
     if (cudaGetDeviceCount(&n) != cudaSuccess || n < 1) {
         fprintf(stderr, "vp8oclenc_b200: no CUDA device -- this OpenCL shim has no CPU fallback\n");
         return false;
     }
+    startup_mark("driver initialised (cudaGetDeviceCount)");
     const char *dev_env = getenv("VP8B200_DEVICE");
     if (dev_env) cudaSetDevice(atoi(dev_env));
     // VP8B200_HOST_PROFILE=reference: the caller vouches that the host program is the reference's (it keeps its
@@ -268,6 +284,7 @@ static bool cuda_init() {
         if (const char *sp = getenv("VP8B200_SYNC_SPIN_US")) g_sync_spin_us = atoi(sp);
     }
     if (cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking) != cudaSuccess) return false;
+    startup_mark("context and stream created");
     vp8b200_device_info(g_dev_name, sizeof(g_dev_name), &g_sm_count, nullptr, nullptr);
     if (const char *f = getenv("VP8B200_FUSED")) g_fuse = f[0] != '0';
     if (const char *f = getenv("VP8B200_GPU_TOKENS")) g_gpu_tokens = f[0] != '0';
@@ -1612,6 +1629,13 @@ cl_int clEnqueueNDRangeKernel(cl_command_queue, cl_kernel k, cl_uint dim, const 
         if (!k->set[i]) return CL_INVALID_KERNEL_ARGS;
     start_gate(k->id == K_RESET_VECTORS);
     if (k->id == K_RESET_VECTORS) stats_frame_start();
+    {
+        static int seen = 0;
+        if (seen < 2 && (seen == 0 || k->id == K_RESET_VECTORS)) {
+            startup_mark(k->id == K_RESET_VECTORS ? "first inter frame starts" : "first kernel enqueued (key frame coded by the host)");
+            seen = k->id == K_RESET_VECTORS ? 2 : 1;
+        }
+    }
     ScopedTimer timer(k->id >= K_COUNT_PROBS ? T_HOST_KERNEL : T_LAUNCH);
     return dispatch(k, gsz[0]);
 }
