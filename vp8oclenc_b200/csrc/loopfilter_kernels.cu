@@ -21,7 +21,9 @@
 // Arithmetic: the reference uses short8 lanes.  Every intermediate stays far inside int16
 // (pixels - 128 drift by at most a few dozen between the clamped stores, the largest product
 // is 27 * 127), so plain int arithmetic is bit-identical.
+#include <cstdlib>
 #include <mutex>
+#include <cooperative_groups.h>
 
 #include "common.cuh"
 
@@ -196,6 +198,34 @@ __device__ __forceinline__ int flag_acquire(volatile int *p) {
     return v;
 }
 
+// Hand-off between two CTAs of a cluster through distributed shared memory.  A cluster-scope release/acquire pair
+// compiles to MEMBAR.ALL.GPU / CCTL.IVALL on sm_100a -- far too heavy for a once-per-macroblock signal on the
+// critical warp -- so the lines travel as st.async stores that count bytes on an mbarrier of the receiving CTA:
+// the receiver waits for the barrier's phase (a CTA-local SYNCS.PHASECHK), no fence on either side.
+__device__ __forceinline__ uint32_t smem_addr(const volatile void *p) { return (uint32_t)__cvta_generic_to_shared(const_cast<void *>(p)); }
+__device__ __forceinline__ uint32_t cluster_addr(uint32_t local, int rank) {  // the same location in CTA `rank`
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_async_u32(uint32_t remote, uint32_t v, uint32_t remote_mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.u32 [%0], %1, [%2];" ::"r"(remote), "r"(v), "r"(remote_mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect(uint32_t mbar, int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t mbar, int parity) {
+    uint32_t done;
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+    return done != 0;
+}
+__device__ __forceinline__ int ld_acquire_cluster(uint32_t remote) {
+    int v;
+    asm volatile("ld.acquire.cluster.shared::cluster.s32 %0, [%1];" : "=r"(v) : "r"(remote) : "memory");
+    return v;
+}
+
 struct LFPlanes {
     uint8_t *ptr[3];
 };
@@ -210,9 +240,10 @@ struct LFSlot {
     int4 *lims;            // per macroblock {mb_lim, b_lim, int_lim, hev_thr | inner<<16}
     uint32_t *topq;        // [LF_TOPQ][4 lines][N/4 words]: the four pixel lines above each macroblock
     volatile int *flags;   // h_done, v_done, top_ready
+    uint64_t *mbar;        // [LF_TOPQ] one per ring slot: bytes of the lines above, sent by the CTA above (cluster hand-off)
 };
 __host__ __device__ inline size_t lf_slot_bytes(int n, int width) {
-    return (((size_t)n * (width + 4) + 15) & ~(size_t)15) + (size_t)(width / n) * 16 + (size_t)LF_TOPQ * n * 4 + 16;
+    return (((size_t)n * (width + 4) + 15) & ~(size_t)15) + (size_t)(width / n) * 16 + (size_t)LF_TOPQ * n * 4 + 16 + (size_t)LF_TOPQ * 8;
 }
 __device__ inline LFSlot lf_slot(unsigned char *base, int n, int width) {
     LFSlot s;
@@ -220,6 +251,7 @@ __device__ inline LFSlot lf_slot(unsigned char *base, int n, int width) {
     s.lims = reinterpret_cast<int4 *>(base + (((size_t)n * (width + 4) + 15) & ~(size_t)15));
     s.topq = reinterpret_cast<uint32_t *>(s.lims + width / n);
     s.flags = reinterpret_cast<volatile int *>(s.topq + LF_TOPQ * n);
+    s.mbar = reinterpret_cast<uint64_t *>(const_cast<int *>(s.flags) + 4);
     return s;
 }
 
@@ -245,7 +277,11 @@ __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p) {
 template <int N>
 __device__ void lf_plane_roles(uint8_t *__restrict__ frame, int width, int r, int ncols, bool row_below_exists,
                                int stop_below_cols, LFSlot sl, uint32_t *mail_row, const uint32_t *mail_above,
-                               unsigned tag, int role, int lane) {
+                               unsigned tag, int role, int lane, bool dsmem_up, int rank_below) {
+    // dsmem_up: the row above runs in the previous CTA of this cluster and sends the lines above every macroblock
+    // straight into this CTA's ring (topq), counted on the ring slot's mbarrier; rank_below >= 0: this row does the
+    // same for that CTA of the cluster.  Rows at a cluster border use the global mailbox.
+    const bool dsmem_down = rank_below >= 0;
     const int S = width + 4;
     const int y0 = r * N;
     uint8_t *strip = sl.strip;
@@ -279,8 +315,14 @@ __device__ void lf_plane_roles(uint8_t *__restrict__ frame, int width, int r, in
             }
             __syncwarp();
             if (lane == 0) flag_release(&flags[0], c + 1);  // h_done: macroblock c-1 is final now
-            if (r > 0) {
-                while (flag_acquire(&flags[2]) < c + 1) {}  // the lines above macroblock c are in the ring
+            if (r > 0) {  // the lines above macroblock c are in the ring
+                if (dsmem_up) {
+                    const uint32_t mb_slot = smem_addr(sl.mbar + (c % TOPQ));
+                    if (lane == 0) mbar_expect(mb_slot, 4 * N);
+                    while (!mbar_try_wait(mb_slot, (c / TOPQ) & 1)) {}
+                } else {
+                    while (flag_acquire(&flags[2]) < c + 1) {}
+                }
             }
             if (lane < N) {  // pass 2: one lane per pixel column, the whole column in registers
                 uint8_t *scol = strip + 4 + x0 + lane;
@@ -309,11 +351,13 @@ __device__ void lf_plane_roles(uint8_t *__restrict__ frame, int width, int r, in
                 }
             }
             __syncwarp();
-            if (lane == 0) flag_release(&flags[1], c + 1);  // v_done
+            // v_done.  (With dsmem_up the sender of the row above reads it to know a ring slot is free again: this
+            // warp's loads of the slot have long returned -- pass 2 consumed them -- when the flag is written.)
+            if (lane == 0) flag_release(&flags[1], c + 1);
         }
     } else if (role == 1) {
         // ---- receiver warp: the four lines above each macroblock, from the mailbox of the row above ----
-        if (r > 0) {
+        if (r > 0 && !dsmem_up) {
             for (int c = 0; c < ncols; ++c) {
                 while (c - flag_acquire(&flags[1]) >= TOPQ) {}  // ring slot free again
                 const uint32_t *m = mail_above + (size_t)c * 32 + lane;
@@ -335,6 +379,10 @@ __device__ void lf_plane_roles(uint8_t *__restrict__ frame, int width, int r, in
         }
     } else {
         // ---- sender warp: bottom lines of every finalised macroblock ----
+        int below_v_done = 0;  // last progress seen of the row below (ring flow control of the cluster hand-off)
+        const uint32_t topq_below = dsmem_down ? cluster_addr(smem_addr(topq), rank_below) : 0u;
+        const uint32_t mbar_below = dsmem_down ? cluster_addr(smem_addr(sl.mbar), rank_below) : 0u;
+        const uint32_t flags_below_v_done = dsmem_down ? cluster_addr(smem_addr(flags + 1), rank_below) : 0u;
         for (int c = 0; c < ncols; ++c) {
             // macroblock c is final once pass 1 of macroblock c+1 ran, the last one after its own pass 2
             if (c + 1 < ncols) {
@@ -343,7 +391,16 @@ __device__ void lf_plane_roles(uint8_t *__restrict__ frame, int width, int r, in
                 while (flag_acquire(&flags[1]) < ncols) {}
             }
             const bool consumer = row_below_exists && c < stop_below_cols;
-            if (consumer) {
+            if (consumer && dsmem_down) {
+                // straight into the ring of the CTA below: 4 lines x N/4 words, word k from lane k
+                while (c - below_v_done >= LF_TOPQ) below_v_done = ld_acquire_cluster(flags_below_v_done);
+                if (lane < N) {
+                    const int line = N - 4 + lane / (N / 4), wd = lane % (N / 4);
+                    st_async_u32(topq_below + 4u * (uint32_t)((c % LF_TOPQ) * N + lane),
+                                 *reinterpret_cast<const uint32_t *>(strip + line * S + 4 + c * N + 4 * wd),
+                                 mbar_below + 8u * (uint32_t)(c % LF_TOPQ));
+                }
+            } else if (consumer) {
                 // 4 lines x N/4 words, split in halves: word k -> lanes 2k, 2k+1 (N=8 uses lanes 0..15)
                 const int k = lane >> 1, h = lane & 1;
                 if (N == 16 || lane < 16) {
@@ -372,9 +429,33 @@ k_loop_filter(LFPlanes planes, int first_plane, int num_planes, const int *__res
     __shared__ int s_ticket, s_stop;
     const int mbw = luma_width / 16, mbh = luma_height / 16, mb_count = mbw * mbh;
     const int tid = threadIdx.x;
+    // A cluster of C CTAs takes C consecutive rows (one ticket per cluster): inside the cluster a row hands its bottom
+    // lines to the next one through distributed shared memory instead of the global mailbox.
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int crank = (int)cluster.block_rank(), csize = (int)cluster.num_blocks();
+    // slot ps starts after the slots before it (no pointer table: the accesses stay LDS/STS)
+    auto slot_of = [&](int ps) {
+        size_t off = 0;
+        for (int i = 0; i < ps; ++i) off += lf_slot_bytes(first_plane + i == 0 ? 16 : 8, first_plane + i == 0 ? luma_width : luma_width / 2);
+        return lf_slot(smem + off, first_plane + ps == 0 ? 16 : 8, first_plane + ps == 0 ? luma_width : luma_width / 2);
+    };
     if (tid == 0) {
-        s_ticket = atomicAdd(&ctrl[0], 1);  // rows start in ticket order: a row's predecessor is always running
+        if (crank == 0) s_ticket = atomicAdd(&ctrl[0], 1);  // clusters start in ticket order: a row's predecessor is always running
         s_stop = mb_count;
+    }
+    // progress flags: cleared before the cluster barrier, because the CTA above may write top_ready of this one
+    // as soon as it has passed that barrier
+    for (int ps = 0; ps < num_planes; ++ps) {
+        const LFSlot slot = slot_of(ps);
+        if (tid < 3) slot.flags[tid] = 0;
+        if (csize > 1 && tid >= 32 && tid < 32 + LF_TOPQ)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(slot.mbar + (tid - 32))) : "memory");
+    }
+    if (csize > 1) {
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        cluster.sync();
+        if (tid == 0 && crank != 0) s_ticket = *cluster.map_shared_rank(&s_ticket, 0);
     }
     __syncthreads();
     // "if (SD[i].loop_filter_level == 0) return;" ends the WHOLE plane at the first such macroblock
@@ -389,20 +470,18 @@ k_loop_filter(LFPlanes planes, int first_plane, int num_planes, const int *__res
         if (first < mb_count) atomicMin(&s_stop, first);
     }
     __syncthreads();
-    const int r = s_ticket, stop = s_stop;
-    if (r >= mbh) return;
-    const int ncols = max(0, min(mbw, stop - r * mbw));  // macroblocks of this row before the Q6 stop
-    if (ncols == 0) return;
+    const int r = s_ticket * csize + crank, stop = s_stop;
+    const int ncols = r < mbh ? max(0, min(mbw, stop - r * mbw)) : 0;  // macroblocks of this row before the Q6 stop
+    if (ncols == 0) {  // nothing to filter: nobody writes into this CTA (its predecessor sees below_cols == 0)
+        if (csize > 1) cluster.sync();
+        return;
+    }
     const int below_cols = max(0, min(mbw, stop - (r + 1) * mbw));
     const bool row_below = r + 1 < mbh;
+    const bool dsmem_up = csize > 1 && crank > 0 && r > 0;
+    const bool dsmem_down = csize > 1 && crank + 1 < csize && row_below;
 
     // ---- stage the strips and the per-macroblock limits of every plane ----
-    // slot ps starts after the slots before it (no pointer table: the accesses stay LDS/STS)
-    auto slot_of = [&](int ps) {
-        size_t off = 0;
-        for (int i = 0; i < ps; ++i) off += lf_slot_bytes(first_plane + i == 0 ? 16 : 8, first_plane + i == 0 ? luma_width : luma_width / 2);
-        return lf_slot(smem + off, first_plane + ps == 0 ? 16 : 8, first_plane + ps == 0 ? luma_width : luma_width / 2);
-    };
     for (int ps = 0; ps < num_planes; ++ps) {
         const int plane = first_plane + ps;
         const int n = plane == 0 ? 16 : 8;
@@ -423,7 +502,6 @@ k_loop_filter(LFPlanes planes, int first_plane, int num_planes, const int *__res
             slot.lims[c] = make_int4((short)sd->mbedge_limit, (short)sd->sub_bedge_limit, (short)sd->interior_limit,
                                           ((short)sd->hev_threshold & 0xffff) | (mb_mask[mb] != 0 ? 0x10000 : 0));
         }
-        if (tid < 3) slot.flags[tid] = 0;
     }
     __syncthreads();
 
@@ -437,12 +515,13 @@ k_loop_filter(LFPlanes planes, int first_plane, int num_planes, const int *__res
             uint32_t *mail_row = mail_plane + (size_t)r * mbw * 32;
             const uint32_t *mail_above = mail_plane + (size_t)(r - 1) * mbw * 32;  // only read when r > 0
             const LFSlot slot = slot_of(ps);
+            const int rank_below = dsmem_down ? crank + 1 : -1;
             if (plane == 0)
                 lf_plane_roles<16>(planes.ptr[0], luma_width, r, ncols, row_below, below_cols, slot, mail_row,
-                                   mail_above, tag, role, lane);
+                                   mail_above, tag, role, lane, dsmem_up, rank_below);
             else
                 lf_plane_roles<8>(planes.ptr[plane], luma_width / 2, r, ncols, row_below, below_cols, slot, mail_row,
-                                  mail_above, tag, role, lane);
+                                  mail_above, tag, role, lane, dsmem_up, rank_below);
         }
     }
     __syncthreads();
@@ -463,6 +542,7 @@ k_loop_filter(LFPlanes planes, int first_plane, int num_planes, const int *__res
             *reinterpret_cast<uint2 *>(frame + (size_t)(y0 + row) * width + 8 * xc) = make_uint2(s[0], s[1]);
         }
     }
+    if (csize > 1) cluster.sync();  // no CTA of a cluster leaves while a neighbour may still touch its shared memory
 }
 
 // one warp per macroblock: sum of |coefficient| over the positions the entropy coder will
@@ -574,8 +654,30 @@ static int launch_loop_filter(void *stream, LFPlanes p, int first_plane, int num
             return -(int)cudaGetLastError();
         c->smem_configured = smem;
     }
-    k_loop_filter<<<mbh, LF_THREADS, smem, st>>>(p, first_plane, num_planes, seg, mb_mask, SD, luma_w, luma_h, c->ctrl,
-                                                 c->mail, c->tag);
+    // clusters of LF_CLUSTER consecutive rows (VP8B200_LF_CLUSTER=1 switches the distributed-shared-memory hand-off off)
+    static const int cluster_rows = [] {
+        const char *e = getenv("VP8B200_LF_CLUSTER");
+        const int v = e ? atoi(e) : 8;
+        return v < 1 ? 1 : (v > 8 ? 8 : v);
+    }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((mbh + cluster_rows - 1) / cluster_rows * cluster_rows));
+    cfg.blockDim = dim3(LF_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cluster_rows;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int *ctrl = c->ctrl;
+    uint32_t *mail = c->mail;
+    unsigned tag = c->tag;
+    if (cudaLaunchKernelEx(&cfg, k_loop_filter, p, first_plane, num_planes, (const int *)seg, (const int *)mb_mask, SD, luma_w,
+                           luma_h, ctrl, mail, tag) != cudaSuccess)
+        return -(int)cudaGetLastError();
     VP8_LAUNCH_CHECK();
 }
 
