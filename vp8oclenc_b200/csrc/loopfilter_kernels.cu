@@ -230,8 +230,23 @@ struct LFPlanes {
     uint8_t *ptr[3];
 };
 
-// warps: 3 per plane slot (filter, receiver, sender); up to 3 plane slots per CTA
-constexpr int LF_THREADS = 288;
+// warps: 3 per plane slot (filter, receiver, sender); up to 3 plane slots per CTA.  The helper warps spin on flags
+// and on the mailbox; a warp that spins on the scheduler of a filter warp takes issue slots from the one warp the
+// whole wavefront waits for (28 % + 20 % of the kernel's executed instructions were those two loops).  So:
+// twelve warps, the luma filter warp alone on its scheduler (warps 4 and 8 idle), and the helpers back off with
+// nanosleep between polls.
+#ifndef VP8_LF_SPREAD
+#define VP8_LF_SPREAD 1
+#endif
+#ifndef VP8_LF_BACKOFF_NS
+#define VP8_LF_BACKOFF_NS 40
+#endif
+constexpr int LF_THREADS = VP8_LF_SPREAD ? 384 : 288;
+__device__ __forceinline__ void lf_backoff() {
+#if VP8_LF_BACKOFF_NS > 0
+    __nanosleep(VP8_LF_BACKOFF_NS);
+#endif
+}
 constexpr int LF_TOPQ = 8;  // depth of the top-line ring
 
 // shared-memory layout of one plane slot
@@ -359,12 +374,14 @@ __device__ void lf_plane_roles(uint8_t *__restrict__ frame, int width, int r, in
         // ---- receiver warp: the four lines above each macroblock, from the mailbox of the row above ----
         if (r > 0 && !dsmem_up) {
             for (int c = 0; c < ncols; ++c) {
-                while (c - flag_acquire(&flags[1]) >= TOPQ) {}  // ring slot free again
+                while (c - flag_acquire(&flags[1]) >= TOPQ) lf_backoff();  // ring slot free again
                 const uint32_t *m = mail_above + (size_t)c * 32 + lane;
                 uint32_t w;
-                do {
+                for (;;) {
                     w = ld_volatile_u32(m);
-                } while (!__all_sync(0xffffffffu, (w >> 16) == tag));
+                    if (__all_sync(0xffffffffu, (w >> 16) == tag)) break;
+                    lf_backoff();
+                }
                 // lane = 2*k + h holds pixels (2h, 2h+1) of word k of the 4 x N/4 word block (N=16),
                 // see the sender; reassemble whole words
                 const uint32_t other = __shfl_xor_sync(0xffffffffu, w, 1);
@@ -386,14 +403,17 @@ __device__ void lf_plane_roles(uint8_t *__restrict__ frame, int width, int r, in
         for (int c = 0; c < ncols; ++c) {
             // macroblock c is final once pass 1 of macroblock c+1 ran, the last one after its own pass 2
             if (c + 1 < ncols) {
-                while (flag_acquire(&flags[0]) < c + 2) {}
+                while (flag_acquire(&flags[0]) < c + 2) lf_backoff();
             } else {
-                while (flag_acquire(&flags[1]) < ncols) {}
+                while (flag_acquire(&flags[1]) < ncols) lf_backoff();
             }
             const bool consumer = row_below_exists && c < stop_below_cols;
             if (consumer && dsmem_down) {
                 // straight into the ring of the CTA below: 4 lines x N/4 words, word k from lane k
-                while (c - below_v_done >= LF_TOPQ) below_v_done = ld_acquire_cluster(flags_below_v_done);
+                while (c - below_v_done >= LF_TOPQ) {
+                    below_v_done = ld_acquire_cluster(flags_below_v_done);
+                    if (c - below_v_done >= LF_TOPQ) lf_backoff();
+                }
                 if (lane < N) {
                     const int line = N - 4 + lane / (N / 4), wd = lane % (N / 4);
                     st_async_u32(topq_below + 4u * (uint32_t)((c % LF_TOPQ) * N + lane),
@@ -508,7 +528,14 @@ k_loop_filter(LFPlanes planes, int first_plane, int num_planes, const int *__res
     // ---- the serial walk: warp w serves plane slot w/3 in role w%3 ----
     {
         const int warp = tid >> 5, lane = tid & 31;
+#if VP8_LF_SPREAD
+        // warp -> scheduler warp % 4:  0: luma filter alone | 1: U filter, U receiver, U sender | 2: the same for V |
+        // 3: luma receiver, luma sender
+        const int ps = (warp & 3) == 0 ? (warp == 0 ? 0 : 99) : ((warp & 3) == 3 ? (warp == 11 ? 99 : 0) : (warp & 3));
+        const int role = (warp & 3) == 3 ? 1 + (warp >> 2) : (warp >> 2);
+#else
         const int ps = warp / 3, role = warp % 3;
+#endif
         if (ps < num_planes) {
             const int plane = first_plane + ps;
             uint32_t *mail_plane = mail + (size_t)ps * mbh * mbw * 32;
