@@ -168,7 +168,7 @@ def reference_stages(stage_file, stamps):
         tot = sum(ms.get(n, 0.0) for n in names)
         out[stage] = tot / (inter if stage in ("motion_search", "predict_transform") else frames)
     per_inter = 1000.0 * (stamps[-1] - stamps[0]) / inter
-    out["host_rest"] = per_inter - sum(out.values())
+    out["host_rest"] = max(0.0, per_inter - sum(out.values()))  # (the key frames' denser entropy stage is in the average)
     out["frame"] = per_inter
     return {k: round(v, 3) for k, v in out.items()}
 
