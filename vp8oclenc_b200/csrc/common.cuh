@@ -97,8 +97,11 @@ __device__ __forceinline__ ColFeat col_features(int p0, int p1, int p2, int p3, 
     return f;
 }
 // pass 2 of weight4x4 on the intermediate o (rows 0 and 2 are the reference's values / 8)
+#ifndef VP8_COST_SAD
+#define VP8_COST_SAD 1
+#endif
 __device__ __forceinline__ int weight4x4_rows(const int (&o)[16]) {
-    int sum = 0;
+    int sum = 0, sum2 = 0;
 #pragma unroll
     for (int row = 0; row < 4; ++row) {
         const int a = o[4 * row] + o[4 * row + 3], d = o[4 * row] - o[4 * row + 3];
@@ -115,9 +118,19 @@ __device__ __forceinline__ int weight4x4_rows(const int (&o)[16]) {
             f1 = ((c * 17736 + d * 42816 + 12000) >> 16) + (d != 0);
             f3 = (d * 17736 - c * 42816 + 51000) >> 16;
         }
+#if VP8_COST_SAD
+        // |x| + acc is one VABSDIFF (x - 0, accumulate) instead of IABS + a share of an IADD3
+        if (row == 0) sum += abs(f0) >> 2; else sum = __sad(f0, 0, sum);
+        sum2 = __sad(f1, 0, sum2);
+        sum = __sad(f2, 0, sum);
+        sum2 = __sad(f3, 0, sum2);
+    }
+    return sum + sum2;
+#else
         sum += (row == 0 ? (abs(f0) >> 2) : abs(f0)) + abs(f1) + abs(f2) + abs(f3);
     }
     return sum;
+#endif
 }
 
 // Truncating x / q through m = magic(q): |x| * m >> 32 with the sign put back.  m * q = 2^32 + e with 0 <= e < q,

@@ -267,7 +267,7 @@ k_intra_frame(const uint8_t *__restrict__ cur_y, const uint8_t *__restrict__ cur
                     intra_fdct(res, f);
                     int wgt = abs(s16(f[0] / 4));
 #pragma unroll
-                    for (int i = 1; i < 16; ++i) wgt += abs(f[i]);
+                    for (int i = 1; i < 16; ++i) wgt = (int)__sad(f[i], 0, (unsigned)wgt);  // |f| + wgt: one VABSDIFF
                     key = (s16(wgt) << 4) | m;  // ties: the earlier mode
                 }
                 int best = key;

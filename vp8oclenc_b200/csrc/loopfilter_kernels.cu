@@ -33,19 +33,25 @@ __device__ __forceinline__ int c128(int v) { return min(max(v, -128), 127); }
 
 // branch-free on purpose: the lanes of the filtering warp take different decisions per pixel line,
 // short-circuit evaluation would serialise them
-__device__ __forceinline__ int lf_over(int a, int b, int lim) { return abs(a - b) > lim; }
+// (|a - b| is one VABSDIFF through __sad; the six interior terms meet in one maximum before the single compare)
+__device__ __forceinline__ int lf_ad(int a, int b) { return (int)__sad(a, b, 0u); }
+__device__ __forceinline__ int lf_over(int a, int b, int lim) { return lf_ad(a, b) > lim; }
 
 __device__ __forceinline__ int lf_filter_off(int p3, int p2, int p1, int p0, int q0, int q1, int q2, int q3, int e_lim,
                                              int i_lim) {
-    return lf_over(p3, p2, i_lim) | lf_over(p2, p1, i_lim) | lf_over(p1, p0, i_lim) | lf_over(q1, q0, i_lim) |
-           lf_over(q2, q1, i_lim) | lf_over(q3, q2, i_lim) | ((abs(p0 - q0) * 2 + (abs(p1 - q1) >> 1)) > e_lim);
+    const int inner = max(max(max(lf_ad(p3, p2), lf_ad(p2, p1)), lf_ad(p1, p0)),
+                          max(max(lf_ad(q1, q0), lf_ad(q2, q1)), lf_ad(q3, q2)));
+    return (inner > i_lim) | ((lf_ad(p0, q0) * 2 + (lf_ad(p1, q1) >> 1)) > e_lim);
+}
+__device__ __forceinline__ int lf_hev(int p1, int p0, int q0, int q1, int hev_thr) {
+    return max(lf_ad(p1, p0), lf_ad(q1, q0)) > hev_thr;
 }
 
 // macroblock edge (filter_mb_edge8, src/CPU_kernels.cl:829-883), one lane
 __device__ __forceinline__ void filter_mb_edge(int p3, int &p2, int &p1, int &p0, int &q0, int &q1, int &q2, int q3,
                                                int mb_lim, int int_lim, int hev_thr) {
     const int off = lf_filter_off(p3, p2, p1, p0, q0, q1, q2, q3, mb_lim, int_lim);
-    const int hev = lf_over(p1, p0, hev_thr) | lf_over(q1, q0, hev_thr);
+    const int hev = lf_hev(p1, p0, q0, q1, hev_thr);
     int w = c128(c128(p1 - q1) + 3 * (q0 - p0));
     w = off ? 0 : w;
     int a = hev ? w : 0;
@@ -69,7 +75,7 @@ __device__ __forceinline__ void filter_mb_edge(int p3, int &p2, int &p1, int &p0
 __device__ __forceinline__ void filter_b_edge(int p3, int p2, int &p1, int &p0, int &q0, int &q1, int q2, int q3,
                                               int b_lim, int int_lim, int hev_thr) {
     const int off = lf_filter_off(p3, p2, p1, p0, q0, q1, q2, q3, b_lim, int_lim);
-    const int hev = lf_over(p1, p0, hev_thr) | lf_over(q1, q0, hev_thr);
+    const int hev = lf_hev(p1, p0, q0, q1, hev_thr);
     int a = hev ? c128(p1 - q1) : 0;
     a = c128(a + 3 * (q0 - p0));
     a = off ? 0 : a;
@@ -96,8 +102,8 @@ __device__ __forceinline__ SpecEdge spec_b_edge(int p1, int p0, int q0, int q1, 
                                                 int hev_thr) {
     SpecEdge s;
     s.off = lf_over(p1, p0, int_lim) | lf_over(q1, q0, int_lim) | lf_over(q2, q1, int_lim) | lf_over(q3, q2, int_lim) |
-            ((abs(p0 - q0) * 2 + (abs(p1 - q1) >> 1)) > b_lim);
-    const int hev = lf_over(p1, p0, hev_thr) | lf_over(q1, q0, hev_thr);
+            ((lf_ad(p0, q0) * 2 + (lf_ad(p1, q1) >> 1)) > b_lim);
+    const int hev = lf_hev(p1, p0, q0, q1, hev_thr);
     int a = hev ? c128(p1 - q1) : 0;
     a = c128(a + 3 * (q0 - p0));
     const int b = c128(a + 3) >> 3;

@@ -250,8 +250,8 @@ k_mb_fused(const uint8_t *__restrict__ cur_y, const uint8_t *__restrict__ cur_u,
             for (int r = 0; r < 4; ++r) {
                 const uint32_t a = *reinterpret_cast<const uint32_t *>(&s_cur[warp][tile0 + (by * 4 + r) * n + bx * 4]);
                 const uint32_t b = *reinterpret_cast<const uint32_t *>(&s_rec[warp][tile0 + (by * 4 + r) * n + bx * 4]);
-                sc += (a & 255) + ((a >> 8) & 255) + ((a >> 16) & 255) + (a >> 24);
-                sr += (b & 255) + ((b >> 8) & 255) + ((b >> 16) & 255) + (b >> 24);
+                sc = (int)__dp4a(a, 0x01010101u, (unsigned)sc);  // sum of the four bytes, one instruction
+                sr = (int)__dp4a(b, 0x01010101u, (unsigned)sr);
             }
         }
         // segmented reductions: lanes 0-15 | 16-19 | 20-23
