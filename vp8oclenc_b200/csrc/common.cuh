@@ -49,7 +49,8 @@ static __constant__ const unsigned char c_inv_zigzag[16] = {0, 1, 5, 6, 2, 4, 7,
 __device__ __forceinline__ constexpr int inv_zz(int k) { return (int)((0xFEA9DB83C7426510ULL >> (4 * k)) & 15); }
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
-__device__ __forceinline__ int sat8(int v) { return min(max(v, 0), 255); }
+// clamp to 0..255 in one instruction: VIMNMX.RELU = max(min(v, 255), 0)
+__device__ __forceinline__ int sat8(int v) { return __vimin_s32_relu(v, 255); }
 
 // Block cost of a 4x4 residual r[row*4+col] (weight_opt, src/GPU_kernels.cl:85-190).
 // Pass 1 runs down the columns with the reference's register clobber (Q1): the "b1" term is

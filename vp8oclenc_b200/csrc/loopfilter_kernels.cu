@@ -54,19 +54,21 @@ __device__ __forceinline__ void filter_mb_edge(int p3, int &p2, int &p1, int &p0
     const int hev = lf_hev(p1, p0, q0, q1, hev_thr);
     int w = c128(c128(p1 - q1) + 3 * (q0 - p0));
     w = off ? 0 : w;
+    // (w is in -128..127 from here on: w + 3 and w + 4 can only leave the range at the top, and
+    // (27 w + 63) >> 7 and its siblings stay within -27..27 -- the reference's clamps there never act)
     int a = hev ? w : 0;
-    const int b = c128(a + 3) >> 3;
-    a = c128(a + 4) >> 3;
+    const int b = min(a + 3, 127) >> 3;
+    a = min(a + 4, 127) >> 3;
     q0 -= a;
     p0 += b;
     w = hev ? 0 : w;
-    a = c128((27 * w + 63) >> 7);
+    a = (27 * w + 63) >> 7;
     q0 -= a;
     p0 += a;
-    a = c128((18 * w + 63) >> 7);
+    a = (18 * w + 63) >> 7;
     q1 -= a;
     p1 += a;
-    a = c128((9 * w + 63) >> 7);
+    a = (9 * w + 63) >> 7;
     q2 -= a;
     p2 += a;
 }
@@ -79,8 +81,8 @@ __device__ __forceinline__ void filter_b_edge(int p3, int p2, int &p1, int &p0, 
     int a = hev ? c128(p1 - q1) : 0;
     a = c128(a + 3 * (q0 - p0));
     a = off ? 0 : a;
-    const int b = c128(a + 3) >> 3;
-    a = c128(a + 4) >> 3;
+    const int b = min(a + 3, 127) >> 3;  // (a is in -128..127: only the upper clamp can act)
+    a = min(a + 4, 127) >> 3;
     q0 -= a;
     p0 += b;
     a = (a + 1) >> 1;
