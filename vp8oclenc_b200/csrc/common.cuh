@@ -108,6 +108,27 @@ __device__ __forceinline__ int weight4x4_rows(const int (&o)[16]) {
         const int a = o[4 * row] + o[4 * row + 3], d = o[4 * row] - o[4 * row + 3];
         const int b = o[4 * row + 1] + o[4 * row + 2], c = o[4 * row + 1] - o[4 * row + 2];
         int f0, f1, f2, f3;
+#if VP8_COST_SAD
+        // |x| + acc is one VABSDIFF (x - 0, accumulate) instead of IABS + a share of an IADD3; the "+ (d != 0)" of f1
+        // rides in the VABSDIFF's second operand: |t + (d != 0)| = |t - m| with m = d ? -1 : 0
+        if (row & 1) {
+            f0 = (a + b + 7) >> 4;
+            f2 = (a - b + 7) >> 4;
+            f1 = (c * 2217 + d * 5352 + 12000) >> 16;
+            f3 = (d * 2217 - c * 5352 + 51000) >> 16;
+        } else {
+            f0 = (a + b) >> 1;
+            f2 = (a - b) >> 1;
+            f1 = (c * 17736 + d * 42816 + 12000) >> 16;
+            f3 = (d * 17736 - c * 42816 + 51000) >> 16;
+        }
+        if (row == 0) sum += abs(f0) >> 2; else sum = __sad(f0, 0, sum);
+        sum2 = __sad(f1, d != 0 ? -1 : 0, sum2);
+        sum = __sad(f2, 0, sum);
+        sum2 = __sad(f3, 0, sum2);
+    }
+    return sum + sum2;
+#else
         if (row & 1) {
             f0 = (a + b + 7) >> 4;
             f2 = (a - b + 7) >> 4;
@@ -119,15 +140,6 @@ __device__ __forceinline__ int weight4x4_rows(const int (&o)[16]) {
             f1 = ((c * 17736 + d * 42816 + 12000) >> 16) + (d != 0);
             f3 = (d * 17736 - c * 42816 + 51000) >> 16;
         }
-#if VP8_COST_SAD
-        // |x| + acc is one VABSDIFF (x - 0, accumulate) instead of IABS + a share of an IADD3
-        if (row == 0) sum += abs(f0) >> 2; else sum = __sad(f0, 0, sum);
-        sum2 = __sad(f1, 0, sum2);
-        sum = __sad(f2, 0, sum);
-        sum2 = __sad(f3, 0, sum2);
-    }
-    return sum + sum2;
-#else
         sum += (row == 0 ? (abs(f0) >> 2) : abs(f0)) + abs(f1) + abs(f2) + abs(f3);
     }
     return sum;

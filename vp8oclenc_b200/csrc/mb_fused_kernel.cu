@@ -268,9 +268,10 @@ k_mb_fused(const uint8_t *__restrict__ cur_y, const uint8_t *__restrict__ cur_u,
         float M1[3], M2[3];
 #pragma unroll
         for (int p = 0; p < 3; ++p) {
-            const float area = p == 0 ? 256.0f : 64.0f;
-            M1[p] = __fdiv_rn((float)sumc[p], area);
-            M2[p] = __fdiv_rn((float)sumr[p], area);
+            // (x / 256 and x / 64 are exact scalings: the correctly rounded quotient is the product with 2^-8 / 2^-6)
+            const float inv_area = p == 0 ? 0.00390625f : 0.015625f;
+            M1[p] = __fmul_rn((float)sumc[p], inv_area);
+            M2[p] = __fmul_rn((float)sumr[p], inv_area);
         }
         // 36 ordered chains: quantity qn (0 var(cur), 1 var(rec), 2 cov) x float4 lane kk, per plane.
         // lanes 0-11: luma (64 elements each); lanes 12-23: U then V (16 elements each).
@@ -350,13 +351,13 @@ k_mb_fused(const uint8_t *__restrict__ cur_y, const uint8_t *__restrict__ cur_u,
 #pragma unroll
         for (int p = 0; p < 3; ++p) {
             const int base = p == 0 ? 0 : 12;
-            const float area = p == 0 ? 256.0f : 64.0f;
+            const float inv_area = p == 0 ? 0.00390625f : 0.015625f;  // exact, as above
             const float v1 = p == 2 ? __shfl_sync(0xffffffffu, tot1, base) : __shfl_sync(0xffffffffu, tot0, base);
             const float v2 = p == 2 ? __shfl_sync(0xffffffffu, tot1, base + 4) : __shfl_sync(0xffffffffu, tot0, base + 4);
             const float cv = p == 2 ? __shfl_sync(0xffffffffu, tot1, base + 8) : __shfl_sync(0xffffffffu, tot0, base + 8);
-            float D = __fdiv_rn(v1, area);
-            D = __fadd_rn(D, __fdiv_rn(v2, area));
-            float C = __fdiv_rn(cv, area);
+            float D = __fmul_rn(v1, inv_area);
+            D = __fadd_rn(D, __fmul_rn(v2, inv_area));
+            float C = __fmul_rn(cv, inv_area);
             const float c1 = __fmul_rn(__fmul_rn(__fmul_rn(0.01f, 0.01f), 255.0f), 255.0f);
             const float c2 = __fmul_rn(__fmul_rn(__fmul_rn(0.03f, 0.03f), 255.0f), 255.0f);
             const float num = __fmul_rn(__fmaf_rn(M1[p], __fmul_rn(M2[p], 2.0f), c1), __fmaf_rn(C, 2.0f, c2));
