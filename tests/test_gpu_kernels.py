@@ -322,6 +322,22 @@ def test_loop_filter_three_planes_1080p(eng):
     assert np.array_equal(ya, host(dy)) and np.array_equal(ua, host(du)) and np.array_equal(va, host(dv))
 
 
+@pytest.mark.parametrize("cluster", ["1", "2", "5"])
+def test_loop_filter_other_cluster_sizes(cluster):
+    """the hand-off between rows has two forms: distributed shared memory inside a cluster of rows, the global mailbox
+    at cluster borders (and everywhere with VP8B200_LF_CLUSTER=1).  The default (8) is what every other test runs;
+    here the same loop-filter cases run with no clusters, with pairs, and with a size that does not divide the rows
+    (the variable is read once per process, hence the child process)."""
+    import subprocess
+    import sys
+    env = dict(os.environ, VP8B200_LF_CLUSTER=cluster)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k",
+                        "test_loop_filter and not other_cluster", "-p", "no:cacheprovider"],
+                       env=env, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-500:]
+
+
 @pytest.mark.parametrize("w,h", [(352, 288), (208, 176), (1920, 1088)])
 def test_luma_search_2step_tma_variant_identical(w, h):
     """the TMA-staged experiment kernel (vp8b200_experiment_search_2step_tma: box copies out of a replicate-padded
