@@ -192,3 +192,25 @@ def test_segments_equal_serial_encode_cuda_shim(tmp_path):
     if not os.path.exists(segments.HOST_BIN):
         pytest.skip("host binary not built")
     _check(str(tmp_path), segments.SHIM_DIR, segments.HOST_BIN, per_device=3)
+
+
+def test_reference_stage_split_of_the_cpu_baseline(tmp_path):
+    """bench.py's per-stage split of the reference on the CPU: the per-kernel wall times the
+    reference runtime writes (VP8CL_STAGES) are grouped into motion search / predict + transform / loop filter /
+    entropy, search and transform averaged over the inter frames only, and what is left of a frame is the host"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    f = tmp_path / "stages.txt"
+    f.write_text("total_wall 1000.0\nluma_search_1step 50 300.0\nluma_search_2step 10 500.0\ndct4x4 40 40.0\n"
+                 "loop_filter_frame_luma 5 55.0\nencode_coefficients 5 22.0\ncount_probs 5 11.0\nunknown_kernel 1 9.0\n")
+    stamps = [0.0, 0.25, 0.5, 0.75, 1.0]  # 1 key + 4 inter frames, 250 ms each
+    st = bench.reference_stages(str(f), stamps)
+    assert st["motion_search"] == pytest.approx(800.0 / 4)
+    assert st["predict_transform"] == pytest.approx(40.0 / 4)
+    assert st["loop_filter"] == pytest.approx(55.0 / 5)
+    assert st["entropy"] == pytest.approx(33.0 / 5)
+    assert st["frame"] == pytest.approx(250.0)
+    assert st["host_rest"] == pytest.approx(250.0 - 200.0 - 10.0 - 11.0 - 6.6, abs=1e-3)
+    assert bench.reference_stages(str(tmp_path / "missing.txt"), stamps) is None
