@@ -19,3 +19,8 @@ for r in range(4):
     for c in (5, 6, 60):
         d = np.diff(t[r, c, :15]) / 1000.0
         print(r, c, " ".join("%5.2f" % x for x in d))
+ph = np.zeros((10, 8), dtype=np.int64)
+print(lib.vp8b200_intra_debug_phases(ph.ctypes.data_as(ctypes.c_void_p)))
+print("cycles inside the steps of macroblock (0,5): edges | predict+fdct+weight | min | winner: quantise, reconstruct, store")
+for t in range(10):
+    print(t, " ".join("%6d" % x for x in np.diff(ph[t, :5])), "  -> next step %6d" % ((ph[t + 1, 0] - ph[t, 4]) if t < 9 else 0))

@@ -118,6 +118,40 @@ __device__ __forceinline__ void intra_quant_recon(int (&f)[16], const int (&pred
     }
 }
 
+// The same on the sixteen lanes of a half-warp, lane i owning coefficient / pixel i (i = 4 row + column): returns the
+// reconstructed pixel and stores the quantised coefficient at its zig-zag position of dst (if not null).  Every lane
+// of the warp has to call it (shuffles in segments of 16).
+__device__ __forceinline__ int intra_quant_recon_lane(int f, int pred, int i, int dc_q, int ac_q, uint32_t m_dc, uint32_t m_ac,
+                                                      int16_t *dst) {
+    const int q = i == 0 ? dc_q : ac_q, hq = q / 2;
+    const int own = s16(f + (f < 0 ? -hq : hq));
+    const int ten = __shfl_sync(0xffffffffu, own, 10, 16);  // coefficient 11 rounds the way the rounded coefficient 10 points
+    const int r = i == 11 ? s16(f + (ten < 0 ? -hq : hq)) : own;
+    const int qv = div_magic(r, i == 0 ? m_dc : m_ac);
+    if (dst) dst[(int)((0xFEA9DB83C7426510ull >> (4 * i)) & 15)] = (int16_t)qv;  // inverse of the zig-zag scan
+    const int dq = qv * q;
+    const int col = i & 3, row = i >> 2;
+    {   // vertical pass: the column's four coefficients
+        const int i0 = __shfl_sync(0xffffffffu, dq, col, 16), i4 = __shfl_sync(0xffffffffu, dq, 4 + col, 16);
+        const int i8 = __shfl_sync(0xffffffffu, dq, 8 + col, 16), i12 = __shfl_sync(0xffffffffu, dq, 12 + col, 16);
+        const int a = i0 + i8, b = i0 - i8;
+        const int c = ((i4 * 35468) >> 16) - (i12 + ((i12 * 20091) >> 16));
+        const int d = (i4 + ((i4 * 20091) >> 16)) + ((i12 * 35468) >> 16);
+        const int outer = (row == 0 || row == 3), p = outer ? a : b, s = outer ? d : c;
+        f = s16(row < 2 ? (row == 0 ? p + s : p + s) : p - s);  // rows 0..3: a + d, b + c, b - c, a - d
+    }
+    {   // horizontal pass: the line's four values
+        const int p0 = __shfl_sync(0xffffffffu, f, 4 * row, 16), p1 = __shfl_sync(0xffffffffu, f, 4 * row + 1, 16);
+        const int p2 = __shfl_sync(0xffffffffu, f, 4 * row + 2, 16), p3 = __shfl_sync(0xffffffffu, f, 4 * row + 3, 16);
+        const int a = p0 + p2, b = p0 - p2;
+        const int c = ((p1 * 35468) >> 16) - (p3 + ((p3 * 20091) >> 16));
+        const int d = (p1 + ((p1 * 20091) >> 16)) + ((p3 * 35468) >> 16);
+        const int outer = (col == 0 || col == 3), p = outer ? a : b, s = outer ? d : c;
+        const int v = col < 2 ? p + s : p - s;  // columns 0..3: a + d, b + c, b - c, a - d
+        return sat8(s16(((v + 4) >> 3) + pred));
+    }
+}
+
 // the quantised block in zig-zag order as eight packed words
 __device__ __forceinline__ void store_zigzag(int16_t *dst, const int (&f)[16]) {
     constexpr int zz[16] = {0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7, 11, 14, 15};
@@ -148,7 +182,11 @@ struct IntraQuants { int y_dc, y_ac, uv_dc, uv_ac; };
 // ctrl[0] = ticket, ctrl[1 + r] = luma macroblocks finished in row r, ctrl[1 + mbh + r] = chroma macroblocks finished
 #if defined(INTRA_EXP_TIMELINE)
 __device__ unsigned long long g_timeline[4][128][16];
+__device__ long long g_phase[10][8];  // clock64 inside the ten sub-block steps of macroblock (0, 5)
+#define PHASE_MARK(k) do { if (lane == 0 && r == 0 && c == 5) g_phase[t][k] = clock64(); } while (0)
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#else
+#define PHASE_MARK(k) do { } while (0)
 #endif
 __global__ void __launch_bounds__(64)
 k_intra_frame(const uint8_t *__restrict__ cur_y, const uint8_t *__restrict__ cur_u, const uint8_t *__restrict__ cur_v,
@@ -164,6 +202,7 @@ k_intra_frame(const uint8_t *__restrict__ cur_y, const uint8_t *__restrict__ cur
     __shared__ __align__(16) uint8_t ty[17][28];
     __shared__ __align__(16) uint8_t sy[16][16];  // source luma
     __shared__ int s_edge[2][16];      // per half-warp: L3 L2 L1 L0 P A0..A7, DC value
+    __shared__ __align__(16) int s_blk[2][32];  // per half-warp: the winning mode's coefficients and predictor
     // the tap table, transposed ([pixel][mode]): the ten lanes of a half-warp read ten neighbouring entries (from
     // constant memory their ten different addresses would be served one after the other)
     __shared__ unsigned short s_taps[16][16];
@@ -230,6 +269,7 @@ k_intra_frame(const uint8_t *__restrict__ cur_y, const uint8_t *__restrict__ cur
                 const int br = br0 + h, bc = t - 2 * br;
                 const bool valid = h < nvalid && bc >= 0 && bc <= 3;
                 const int y0 = 4 * br, x0 = 4 * bc;
+                PHASE_MARK(0);
                 if (valid && m < 14) {
                     // edge pixels of the sub-block out of the tile: m = 0..3 -> L3..L0, 4 -> P, 5..12 -> A0..A7
                     int v;
@@ -247,6 +287,7 @@ k_intra_frame(const uint8_t *__restrict__ cur_y, const uint8_t *__restrict__ cur
                     s_edge[h][13] = dc >> 3;
                 }
                 __syncwarp();
+                PHASE_MARK(1);
                 int pred[16], f[16];
                 int key = 0x7fffffff;
                 if (valid && m < 10) {
@@ -270,20 +311,31 @@ k_intra_frame(const uint8_t *__restrict__ cur_y, const uint8_t *__restrict__ cur
                     for (int i = 1; i < 16; ++i) wgt = (int)__sad(f[i], 0, (unsigned)wgt);  // |f| + wgt: one VABSDIFF
                     key = (s16(wgt) << 4) | m;  // ties: the earlier mode
                 }
+                PHASE_MARK(2);
                 int best = key;
 #pragma unroll
                 for (int o = 8; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+                PHASE_MARK(3);
+                // The winning lane hands its coefficients and predictor to the sixteen lanes of its half-warp: quantising,
+                // the inverse transform (two passes, each lane one output, inputs by shuffles) and the stores on sixteen
+                // lanes instead of one (this tail was 58 % of a step when the winner did it alone).
                 if (valid && key == best) {  // exactly one lane of the half-warp
-                    int out[16];
-                    intra_quant_recon(f, pred, out, q.y_dc, q.y_ac, m_y_dc, m_y_ac);
+                    int4 *blk = reinterpret_cast<int4 *>(s_blk[h]);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        *reinterpret_cast<uint32_t *>(&ty[1 + y0 + i][XO + x0]) =
-                            (uint32_t)out[4 * i] | ((uint32_t)out[4 * i + 1] << 8) | ((uint32_t)out[4 * i + 2] << 16) | ((uint32_t)out[4 * i + 3] << 24);
-                    store_zigzag(MB + (size_t)mb * 400 + 16 * (4 * br + bc), f);
+                    for (int i = 0; i < 4; ++i) {
+                        blk[i] = make_int4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+                        blk[4 + i] = make_int4(pred[4 * i], pred[4 * i + 1], pred[4 * i + 2], pred[4 * i + 3]);
+                    }
                     modes[16 * mb + 4 * br + bc] = m;
                 }
                 __syncwarp();
+                {
+                    const int out = intra_quant_recon_lane(s_blk[h][m], s_blk[h][16 + m], m, q.y_dc, q.y_ac, m_y_dc, m_y_ac,
+                                                           valid ? MB + (size_t)mb * 400 + 16 * (4 * br + bc) : nullptr);
+                    if (valid) ty[1 + y0 + (m >> 2)][XO + x0 + (m & 3)] = (uint8_t)out;
+                }
+                __syncwarp();
+                PHASE_MARK(4);
 #if defined(INTRA_EXP_TIMELINE)
                 if (lane == 0 && r < 4 && c < 128) g_timeline[r][c][3 + t] = gtime();
 #endif
@@ -365,6 +417,9 @@ using namespace vp8;
 #if defined(INTRA_EXP_TIMELINE)
 extern "C" int vp8b200_intra_debug_timeline(unsigned long long *out) {
     return (int)cudaMemcpyFromSymbol(out, g_timeline, sizeof(g_timeline));
+}
+extern "C" int vp8b200_intra_debug_phases(long long *out) {
+    return (int)cudaMemcpyFromSymbol(out, g_phase, sizeof(g_phase));
 }
 #endif
 extern "C" size_t vp8b200_intra_frame_scratch_bytes(int width, int height) {
