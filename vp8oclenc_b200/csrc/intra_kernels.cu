@@ -205,11 +205,21 @@ k_intra_frame(const uint8_t *__restrict__ cur_y, const uint8_t *__restrict__ cur
     __shared__ __align__(16) int s_blk[2][32];  // per half-warp: the winning mode's coefficients and predictor
     // the tap table, transposed ([pixel][mode]): the ten lanes of a half-warp read ten neighbouring entries (from
     // constant memory their ten different addresses would be served one after the other)
-    __shared__ unsigned short s_taps[16][16];
+    __shared__ uint32_t s_idx4[4][16];  // per mode: for each predicted pixel the entry of s_val it is (bytes, four pixels per word)
+    __shared__ int s_val[2][28];        // per half-warp: the values a directional predictor can be, see below
     __shared__ uint8_t tc[2][9][12];   // chroma tiles with border, per plane
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) s_row = atomicAdd(&ctrl[0], 1);
-    for (int i = tid; i < 160; i += 64) s_taps[i & 15][i >> 4] = c_intra_taps.t[i >> 4][i & 15];
+    // Every directional predictor pixel is (E[a] + 2 E[b] + E[c] + 2) >> 2 over the 13 edge pixels E (c_intra_taps), and
+    // only 27 different values occur per sub-block: T3[k] = the three-tap average centred on E[k] with the ends
+    // replicated (k = 0..12), T2[k] = (E[k] + E[k+1] + 1) >> 1 (k = 0..11, stored at 13 + k), the DC value (25) and E[0]
+    // itself (26).  The half-warp computes them once per sub-block; a mode's pixel is then one indexed load.
+    for (int i = tid; i < 160; i += 64) {
+        const int mode = i >> 4, px = i & 15, t = c_intra_taps.t[mode][px];
+        const int a = t & 15, b = (t >> 4) & 15, c3 = t >> 8;
+        const int idx = (a == b && b == c3) ? (a == 13 ? 25 : 26) : (a == c3 ? 13 + min(a, b) : (b == c3 ? (a < b ? 12 : 0) : min(a, c3) + 1));
+        reinterpret_cast<uint8_t *>(&s_idx4[px >> 2][mode])[px & 3] = (uint8_t)idx;
+    }
     __syncthreads();
     const int r = s_row;
     if (r >= mbh) return;
@@ -270,21 +280,25 @@ k_intra_frame(const uint8_t *__restrict__ cur_y, const uint8_t *__restrict__ cur
                 const bool valid = h < nvalid && bc >= 0 && bc <= 3;
                 const int y0 = 4 * br, x0 = 4 * bc;
                 PHASE_MARK(0);
-                if (valid && m < 14) {
+                {
                     // edge pixels of the sub-block out of the tile: m = 0..3 -> L3..L0, 4 -> P, 5..12 -> A0..A7
-                    int v;
-                    if (m < 4) v = ty[1 + y0 + (3 - m)][XO - 1 + x0];
-                    else if (m == 4) v = ty[y0][XO - 1 + x0];
-                    else if (m < 13) v = ty[y0][XO + x0 + (m - 5)];
-                    else v = 0;
-                    s_edge[h][m] = v;
-                }
-                __syncwarp();
-                if (valid && m == 13) {
-                    int dc = 4;
+                    int v = 0;
+                    if (valid && m < 13) {
+                        if (m < 4) v = ty[1 + y0 + (3 - m)][XO - 1 + x0];
+                        else if (m == 4) v = ty[y0][XO - 1 + x0];
+                        else v = ty[y0][XO + x0 + (m - 5)];
+                    }
+                    const int up = __shfl_sync(0xffffffffu, v, max(m - 1, 0), 16), dn = __shfl_sync(0xffffffffu, v, min(m + 1, 12), 16);
+                    int dc = (m < 4 || (m >= 5 && m < 9)) ? v : 0;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) dc += s_edge[h][i] + s_edge[h][5 + i];
-                    s_edge[h][13] = dc >> 3;
+                    for (int o = 8; o > 0; o >>= 1) dc += __shfl_xor_sync(0xffffffffu, dc, o);
+                    if (valid && m < 13) {
+                        s_edge[h][m] = v;  // (B_TM_PRED works on the pixels themselves)
+                        s_val[h][m] = (up + 2 * v + dn + 2) >> 2;
+                        if (m < 12) s_val[h][13 + m] = (v + dn + 1) >> 1;
+                        if (m == 0) s_val[h][26] = v;
+                    }
+                    if (valid && m == 13) s_val[h][25] = (dc + 4) >> 3;
                 }
                 __syncwarp();
                 PHASE_MARK(1);
@@ -298,9 +312,10 @@ k_intra_frame(const uint8_t *__restrict__ cur_y, const uint8_t *__restrict__ cur
                         for (int i = 0; i < 16; ++i) pred[i] = sat8(s_edge[h][5 + (i & 3)] + s_edge[h][3 - (i >> 2)] - P);
                     } else {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const int tp = s_taps[i][m];
-                            pred[i] = (s_edge[h][tp & 15] + 2 * s_edge[h][(tp >> 4) & 15] + s_edge[h][tp >> 8] + 2) >> 2;
+                        for (int j = 0; j < 4; ++j) {
+                            const uint32_t ix = s_idx4[j][m];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) pred[4 * j + k] = s_val[h][(ix >> (8 * k)) & 255];
                         }
                     }
 #pragma unroll
