@@ -141,6 +141,32 @@ struct StageScope {
     }
 };
 
+// ---- crash report: a SIGSEGV of the reference (host code or kernels on the CPU) prints where it happened ----------
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+static const char *volatile g_running_kernel = nullptr;
+static void crash_report(int sig, siginfo_t *info, void *) {
+    char line[256];
+    const char *k = g_running_kernel;
+    const int n = snprintf(line, sizeof(line), "vp8ref runtime: signal %d at address %p, kernel %s\n", sig, info ? info->si_addr : nullptr, k ? k : "(host code)");
+    if (n > 0) (void)!write(2, line, (size_t)n);
+    void *frames[48];
+    backtrace_symbols_fd(frames, backtrace(frames, 48), 2);
+    signal(sig, SIG_DFL);
+    raise(sig);
+}
+static void crash_report_init() {
+    static bool done = false;
+    if (done) return;
+    done = true;
+    struct sigaction sa = {};
+    sa.sa_sigaction = crash_report;
+    sa.sa_flags = SA_SIGINFO;
+    sigaction(SIGSEGV, &sa, nullptr);
+    sigaction(SIGBUS, &sa, nullptr);
+}
+
 extern "C" const clc::kernel_desc vp8ref_gpu_kernels[];
 extern "C" const clc::kernel_desc vp8ref_cpu_kernels[];
 
@@ -155,6 +181,19 @@ struct _cl_mem {
     unsigned char *data;
     clc::image2d img;
 };
+// The reference's search kernels read the previous frame WITHOUT clamping the candidate position (candidates that
+// hang over the edge can never win, so what they read does not matter; src/GPU_kernels.cl:459-560): a few rows before
+// and after the plane.  On a GPU that lands in neighbouring allocations; here a large plane is its own mmap and the
+// read can hit an unmapped page -- the 2160p encode died with SIGSEGV about once in eight runs (luma_search_1step).
+// Every object therefore gets zero-filled slack on both sides.
+static const size_t kSlack = 1u << 20;
+static unsigned char *alloc_with_slack(size_t size) {
+    unsigned char *base = (unsigned char *)calloc(size + 2 * kSlack, 1);
+    return base ? base + kSlack : nullptr;
+}
+static void free_with_slack(unsigned char *data) {
+    if (data) free(data - kSlack);
+}
 struct _cl_program { bool is_gpu_program; };
 struct _cl_kernel {
     const clc::kernel_desc *desc;
@@ -180,6 +219,7 @@ extern "C" {
 cl_int clGetPlatformIDs(cl_uint num_entries, cl_platform_id *platforms, cl_uint *num_platforms) {
     gaps_init();
     stages_init();
+    crash_report_init();
     if (num_platforms) *num_platforms = 1;
     if (platforms && num_entries >= 1) platforms[0] = &g_platform;
     return CL_SUCCESS;
@@ -236,7 +276,7 @@ cl_mem clCreateBuffer(cl_context, cl_mem_flags, size_t size, void *host_ptr, cl_
     m->is_image = false;
     m->size = size;
     trace_rec(0, m->index, 0, size, nullptr);
-    m->data = (unsigned char *)calloc(size ? size : 1, 1);
+    m->data = alloc_with_slack(size);
     if (host_ptr && m->data) memcpy(m->data, host_ptr, size);
     if (err) *err = m->data ? CL_SUCCESS : CL_MEM_OBJECT_ALLOCATION_FAILURE;
     return m;
@@ -254,7 +294,7 @@ cl_mem clCreateImage2D(cl_context, cl_mem_flags, const cl_image_format *fmt, siz
     m->is_image = true;
     m->size = w * h;
     trace_rec(1, m->index, w, h, nullptr);
-    m->data = (unsigned char *)calloc(m->size ? m->size : 1, 1);
+    m->data = alloc_with_slack(m->size);
     m->img.data = m->data;
     m->img.width = (int)w;
     m->img.height = (int)h;
@@ -264,7 +304,7 @@ cl_mem clCreateImage2D(cl_context, cl_mem_flags, const cl_image_format *fmt, siz
 
 cl_int clReleaseMemObject(cl_mem m) {
     if (!m) return CL_INVALID_MEM_OBJECT;
-    free(m->data);
+    free_with_slack(m->data);
     delete m;
     return CL_SUCCESS;
 }
@@ -316,6 +356,8 @@ cl_int clEnqueueNDRangeKernel(cl_command_queue, cl_kernel k, cl_uint dim, const 
     if (!k) return CL_INVALID_KERNEL;
     if (dim != 1) return CL_INVALID_WORK_DIMENSION;
     StageScope stage_scope(k->desc->name);
+    g_running_kernel = k->desc->name;
+    struct KernelNameScope { ~KernelNameScope() { g_running_kernel = nullptr; } } kernel_name_scope;
     const int n = k->desc->nargs;
     void *resolved[24];
     void *argv[24];

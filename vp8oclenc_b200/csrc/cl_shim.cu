@@ -727,9 +727,16 @@ static void maybe_pin(const void *ptr, size_t size) {
         if (r.base == (const char *)ptr && r.bytes == size) {
             if (!r.tried && ++r.seen >= 2) {
                 const size_t page = (size_t)sysconf(_SC_PAGESIZE);
-                const size_t lo = (size_t)ptr / page * page, hi = ((size_t)ptr + size + page - 1) / page * page;
+                size_t lo = (size_t)ptr / page * page, hi = ((size_t)ptr + size + page - 1) / page * page;
                 r.tried = true;  // (once, whatever the outcome)
-                if (cudaHostRegister((void *)lo, hi - lo, cudaHostRegisterDefault) == cudaSuccess) {
+                // pages an earlier registration already covers (the neighbouring plane's rounded edge) are left out:
+                // the runtime refuses a range that overlaps a registered one
+                for (const PinnedRange &o : g_pin_ranges) {
+                    if (!o.pinned) continue;
+                    if ((size_t)o.lo <= lo && (size_t)o.hi > lo) lo = (size_t)o.hi < hi ? (size_t)o.hi : hi;
+                    if ((size_t)o.lo < hi && (size_t)o.hi >= hi) hi = (size_t)o.lo > lo ? (size_t)o.lo : lo;
+                }
+                if (hi > lo && cudaHostRegister((void *)lo, hi - lo, cudaHostRegisterDefault) == cudaSuccess) {
                     r.pinned = true;
                     r.lo = (const char *)lo;
                     r.hi = (const char *)hi;
