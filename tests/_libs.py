@@ -78,6 +78,8 @@ def oracle():
 
 def ref_intra():
     """ctypes handle of oracle/_ref/libref_intra.so (the reference's own intra path, oracle/ref_intra.cpp) or None"""
+    if os.environ.get("VP8_NO_REF"):
+        return None
     so = os.path.join(ORACLE_DIR, "_ref", "libref_intra.so")
     if not os.path.exists(so) and os.path.isdir("/root/reference/src"):
         subprocess.call(["make", "-C", ORACLE_DIR, "ref"], stdout=subprocess.DEVNULL)
@@ -86,6 +88,8 @@ def ref_intra():
 
 def ref():
     global _ref, _ref_tried
+    if os.environ.get("VP8_NO_REF"):  # tests/test_oracle_vs_golden.py: behave as on a machine without the reference
+        return None
     if not _ref_tried:
         _ref_tried = True
         so = os.path.join(ORACLE_DIR, "_ref", "libOpenCL.so.1")
@@ -137,3 +141,41 @@ def ref_run(name, global_size, local_size, args):
     argv = (ctypes.c_void_p * len(slots))(*slots)
     rc = lib.vp8ref_run_kernel(name.encode(), int(global_size), int(local_size), argv)
     assert rc == 0, "reference kernel %s not found" % name
+
+
+class GoldenNumpy:
+    """numpy stand-in for tests/test_oracle_vs_ref.py (VP8_GOLDEN=record:<file> | check:<file>).  Those tests compare
+    `np.array_equal(oracle_output, reference_output)`.  In record mode (reference available) the comparison is the real
+    one and the sha256 of every REFERENCE output is stored per test; in check mode (no reference needed) the ORACLE
+    output's sha256 has to equal the stored one.  The committed table is tests/golden/reference_kernels.json; the
+    script that makes it is tests/golden/make_golden.py."""
+
+    def __init__(self, real, spec, oracle_first=True):
+        import atexit
+        import json
+        self._np = real
+        self._oracle_first = oracle_first  # which argument of array_equal is the oracle's output
+        self._mode, self._path = spec.split(":", 1)
+        self._table = {}
+        self._count = {}
+        if self._mode == "check":
+            self._table = json.load(open(self._path))
+        else:
+            atexit.register(lambda: json.dump(self._table, open(self._path, "w"), indent=0, sort_keys=True))
+
+    def __getattr__(self, name):
+        return getattr(self._np, name)
+
+    def array_equal(self, a, b):
+        import hashlib
+        key = os.environ.get("PYTEST_CURRENT_TEST", "?").split(" ")[0].split("::", 1)[-1]
+        i = self._count.get(key, 0)
+        self._count[key] = i + 1
+        if not self._oracle_first:
+            a, b = b, a
+        if self._mode == "record":
+            self._table.setdefault(key, []).append(hashlib.sha256(self._np.ascontiguousarray(b).tobytes()).hexdigest())
+            return self._np.array_equal(a, b)
+        want = self._table.get(key, [])
+        assert i < len(want), "no golden vector %d for %s" % (i, key)
+        return hashlib.sha256(self._np.ascontiguousarray(a).tobytes()).hexdigest() == want[i]

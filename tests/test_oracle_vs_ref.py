@@ -7,13 +7,23 @@ define mad() as fmaf and round after every other operation).  The module is skip
 reference build is not available (it travels to the GPU box as a prebuilt .so).
 """
 import ctypes
+import os
 
 import numpy as np
 import pytest
 
-from _libs import Image, P, make_segment_data, oracle, ref, ref_run
+from _libs import GoldenNumpy, Image, P, make_segment_data, oracle, ref, ref_run
 
-pytestmark = pytest.mark.skipif(ref() is None, reason="oracle/_ref not built (needs /root/reference)")
+# VP8_GOLDEN=record:<file> stores the sha256 of every reference output (tests/golden/make_golden.py);
+# VP8_GOLDEN=check:<file> runs the oracle half alone against those vectors (tests/test_oracle_vs_golden.py)
+GOLDEN = os.environ.get("VP8_GOLDEN", "")
+if GOLDEN:
+    np = GoldenNumpy(np, GOLDEN)
+if GOLDEN.startswith("check:"):
+    def ref_run(*args, **kwargs):  # noqa: F811  (the reference is not needed: its outputs are the golden vectors)
+        return None
+
+pytestmark = pytest.mark.skipif(ref() is None and not GOLDEN.startswith("check:"), reason="oracle/_ref not built (needs /root/reference)")
 
 
 def rng(seed):
@@ -29,6 +39,7 @@ def textured(r, h, w, smooth=4):
 
 
 # ------------------------------------------------------------------------------------------
+@pytest.mark.skipif(GOLDEN.startswith("check:"), reason="compares scalars with the reference directly")
 def test_weight_matches_reference_and_keeps_the_clobber_bug():
     o, rf = oracle(), ref()
     r = rng(1)
