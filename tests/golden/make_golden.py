@@ -26,4 +26,29 @@ env.pop("VP8_NO_REF", None)
 rc2 = subprocess.call([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_intra_oracle.py"), "-q", "-x", "-p", "no:cacheprovider"],
                       cwd=ROOT, env=env)
 print("wrote", out2 if rc2 == 0 else "NOTHING USABLE (tests failed)")
+
+# whole encodes: md5 of the .ivf the reference encoder (its host + its kernels on the CPU) writes for the cases of
+# tests/test_gpu_e2e.py and the first frames of the 1080p / 2160p BASELINE configurations
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import hashlib  # noqa: E402
+import json  # noqa: E402
+import tempfile  # noqa: E402
+import gen_y4m  # noqa: E402
+import _trace  # noqa: E402
+from golden_cases import IVF_CASES  # noqa: E402
+table = {}
+tmp = tempfile.mkdtemp(prefix="golden_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+for name, (w, h, frames, args) in IVF_CASES.items():
+    y4m = os.path.join(tmp, name + ".y4m")
+    gen_y4m.write_y4m(y4m, w, h, frames)
+    ivf = os.path.join(tmp, name + ".ivf")
+    _trace.run_host(_trace.REF_DIR, os.path.join(tmp, name + ".run"), y4m, ivf, args, env_extra={"OMP_NUM_THREADS": str(os.cpu_count() or 1)})
+    b = open(ivf, "rb").read()
+    table[name] = {"md5": hashlib.md5(b).hexdigest(), "bytes": len(b), "frames": frames}
+    os.remove(y4m)
+    print(name, table[name])
+out3 = os.path.join(HERE, "reference_ivf.json")
+json.dump(table, open(out3, "w"), indent=1, sort_keys=True)
+print("wrote", out3)
 sys.exit(rc or rc2)

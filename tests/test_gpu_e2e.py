@@ -29,6 +29,26 @@ CASES = {
 }
 
 
+@pytest.mark.parametrize("case", ["qcif", "cif", "cif_ssim", "odd", "cif_60_baseline", "1080p_12", "2160p_6"])
+def test_ivf_matches_the_committed_reference_md5(case, tmp_path):
+    """the shim's output against GOLDEN md5s of the reference encoder's files (tests/golden/reference_ivf.json, made on
+    the CPU by tests/golden/make_golden.py): no reference run at test time"""
+    import hashlib
+    import json
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_y4m
+    from golden_cases import IVF_CASES
+    want = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_ivf.json")))[case]
+    w, h, frames, args = IVF_CASES[case]
+    d = str(tmp_path)
+    y4m = os.path.join(d, "clip.y4m")
+    gen_y4m.write_y4m(y4m, w, h, frames)
+    _trace.run_host(SHIM_DIR, d, y4m, os.path.join(d, "b200.ivf"), args, env_extra={"VP8B200_HOST_PROFILE": "reference"})
+    b = open(os.path.join(d, "b200.ivf"), "rb").read()
+    assert (len(b), hashlib.md5(b).hexdigest()) == (want["bytes"], want["md5"]), case
+
+
 def first_divergence(tr_a, tr_b):
     fa, _ = _trace.split_frames(_trace.read_trace(tr_a))
     fb, _ = _trace.split_frames(_trace.read_trace(tr_b))
